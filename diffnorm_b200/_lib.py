@@ -1,0 +1,92 @@
+"""ctypes binding of libdiffnorm_b200.so (the C ABI declared in include/diffnorm_b200.h).
+
+There is NO fallback: if the shared library is missing the import fails loudly with build instructions, and every
+wrapper raises on a non-zero status.  The library is built in-tree by ``__graft_entry__.build()`` /
+``make -C diffnorm_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdiffnorm_b200.so")
+
+
+class DiffNormLibraryError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise DiffNormLibraryError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU / torch fallback exists). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or `make -C diffnorm_b200/csrc`.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class GemmSeg(C.Structure):
+    _fields_ = [("a_col0", i32), ("shift_mul", i32), ("k_blocks", i32), ("w_k0", i32), ("n_mma", i32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("T", i32), ("groups", i32),
+        ("A", vp), ("lda", i32), ("a_cols", i32), ("a_batch_stride", i64), ("g_a_col", i32),
+        ("W", vp), ("ldw", i32), ("w_rows", i32), ("g_w_row", i32),
+        ("num_segs", i32), ("seg", GemmSeg * 4),
+        ("dilation", i32), ("dilation_shl_group", i32), ("n_tiles", i32), ("n_out", i32), ("epi", i32),
+        ("bias", vp), ("bias2", vp), ("g_bias", i32),
+        ("gb", vp), ("gb_t_stride", i64), ("g_gb", i32), ("gb_half", i32), ("t_idx", vp), ("t_idx_stride", i32),
+        ("out", vp), ("ldo", i32), ("out_batch_stride", i64), ("g_out_col", i32),
+        ("pe", vp), ("lengths", vp),
+    ]
+
+
+EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_WN_GATE = range(5)
+GEMM_TCGEN05, GEMM_SIMT_CHECK = 0, 1
+
+# name -> argtypes ; every function returns int status except the two info calls
+_SIGS = {
+    "dn_reduce_tgt": [vp, vp, i32, i32, vp, vp, vp, vp, vp],
+    "dn_argmax_units": [vp, i32, i64, i32, i32, i32, vp, vp],
+    "dn_unit_accuracy": [vp, vp, vp, i32, i32, vp, vp],
+    "dn_gather_pack": [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp],
+    "dn_cast_pad_bf16": [vp, i64, i32, i32, vp, i32, vp],
+    "dn_vae_reparam": [vp, i32, vp, i32, i32, i32, i32, vp, vp],
+    "dn_q_sample": [vp, vp, f32, f32, i64, i32, vp, vp, i32, vp],
+    "dn_ddim_step": [vp, vp, i32, vp, vp, i64, i32, i32, vp, i32, vp],
+    "dn_ddpm_step": [vp, vp, i32, vp, vp, vp, i64, i32, vp, i32, vp],
+    "dn_advance_step": [vp, i32, vp],
+    "dn_adarmsnorm": [vp, vp, i32, i32, i32, vp, vp, i64, vp, i32, vp],
+    "dn_wavenet_gate": [vp, vp, vp, i32, i32, i32, vp, i64, vp, i32, vp],
+    "dn_linear_f32": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "dn_time_features": [vp, vp, i32, i32, vp, vp],
+    "dn_gemm": [C.POINTER(GemmDesc), i32, vp],
+    "dn_attention": [vp, vp, vp, i32, i32, i32, i32, vp],
+}
+EXPORTS = sorted(list(_SIGS) + ["dn_abi_version", "dn_launch_count"])
+
+for _name, _args in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = C.c_int
+lib.dn_abi_version.restype = C.c_int
+lib.dn_abi_version.argtypes = []
+lib.dn_launch_count.restype = C.c_ulonglong
+lib.dn_launch_count.argtypes = []
+
+
+def check(status: int, what: str):
+    if status != 0:
+        kind = "argument error" if status < 0 else "cudaError"
+        raise DiffNormLibraryError(f"{what} failed: {kind} {status}")
+
+
+def launch_count() -> int:
+    return int(lib.dn_launch_count())

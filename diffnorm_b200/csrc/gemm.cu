@@ -1,0 +1,459 @@
+// dn_gemm: bf16 x bf16 -> fp32 GEMM / implicit causal dilated convolution on tcgen05 tensor cores.
+//
+// Replaces every nn.Linear / CausalConv1d on the reference path (LM:476-488, :509-511, :887-903, :930-932;
+// SURVEY §2.3 G1-G8).  One persistent, warp-specialised kernel:
+//   warp 0      TMA producer   A tile  = box {64 ch, 128 frames, 1 utt} of a 3-D map [C, T, B]; a conv tap is the
+//                              same box shifted by -shift frames, TMA zero-fills t < 0 (= causal left padding)
+//                              W tile  = box {64, 256 | 128} of the packed K-major weight matrix
+//   warp 1      MMA issuer     tcgen05.mma cta_group::1 kind::f16, M = 128, N <= 256, K = 16 per instruction,
+//                              fp32 accumulators in TMEM (2 x 256 columns, double buffered against the epilogue)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue       tcgen05.ld 32x32b (one accumulator row per thread) -> fused epilogue -> global
+// Epilogues: +bias -> bf16 | fp32 (+ sinusoidal positions) | in-place fp32 residual add | GEGLU | WaveNet
+// FiLM + tanh*sigmoid gate + residual branch (second accumulator half).
+#include "common.cuh"
+
+namespace dn {
+
+unsigned long long g_launch_count = 0;
+
+constexpr int BM = 128;         // frames per tile (UMMA M)
+constexpr int BK = 64;          // bf16 per K block = one 128-byte swizzle atom
+constexpr int WT = 256;         // packed weight rows per N tile (max UMMA N)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = WT * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int ACC_COLS = 256;   // TMEM columns per accumulator stage
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TileCoord {
+    int g, b, t0, n;
+};
+__device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile, int tiles_t) {
+    TileCoord c;
+    c.n = tile % p.n_tiles;
+    int r = tile / p.n_tiles;
+    int m_tiles = p.B * tiles_t;
+    int m = r % m_tiles;
+    c.g = r / m_tiles;
+    c.b = m / tiles_t;
+    c.t0 = (m % tiles_t) * BM;
+    return c;
+}
+
+__device__ __forceinline__ const float* gb_row(const dn_gemm_desc& p, int b, int g) {
+    if (!p.gb) return nullptr;
+    int t = p.t_idx ? p.t_idx[(long long)b * p.t_idx_stride] : 0;
+    return p.gb + (long long)t * p.gb_t_stride + (long long)g * p.g_gb;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmW128, const dn_gemm_desc p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_t = (p.T + BM - 1) / BM;
+    const int total = p.groups * p.B * tiles_t * p.n_tiles;
+    const int rows_pg = p.groups > 1 ? p.g_w_row : p.w_rows;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmW128);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                TileCoord c = decode_tile(p, tile, tiles_t);
+                const int d = p.dilation << (p.dilation_shl_group ? c.g : 0);
+                for (int s = 0; s < p.num_segs; ++s) {
+                    const dn_gemm_seg sg = p.seg[s];
+                    const bool half_w = sg.n_mma == 128;
+                    for (int kb = 0; kb < sg.k_blocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * STAGE_BYTES;
+                        uint8_t* sb = sa + A_BYTES;
+                        mbar_expect_tx(&full[stage], A_BYTES + (half_w ? B_BYTES / 2 : B_BYTES));
+                        tma_load_3d(&tmA, &full[stage], sa, sg.a_col0 + c.g * p.g_a_col + kb * BK,
+                                    c.t0 - sg.shift_mul * d, c.b);
+                        tma_load_2d(half_w ? &tmW128 : &tmW, &full[stage], sb, sg.w_k0 + kb * BK,
+                                    c.g * p.g_w_row + c.n * WT);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- MMA issuer (one thread)
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                TileCoord c = decode_tile(p, tile, tiles_t);
+                int n_full = rows_pg - c.n * WT;
+                n_full = n_full > WT ? WT : n_full;
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+                uint32_t acc = 0;
+                for (int s = 0; s < p.num_segs; ++s) {
+                    const dn_gemm_seg sg = p.seg[s];
+                    const uint32_t idesc = umma_idesc_bf16_m128(sg.n_mma ? sg.n_mma : n_full);
+                    for (int kb = 0; kb < sg.k_blocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t da = umma_desc_sw128(sa);
+                        const uint64_t db = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+                            acc = 1;
+                        }
+                        umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // -------------------------------------------------------------------- epilogue (8 warps)
+        const int q = warp & 3;            // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;  // which half of the column chunks
+        const int row = q * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            TileCoord c = decode_tile(p, tile, tiles_t);
+            const int t = c.t0 + row;
+            const bool valid = t < p.T;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            const long long orow = (long long)c.b * p.out_batch_stride + (long long)t * p.ldo + c.g * p.g_out_col;
+
+            if constexpr (EPI == DN_EPI_BF16 || EPI == DN_EPI_F32 || EPI == DN_EPI_RESID) {
+                const float* bias = p.bias ? p.bias + c.g * p.g_bias : nullptr;
+                long long pe_row = -1;
+                if (EPI == DN_EPI_F32 && p.pe) {
+                    int pos = t + 1;
+                    if (p.lengths && t >= p.lengths[c.b]) pos = 0;
+                    pe_row = (long long)pos * p.n_out;
+                }
+                for (int ch = half; ch < WT / 32; ch += 2) {
+                    const int col = c.n * WT + ch * 32;
+                    if (col >= p.n_out) break;
+                    float v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int cj = col + j * 8;
+                            if (cj + 8 > p.n_out) break;
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i] + (bias ? __ldg(bias + cj + i) : 0.f);
+                            if constexpr (EPI == DN_EPI_BF16) {
+                                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + cj;
+                                uint4 w = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                     pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                                *reinterpret_cast<uint4*>(op) = w;
+                            } else {
+                                float* op = reinterpret_cast<float*>(p.out) + orow + cj;
+                                if constexpr (EPI == DN_EPI_RESID) {
+                                    float4 r0 = *reinterpret_cast<float4*>(op);
+                                    float4 r1 = *reinterpret_cast<float4*>(op + 4);
+                                    o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
+                                    o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+                                } else if (pe_row >= 0) {
+                                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.pe + pe_row + cj));
+                                    const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.pe + pe_row + cj + 4));
+                                    o[0] += e0.x; o[1] += e0.y; o[2] += e0.z; o[3] += e0.w;
+                                    o[4] += e1.x; o[5] += e1.y; o[6] += e1.z; o[7] += e1.w;
+                                }
+                                *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+                                *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // GEGLU / WN_GATE: two 128-column accumulator halves -> 128 output columns per tile
+                const float* gbr = (EPI == DN_EPI_WN_GATE) ? gb_row(p, c.b, c.g) : nullptr;
+                for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
+                    const int col = c.n * 128 + ch * 32;  // logical output column
+                    if (col >= p.n_out) break;
+                    float lo[32], hi[32];
+                    tmem_ld32(taddr + ch * 32, lo);
+                    tmem_ld32(taddr + 128 + ch * 32, hi);
+                    tmem_ld_wait();
+                    if (valid) {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + col;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (col + j * 8 + 8 > p.n_out) break;
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int k = j * 8 + i;
+                                if constexpr (EPI == DN_EPI_GEGLU) {
+                                    const int wr = c.g * p.g_bias + c.n * WT + ch * 32 + k;  // packed W row
+                                    const float x = lo[k] + (p.bias ? __ldg(p.bias + wr) : 0.f);
+                                    const float gt = hi[k] + (p.bias ? __ldg(p.bias + wr + 128) : 0.f);
+                                    o[i] = gelu_erf(gt) * x;
+                                } else {
+                                    const int oc = col + k;
+                                    float u = lo[k] + (p.bias ? __ldg(p.bias + c.g * p.g_bias + oc) : 0.f);
+                                    const float r = hi[k] + (p.bias2 ? __ldg(p.bias2 + c.g * p.g_bias + oc) : 0.f);
+                                    if (gbr) u = u * __ldg(gbr + oc) + __ldg(gbr + p.gb_half + oc);
+                                    o[i] = wn_gate(u) + r;
+                                }
+                            }
+                            uint4 w = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                                 pack_bf16(o[6], o[7]));
+                            *reinterpret_cast<uint4*>(op + j * 8) = w;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// SIMT checker: one thread per output element, identical semantics, used only by tests / bring-up.
+// ------------------------------------------------------------------------------------------------------
+__global__ void gemm_check_kernel(const dn_gemm_desc p) {
+    const long long total = (long long)p.groups * p.B * p.T * p.n_out;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int oc = (int)(idx % p.n_out);
+        long long r = idx / p.n_out;
+        const int t = (int)(r % p.T);
+        r /= p.T;
+        const int b = (int)(r % p.B);
+        const int g = (int)(r / p.B);
+        const int d = p.dilation << (p.dilation_shl_group ? g : 0);
+        const bool dual = p.epi == DN_EPI_GEGLU || p.epi == DN_EPI_WN_GATE;
+        const int wrow_lo = g * p.g_w_row + (dual ? (oc / 128) * WT + (oc % 128) : oc);
+        const int wrow_hi = wrow_lo + 128;
+        const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(p.A);
+        const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(p.W);
+        float lo = 0.f, hi = 0.f;
+        for (int s = 0; s < p.num_segs; ++s) {
+            const dn_gemm_seg sg = p.seg[s];
+            const int ts = t - sg.shift_mul * d;
+            if (ts < 0) continue;
+            const __nv_bfloat16* a = A + (long long)b * p.a_batch_stride + (long long)ts * p.lda + sg.a_col0 + g * p.g_a_col;
+            const __nv_bfloat16* wl = W + (long long)wrow_lo * p.ldw + sg.w_k0;
+            const __nv_bfloat16* wh = W + (long long)wrow_hi * p.ldw + sg.w_k0;
+            const int klen = sg.k_blocks * BK;
+            for (int k = 0; k < klen; ++k) {
+                // columns past the tensor extent read as zero (TMA out-of-bounds fill)
+                const float av = (sg.a_col0 + g * p.g_a_col + k < p.a_cols) ? __bfloat162float(a[k]) : 0.f;
+                lo += av * __bfloat162float(wl[k]);
+                if (dual && sg.n_mma == 0) hi += av * __bfloat162float(wh[k]);
+            }
+        }
+        const long long o = (long long)b * p.out_batch_stride + (long long)t * p.ldo + g * p.g_out_col + oc;
+        if (p.epi == DN_EPI_BF16) {
+            reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f));
+        } else if (p.epi == DN_EPI_F32) {
+            float v = lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f);
+            if (p.pe) {
+                int pos = t + 1;
+                if (p.lengths && t >= p.lengths[b]) pos = 0;
+                v += p.pe[(long long)pos * p.n_out + oc];
+            }
+            reinterpret_cast<float*>(p.out)[o] = v;
+        } else if (p.epi == DN_EPI_RESID) {
+            reinterpret_cast<float*>(p.out)[o] += lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f);
+        } else if (p.epi == DN_EPI_GEGLU) {
+            const int wr = g * p.g_bias + (oc / 128) * WT + (oc % 128);
+            const float x = lo + (p.bias ? p.bias[wr] : 0.f);
+            const float gt = hi + (p.bias ? p.bias[wr + 128] : 0.f);
+            reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(gelu_erf(gt) * x);
+        } else {
+            float u = lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f);
+            const float rr = hi + (p.bias2 ? p.bias2[g * p.g_bias + oc] : 0.f);
+            const float* gbr = gb_row(p, b, g);
+            if (gbr) u = u * gbr[oc] + gbr[p.gb_half + oc];
+            reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(tanhf(u) / (1.f + expf(-u)) + rr);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+static int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                           const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return DN_EDRIVER;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : DN_EINVAL;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int EPI>
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& w128, const dn_gemm_desc& d,
+                     int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        DN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        attr_set = true;
+    }
+    gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, w, w128, d);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
+    if (!dp || !dp->A || !dp->W || !dp->out) return DN_EINVAL;
+    const dn_gemm_desc& d = *dp;
+    if (d.B <= 0 || d.T <= 0 || d.groups <= 0 || d.num_segs <= 0 || d.num_segs > 4 || d.n_tiles <= 0) return DN_EINVAL;
+    if (d.n_out % 8 || d.lda % 8 || d.ldw % 8 || d.w_rows % 16) return DN_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(d.A) | reinterpret_cast<uintptr_t>(d.W) | reinterpret_cast<uintptr_t>(d.out)) & 15)
+        return DN_EINVAL;
+    const bool f32out = d.epi == DN_EPI_F32 || d.epi == DN_EPI_RESID;
+    if (d.ldo % (f32out ? 4 : 8) || d.g_out_col % 8) return DN_EINVAL;
+    for (int s = 0; s < d.num_segs; ++s)
+        if (d.seg[s].k_blocks <= 0 || (d.seg[s].n_mma != 0 && d.seg[s].n_mma != 128) || d.seg[s].a_col0 % 8 ||
+            d.seg[s].w_k0 % 8)
+            return DN_EINVAL;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    if (impl == DN_GEMM_SIMT_CHECK) {
+        const long long total = (long long)d.groups * d.B * d.T * d.n_out;
+        int grid = (int)((total + 255) / 256 > 148 * 64 ? 148 * 64 : (total + 255) / 256);
+        gemm_check_kernel<<<grid, 256, 0, st>>>(d);
+        DN_LAUNCH_CHECK();
+        count_launch();
+        return 0;
+    }
+
+    CUtensorMap ma, mw, mw128;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)d.a_cols, (cuuint64_t)d.T, (cuuint64_t)d.B};
+        cuuint64_t str[2] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.a_batch_stride * 2};
+        cuuint32_t box[3] = {BK, BM, 1};
+        int r = encode_bf16_map(&ma, d.A, 3, dims, str, box);
+        if (r) return r;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)d.ldw, (cuuint64_t)d.w_rows};
+        cuuint64_t str[1] = {(cuuint64_t)d.ldw * 2};
+        cuuint32_t box[2] = {BK, WT};
+        int r = encode_bf16_map(&mw, d.W, 2, dims, str, box);
+        if (r) return r;
+        cuuint32_t box2[2] = {BK, 128};
+        r = encode_bf16_map(&mw128, d.W, 2, dims, str, box2);
+        if (r) return r;
+    }
+    const int tiles_t = (d.T + BM - 1) / BM;
+    const long long total = (long long)d.groups * d.B * tiles_t * d.n_tiles;
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    switch (d.epi) {
+        case DN_EPI_BF16: return launch_tc<DN_EPI_BF16>(ma, mw, mw128, d, grid, st);
+        case DN_EPI_F32: return launch_tc<DN_EPI_F32>(ma, mw, mw128, d, grid, st);
+        case DN_EPI_RESID: return launch_tc<DN_EPI_RESID>(ma, mw, mw128, d, grid, st);
+        case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU>(ma, mw, mw128, d, grid, st);
+        case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE>(ma, mw, mw128, d, grid, st);
+        default: return DN_EINVAL;
+    }
+}
+
+extern "C" int dn_abi_version(void) { return 1; }
+extern "C" unsigned long long dn_launch_count(void) { return dn::g_launch_count; }

@@ -1,0 +1,413 @@
+"""Host-side engine of the normalization pass: packs a reference ``state_dict`` once, owns the HBM workspace, and
+drives the sm_100a kernels (through the C ABI) for VAE encode -> q_sample -> denoiser loop -> VAE decode ->
+argmax -> run-length reduce.  torch is used only for memory, streams and CUDA-graph capture.
+
+Data layout in HBM: every activation is row-major [B, T, C] (frames x channels, C padded to the GEMM granules),
+bf16 for GEMM operands, fp32 for the transformer residual stream, the latent state and logits.  There are no
+transposes anywhere (the reference flips between [B,C,T] and [B,T,C] around every conv, LM:863-866, :892-896).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .config import UNIT_OFFSET, DiffNormConfig
+from .packing import (pack_conv3, pack_geglu, pack_linear, pack_skip_sum, pack_wavenet_level, rup)
+from .schedule import DDPMScheduler
+
+bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
+
+
+class _Wavenet:
+    """Packed WavenetEncoder / Wavenet (LM:585-617, :1003-1032)."""
+
+    def __init__(self, sd, pre: str, stacks: int, layers: int, cin_pad: int, final_epi: int, final_n_pad: int,
+                 cond: bool):
+        w = sd[pre + "init_conv.weight"]
+        self.c = w.shape[0]
+        self.c_pad = rup(self.c, 128)
+        self.G, self.stacks, self.cond = layers, stacks, cond
+        self.init = pack_conv3(w, sd[pre + "init_conv.bias"], cin_pad=cin_pad, n_pad=self.c_pad, name=pre + "init_conv")
+        self.levels = []
+        for s in range(stacks):
+            blk = [f"{pre}stacks.{s}.blocks.{i}." for i in range(layers)]
+            self.levels.append(pack_wavenet_level(
+                [sd[b + "conv.weight"] for b in blk], [sd[b + "conv.bias"] for b in blk],
+                [sd[b + "res_conv.weight"] for b in blk], [sd[b + "res_conv.bias"] for b in blk], self.c_pad,
+                name=f"{pre}stacks.{s}"))
+        last = [f"{pre}stacks.{stacks - 1}.blocks.{i}." for i in range(layers)]
+        self.skip = pack_skip_sum([sd[b + "skip_conv.weight"] for b in last], [sd[b + "skip_conv.bias"] for b in last],
+                                  self.c_pad, name=pre + "skip_sum")
+        self.final = pack_linear(sd[pre + "final_conv.weight"], sd[pre + "final_conv.bias"], epi=final_epi,
+                                 k_pad=self.c_pad, n_pad=final_n_pad, name=pre + "final_conv")
+
+    def plans(self):
+        return [self.init, *self.levels, self.skip, self.final]
+
+
+class _TfLayer:
+    pass
+
+
+class DiffNormEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: str = "cuda", cfg: Optional[DiffNormConfig] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DiffNormEngine needs a CUDA device: the product has no CPU path")
+        sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
+        self.cfg = cfg or DiffNormConfig.from_state_dict(sd)
+        self.dev = torch.device(device)
+        self.ws: Dict[tuple, torch.Tensor] = {}
+        self.gemm_impl = _lib.GEMM_TCGEN05
+        self._graphs: Dict[tuple, object] = {}
+        c = self.cfg
+        self.zp = rup(c.latent_dim, 64)        # latent staging width (K of the first GEMMs)
+        self.zn = rup(c.latent_dim, 16)        # eps_hat row width
+        self.vp = rup(c.vocab, 16)             # logits row width
+        self._pack_denoiser(sd)
+        self._pack_vae(sd)
+        self._build_time_table(sd)
+        self.sched = DDPMScheduler(c.timesteps)
+        self.ddim_rows = torch.from_numpy(self.sched.ddim_rows()).to(self.dev)
+        self._pe_cache: Dict[int, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _dev(self, plan):
+        return plan.to(self.dev)
+
+    def _pack_tf(self, sd, pre: str, dim: int, depth: int, cond: bool):
+        layers = []
+        ip = rup(DiffNormConfig.ff_inner(dim), 128)
+        for l in range(depth):
+            p = f"{pre}layers.{l}."
+            L = _TfLayer()
+            L.qkv = self._dev(pack_linear(torch.cat([sd[p + "1.to_q.weight"], sd[p + "1.to_kv.weight"]], 0), None,
+                                          name=p + "qkv"))
+            L.out = self._dev(pack_linear(sd[p + "1.to_out.weight"], None, epi=_lib.EPI_RESID, name=p + "to_out"))
+            L.ff1 = self._dev(pack_geglu(sd[p + "5.0.weight"], sd[p + "5.0.bias"], name=p + "ff.geglu"))
+            L.ffc = self._dev(pack_conv3(sd[p + "5.2.1.weight"], sd[p + "5.2.1.bias"], cin_pad=ip, n_pad=ip,
+                                         name=p + "ff.conv"))
+            L.ff3 = self._dev(pack_linear(sd[p + "5.3.weight"], sd[p + "5.3.bias"], epi=_lib.EPI_RESID, k_pad=ip,
+                                          name=p + "ff.out"))
+            if not cond:
+                L.g1 = sd[p + "0.gamma"].float().to(self.dev)
+                L.g2 = sd[p + "4.gamma"].float().to(self.dev)
+            layers.append(L)
+        return layers, ip
+
+    def _pack_denoiser(self, sd):
+        c = self.cfg
+        self.d_init = self._dev(pack_linear(sd["model.init_conv.weight"], sd["model.init_conv.bias"], k_pad=self.zp,
+                                            name="model.init_conv"))
+        self.d_wn = _Wavenet(sd, "model.wavenet.", c.wn_stacks, c.wn_layers, cin_pad=c.hid, final_epi=_lib.EPI_F32,
+                             final_n_pad=c.hid, cond=True)
+        for p in self.d_wn.plans():
+            self._dev(p)
+        self.d_layers, self.d_ip = self._pack_tf(sd, "model.transformer.", c.hid, c.depth, cond=True)
+        self.d_pred_gamma = sd["model.transformer.to_pred.0.gamma"].float().to(self.dev)
+        self.d_pred = self._dev(pack_linear(sd["model.transformer.to_pred.1.weight"], None, name="model.to_pred"))
+        self.d_proj = self._dev(pack_linear(sd["model.final_proj.weight"], sd["model.final_proj.bias"],
+                                            epi=_lib.EPI_F32, n_pad=self.zn, name="model.final_proj"))
+
+    def _pack_vae(self, sd):
+        c = self.cfg
+        pre = "speech_decoder."
+        self.enc: List[_Wavenet] = []
+        cin_pad = c.feat_dim
+        enc_w = c.enc_widths()
+        for i, (cin, cout) in enumerate(enc_w):
+            last = i == len(enc_w) - 1
+            cp = rup(cout, 128)
+            wn = _Wavenet(sd, f"{pre}encoder_wave.{i}.", c.vae_stacks, c.vae_layers, cin_pad=cin_pad,
+                          final_epi=_lib.EPI_F32 if last else _lib.EPI_BF16, final_n_pad=rup(cout, 16) if last else cp,
+                          cond=False)
+            for p in wn.plans():
+                self._dev(p)
+            self.enc.append(wn)
+            cin_pad = cp
+        self.dec: List[_Wavenet] = []
+        cin_pad = self.zp
+        dec_w = c.dec_widths()
+        for i, (cin, cout) in enumerate(dec_w):
+            last = i == len(dec_w) - 1
+            cp = rup(cout, 128)
+            wn = _Wavenet(sd, f"{pre}decoder_wave.{i}.", c.vae_stacks, c.vae_layers, cin_pad=cin_pad,
+                          final_epi=_lib.EPI_F32 if last else _lib.EPI_BF16, final_n_pad=cout if last else cp, cond=False)
+            for p in wn.plans():
+                self._dev(p)
+            self.dec.append(wn)
+            cin_pad = cp
+        self.v_layers, self.v_ip = self._pack_tf(sd, pre + "decoder_tf.", c.feat_dim, c.vae_depth, cond=False)
+        self.v_pred_gamma = sd[pre + "decoder_tf.to_pred.0.gamma"].float().to(self.dev)
+        self.v_pred = self._dev(pack_linear(sd[pre + "decoder_tf.to_pred.1.weight"], None, epi=_lib.EPI_F32,
+                                            name="vae.to_pred"))
+        self.v_lm = self._dev(pack_linear(sd[pre + "decoder_lm.weight"], sd[pre + "decoder_lm.bias"], epi=_lib.EPI_F32,
+                                          n_pad=self.vp, name="vae.decoder_lm"))
+
+    def _build_time_table(self, sd):
+        """gamma/beta of all 32 WaveNet FiLMs + 24 adaptive norms depend only on t (LM:507,:624,:741-745):
+        precompute table[t, layer, 2C] in fp32 with the library's own kernels."""
+        c = self.cfg
+        dev = self.dev
+        steps = torch.arange(c.timesteps, dtype=i32, device=dev)
+        feats = ops.time_features(steps, sd["model.to_time_cond.0.weights"].float().to(dev).contiguous())
+        t_emb = ops.linear_f32(feats, sd["model.to_time_cond.1.weight"].float().to(dev).contiguous(),
+                               sd["model.to_time_cond.1.bias"].float().to(dev).contiguous(), act=1)
+        names = [f"model.wavenet.stacks.{s}.blocks.{i}.to_time_cond" for s in range(c.wn_stacks)
+                 for i in range(c.wn_layers)]
+        for l in range(c.depth):
+            names += [f"model.transformer.layers.{l}.0.to_gamma_beta", f"model.transformer.layers.{l}.4.to_gamma_beta"]
+        W = torch.cat([sd[n + ".weight"].float() for n in names], 0).to(dev).contiguous()
+        b = torch.cat([sd[n + ".bias"].float() for n in names], 0).to(dev).contiguous()
+        self.n_cond = len(names)
+        self.gb_w = 2 * c.hid
+        self.time_table = ops.linear_f32(t_emb, W, b)          # [T, n_cond * 2C]
+        self.table_flat = self.time_table.view(-1)
+        self.gb_t_stride = self.n_cond * self.gb_w
+        self.t_emb = t_emb
+        del W, b
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------------------------------------ workspace
+    def buf(self, name: str, rows: int, width: int, dtype=bf16) -> torch.Tensor:
+        key = (name, rows, width, dtype)
+        t = self.ws.get(key)
+        if t is None:
+            t = torch.zeros(rows, width, dtype=dtype, device=self.dev)
+            self.ws[key] = t
+        return t
+
+    def pe_table(self, T: int) -> torch.Tensor:
+        """Sinusoidal table rows 0..T (row 0 = padding = zeros), sinusoidal_positional_embedding.py:36-58."""
+        t = self._pe_cache.get(T)
+        if t is None:
+            dim = self.cfg.hid
+            half = dim // 2
+            e = np.log(10000.0) / (half - 1)
+            freq = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+            ang = torch.arange(T + 1, dtype=torch.float)[:, None] * freq[None, :]
+            tab = torch.cat([ang.sin(), ang.cos()], dim=1)
+            tab[0] = 0
+            t = tab.to(self.dev).contiguous()
+            self._pe_cache[T] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------------ sub-networks
+    def _run(self, plan, A, out, B, T, **kw):
+        return plan.run(A, out, B, T, impl=self.gemm_impl, **kw)
+
+    def _wavenet(self, wn: _Wavenet, A, out, B, T, tag: str, gb_layer0: Optional[int] = None, t_idx=None,
+                 t_idx_stride=0, pe=None, lengths=None):
+        M = B * T
+        cp, G = wn.c_pad, wn.G
+        h = self.buf(tag + ".h", M, cp)
+        self._run(wn.init, A, h, B, T)
+        ys = [self.buf(tag + ".y0", M, G * cp), self.buf(tag + ".y1", M, G * cp)]
+        src, g_a_col = h, 0
+        for s, lvl in enumerate(wn.levels):
+            dst = ys[s & 1]
+            kw = {}
+            if gb_layer0 is not None:
+                kw = dict(gb=self.table_flat[(gb_layer0 + s * G) * self.gb_w:], gb_t_stride=self.gb_t_stride,
+                          g_gb=self.gb_w, gb_half=self.gb_w // 2, t_idx=t_idx, t_idx_stride=t_idx_stride)
+            self._run(lvl, src, dst, B, T, g_a_col=g_a_col, g_out_col=cp, **kw)
+            src, g_a_col = dst, cp
+        sk = self.buf(tag + ".s", M, cp)
+        self._run(wn.skip, src, sk, B, T)
+        self._run(wn.final, sk, out, B, T, pe=pe, lengths=lengths)
+        return out
+
+    def _transformer(self, layers, ip, x, B, T, dim, heads, dh, lengths, tag, cond_layer0=None, t_idx=None,
+                     t_idx_stride=0):
+        M = B * T
+        hb = self.buf(tag + ".h", M, dim)
+        qkv = self.buf(tag + ".qkv", M, 3 * heads * dh)
+        ao = self.buf(tag + ".ao", M, heads * dh)
+        m1 = self.buf(tag + ".m1", M, ip)
+        m2 = self.buf(tag + ".m2", M, ip)
+        for l, L in enumerate(layers):
+            for which in (0, 1):
+                if cond_layer0 is not None:
+                    gb = self.table_flat[(cond_layer0 + 2 * l + which) * self.gb_w:]
+                    ops.adarmsnorm(x, hb, B, T, None, gb, self.gb_t_stride, t_idx, t_idx_stride)
+                else:
+                    ops.adarmsnorm(x, hb, B, T, L.g1 if which == 0 else L.g2)
+                if which == 0:
+                    self._run(L.qkv, hb, qkv, B, T)
+                    ops.attention(qkv, ao, lengths, B, T, heads, dh)
+                    self._run(L.out, ao, x, B, T)
+                else:
+                    self._run(L.ff1, hb, m1, B, T)
+                    self._run(L.ffc, m1, m2, B, T)
+                    self._run(L.ff3, m2, x, B, T)
+        return x
+
+    def denoise(self, xb: torch.Tensor, lengths: torch.Tensor, B: int, T: int, t_idx: torch.Tensor,
+                t_idx_stride: int = 0) -> torch.Tensor:
+        """Model.forward (LM:828-876).  xb bf16 [B*T, zp] latent staging; returns eps_hat fp32 [B*T, zn]."""
+        c = self.cfg
+        M = B * T
+        h0 = self.buf("d.h0", M, c.hid)
+        self._run(self.d_init, xb, h0, B, T)
+        x = self.buf("d.x", M, c.hid, f32)
+        self._wavenet(self.d_wn, h0, x, B, T, "d.wn", gb_layer0=0, t_idx=t_idx, t_idx_stride=t_idx_stride,
+                      pe=self.pe_table(T), lengths=lengths)
+        self._transformer(self.d_layers, self.d_ip, x, B, T, c.hid, c.heads, c.dim_head, lengths, "d.tf",
+                          cond_layer0=c.wn_stacks * c.wn_layers, t_idx=t_idx, t_idx_stride=t_idx_stride)
+        hb = self.buf("d.tf.h", M, c.hid)
+        ops.adarmsnorm(x, hb, B, T, self.d_pred_gamma)
+        pb = self.buf("d.pred", M, c.hid)
+        self._run(self.d_pred, hb, pb, B, T)
+        eh = self.buf("d.eps", M, self.zn, f32)
+        self._run(self.d_proj, pb, eh, B, T)
+        return eh
+
+    def encode_params(self, feat: torch.Tensor) -> torch.Tensor:
+        """WaveNet encoder stack (LM:1100-1103): feat fp32 [B,T,768] -> posterior params fp32 [B,T,2z]."""
+        B, T, Cf = feat.shape
+        M = B * T
+        a = self.buf("e.in", M, Cf)
+        ops.cast_pad_bf16(feat.contiguous(), Cf, out=a)
+        for i, wn in enumerate(self.enc):
+            last = i == len(self.enc) - 1
+            out = self.buf("e.params", M, wn.final.n_out, f32) if last else self.buf(f"e.o{i}", M, wn.c_pad)
+            self._wavenet(wn, a, out, B, T, f"e.wn{i}")
+            a = out
+        return a.view(B, T, -1)
+
+    def encode(self, feat: torch.Tensor, eps: torch.Tensor, eps_channel_first: bool = True) -> torch.Tensor:
+        """encode_feature + transpose (LM:1099-1107, :1397): -> z fp32 [B,T,z]."""
+        params = self.encode_params(feat)
+        return ops.vae_reparam(params, eps.contiguous(), self.cfg.latent_dim, eps_channel_first)
+
+    def decode(self, xb: torch.Tensor, lengths: torch.Tensor, B: int, T: int):
+        """decode_feature (LM:1109-1116): latent staging bf16 [B*T, zp] -> (recon fp32 [B,T,768], logits fp32 [B,T,vp])."""
+        c = self.cfg
+        M = B * T
+        a = xb
+        x = self.buf("v.x", M, c.feat_dim, f32)
+        for i, wn in enumerate(self.dec):
+            last = i == len(self.dec) - 1
+            out = x if last else self.buf(f"v.o{i}", M, wn.c_pad)
+            self._wavenet(wn, a, out, B, T, f"v.wn{i}")
+            a = out
+        self._transformer(self.v_layers, self.v_ip, x, B, T, c.feat_dim, c.vae_heads, c.vae_dim_head, lengths, "v.tf")
+        hb = self.buf("v.tf.h", M, c.feat_dim)
+        ops.adarmsnorm(x, hb, B, T, self.v_pred_gamma)
+        recon = self.buf("v.recon", M, c.feat_dim, f32)
+        self._run(self.v_pred, hb, recon, B, T)
+        rb = self.buf("v.recon_bf16", M, c.feat_dim)
+        ops.cast_pad_bf16(recon, c.feat_dim, out=rb)
+        logits = self.buf("v.logits", M, self.vp, f32)
+        self._run(self.v_lm, rb, logits, B, T)
+        return recon.view(B, T, -1), logits.view(B, T, -1)
+
+    # ------------------------------------------------------------------------------------------------ the pass
+    def _ddim_step(self, B, T):
+        M, z = B * T, self.cfg.latent_dim
+        x, xb = self.buf("s.x", M, z, f32), self.buf("s.xb", M, self.zp)
+        t_idx, lens = self.buf("s.t", 1, 1, i32).view(-1), self.buf("s.len", B, 1, i32).view(-1)
+        eh = self.denoise(xb, lens, B, T, t_idx)
+        ops.ddim_step(x, eh, self.ddim_rows, t_idx, 0, xb)
+        ops.advance_step(t_idx, -1)
+
+    def _ddim_graph(self, B, T):
+        """One sampler step (denoiser call + DDIM update + device-side t -= 1) captured as a CUDA graph; the step
+        index lives in device memory so the same graph serves every step."""
+        key = ("ddim", B, T)
+        g = self._graphs.get(key)
+        if g is None:
+            t_idx, lens = self.buf("s.t", 1, 1, i32).view(-1), self.buf("s.len", B, 1, i32).view(-1)
+            t_idx.fill_(1)
+            lens.fill_(T)
+            self._ddim_step(B, T)  # warm-up outside capture: function attributes, workspace allocation
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._ddim_step(B, T)
+            self._graphs[key] = g
+        return g
+
+    @torch.no_grad()
+    def normalize(self, feat: torch.Tensor, lengths: torch.Tensor, start_step: int, eps_vae: Optional[torch.Tensor] = None,
+                  eps_q: Optional[torch.Tensor] = None, ref_units: Optional[torch.Tensor] = None, sampler: str = "ddim",
+                  step_noise: Optional[Sequence[torch.Tensor]] = None, timesteps: Optional[Sequence[int]] = None,
+                  large_var: bool = False, use_graph: bool = True, collect: bool = False, reduce: bool = True):
+        """The whole pass on resident inputs (ddim_sample, LM:1386-1471, + the driver's reduce,
+        diff_norm_synthesis.py:211-216).  feat fp32 [B,T,768] cuda, lengths int32 [B] cuda."""
+        c = self.cfg
+        B, T, _ = feat.shape
+        M = B * T
+        z = c.latent_dim
+        if not (0 < start_step < c.timesteps):
+            raise ValueError(f"start_step must be in (0, {c.timesteps}) (LM:1405 indexes the schedule with it)")
+        if eps_vae is None:
+            eps_vae = torch.randn(B, z, T, device=self.dev, dtype=f32)
+        if eps_q is None:
+            eps_q = torch.randn(B, T, z, device=self.dev, dtype=f32)
+        graph = self._ddim_graph(B, T) if (use_graph and sampler == "ddim" and start_step > 2) else None
+        lens = self.buf("s.len", B, 1, i32).view(-1)
+        lens.copy_(lengths)
+        out = {}
+        zlat = self.encode(feat, eps_vae)
+        x = self.buf("s.x", M, z, f32)
+        xb = self.buf("s.xb", M, self.zp)
+        s = self.sched
+        ops.q_sample(zlat, eps_q.contiguous(), float(np.float32(s.sqrt_alphas_cumprod[start_step])),
+                     float(np.float32(s.sqrt_one_minus_alphas_cumprod[start_step])), x, xb)
+        if collect:
+            out["z"] = zlat.clone()
+            out["x_start"] = x.view(B, T, z).clone()
+        t_idx = self.buf("s.t", 1, 1, i32).view(-1)
+        calls = 0
+        if sampler == "ddim":
+            t_idx.fill_(start_step - 1)
+            n = start_step - 1  # t = start-1 .. 1 (LM:1402,1444)
+            if collect and n > 0:
+                out["eps_first"] = self.denoise(xb, lens, B, T, t_idx).view(B, T, -1)[..., :z].clone()
+            for _ in range(n):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self._ddim_step(B, T)
+            calls = n
+        elif sampler == "ddpm":
+            rows = torch.from_numpy(s.ddpm_rows(large_var)).to(self.dev)
+            t_idx.fill_(start_step - 1)
+            n = start_step - 1
+            for k in range(n):
+                eh = self.denoise(xb, lens, B, T, t_idx)
+                noise = step_noise[k] if step_noise is not None else torch.randn(B, T, z, device=self.dev, dtype=f32)
+                ops.ddpm_step(x, eh, noise.contiguous(), rows, t_idx, xb)
+                ops.advance_step(t_idx, -1)
+            calls = n
+        elif sampler == "ddim_strided":
+            sp, tmap = s.spaced(timesteps)
+            rows = torch.from_numpy(sp.ddim_rows()).to(self.dev)
+            r_idx = self.buf("s.r", 1, 1, i32).view(-1)
+            for i in range(len(tmap) - 1, 0, -1):
+                t_idx.fill_(tmap[i])          # the model sees the original step (respace.py:117-129)
+                r_idx.fill_(i)                # the update uses the respaced table row
+                eh = self.denoise(xb, lens, B, T, t_idx)
+                ops.ddim_step(x, eh, rows, r_idx, 1, xb)
+                calls += 1
+        else:
+            raise ValueError(f"unknown sampler {sampler!r}")
+        out["calls"] = calls
+        recon, logits = self.decode(xb, lens, B, T)  # xb mirrors x in bf16 (written by q_sample / step kernels)
+        units = ops.argmax_units(logits, c.vocab, UNIT_OFFSET)
+        out.update(x0=x.view(B, T, z), recon=recon, logits=logits, units=units)
+        if ref_units is not None:
+            out["acc"] = ops.unit_accuracy(units, ref_units.contiguous(), lens)
+        if reduce:
+            out["dedup"], out["duration"], out["index_to_keep"], out["counts"] = ops.reduce_tgt(units, lens)
+        return out
+
+    def stage_latent(self, latent: torch.Tensor) -> torch.Tensor:
+        """fp32 [B,T,z] latent -> bf16 staging buffer [B*T, zp] (for decode / denoise on caller-supplied latents)."""
+        B, T, z = latent.shape
+        xb = self.buf("s.xb", B * T, self.zp)
+        ops.cast_pad_bf16(latent.contiguous().view(B * T, z), self.zp, out=xb)
+        return xb

@@ -1,0 +1,220 @@
+"""Thin torch-tensor wrappers over the C ABI (include/diffnorm_b200.h).  torch is used for device memory and
+streams only; every op below launches hand-written sm_100a kernels from libdiffnorm_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, GemmSeg, check, lib
+
+bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ integer ops
+def reduce_tgt(units: torch.Tensor, lengths: torch.Tensor):
+    """Batched run-length reduction.  units [B,T] int64, lengths [B] int32 ->
+    (dedup [B,T], duration [B,T], index_to_keep [B,T], counts [B] int32); row b valid for j < counts[b]."""
+    _chk(units, i64, "units"), _chk(lengths, i32, "lengths")
+    B, T = units.shape
+    dedup = torch.empty_like(units)
+    dur = torch.empty_like(units)
+    keep = torch.empty_like(units)
+    counts = torch.empty(B, dtype=i32, device=units.device)
+    check(lib.dn_reduce_tgt(_p(units), _p(lengths), B, T, _p(dedup), _p(dur), _p(keep), _p(counts), _stream()),
+          "dn_reduce_tgt")
+    return dedup, dur, keep, counts
+
+
+def argmax_units(logits: torch.Tensor, n_classes: int, offset: int = 4, out: Optional[torch.Tensor] = None):
+    """logits [..., ld] fp32|bf16 (ld >= n_classes) -> units [...] int64 = argmax - offset."""
+    if logits.dtype not in (f32, bf16):
+        raise ValueError("logits must be fp32 or bf16")
+    _chk(logits, logits.dtype, "logits")
+    ld = logits.shape[-1]
+    rows = logits.numel() // ld
+    if out is None:
+        out = torch.empty(logits.shape[:-1], dtype=i64, device=logits.device)
+    check(lib.dn_argmax_units(_p(logits), int(logits.dtype == bf16), rows, n_classes, ld, offset, _p(out), _stream()),
+          "dn_argmax_units")
+    return out
+
+
+def unit_accuracy(units, ref_units, lengths):
+    _chk(units, i64, "units"), _chk(ref_units, i64, "ref_units"), _chk(lengths, i32, "lengths")
+    B, T = units.shape
+    out = torch.empty(2, dtype=i64, device=units.device)
+    check(lib.dn_unit_accuracy(_p(units), _p(ref_units), _p(lengths), B, T, _p(out), _stream()), "dn_unit_accuracy")
+    return out
+
+
+def gather_pack(src, src_row0, index_to_keep, counts, T: int, ldd: Optional[int] = None, dst_dtype=f32):
+    _chk(src, f32, "src"), _chk(src_row0, i64, "src_row0"), _chk(index_to_keep, i64, "index_to_keep")
+    _chk(counts, i32, "counts")
+    B = counts.shape[0]
+    Csrc = src.shape[-1]
+    ldd = Csrc if ldd is None else ldd
+    assert index_to_keep.shape == (B, T)
+    dst = torch.empty(B, T, ldd, dtype=dst_dtype, device=src.device)
+    check(lib.dn_gather_pack(_p(src), _p(src_row0), _p(index_to_keep), _p(counts), B, T, Csrc, _p(dst), ldd,
+                             int(dst_dtype == bf16), _stream()), "dn_gather_pack")
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def cast_pad_bf16(src: torch.Tensor, ldo: int, out: Optional[torch.Tensor] = None):
+    _chk(src, f32, "src")
+    Cc = src.shape[-1]
+    rows = src.numel() // Cc
+    if out is None:
+        out = torch.empty(*src.shape[:-1], ldo, dtype=bf16, device=src.device)
+    check(lib.dn_cast_pad_bf16(_p(src), rows, Cc, Cc, _p(out), ldo, _stream()), "dn_cast_pad_bf16")
+    return out
+
+
+def vae_reparam(params, eps, z: int, eps_channel_first: bool, out=None):
+    _chk(params, f32, "params"), _chk(eps, f32, "eps")
+    B, T, ldp = params.shape
+    if out is None:
+        out = torch.empty(B, T, z, dtype=f32, device=params.device)
+    check(lib.dn_vae_reparam(_p(params), ldp, _p(eps), int(eps_channel_first), B, T, z, _p(out), _stream()),
+          "dn_vae_reparam")
+    return out
+
+
+def q_sample(z_lat, eps, sqrt_ab: float, sqrt_1m_ab: float, x_out, x_bf16=None):
+    _chk(z_lat, f32, "z"), _chk(eps, f32, "eps"), _chk(x_out, f32, "x")
+    z = z_lat.shape[-1]
+    rows = z_lat.numel() // z
+    ldx = 0 if x_bf16 is None else x_bf16.shape[-1]
+    check(lib.dn_q_sample(_p(z_lat), _p(eps), sqrt_ab, sqrt_1m_ab, rows, z, _p(x_out), _p(x_bf16), ldx, _stream()),
+          "dn_q_sample")
+    return x_out
+
+
+def ddim_step(x, eps_hat, coef_table, t_idx, mode: int = 0, x_bf16=None):
+    _chk(x, f32, "x"), _chk(eps_hat, f32, "eps_hat"), _chk(coef_table, f32, "coef"), _chk(t_idx, i32, "t_idx")
+    z = x.shape[-1]
+    rows = x.numel() // z
+    ldx = 0 if x_bf16 is None else x_bf16.shape[-1]
+    check(lib.dn_ddim_step(_p(x), _p(eps_hat), eps_hat.shape[-1], _p(coef_table), _p(t_idx), rows, z, mode, _p(x_bf16),
+                           ldx, _stream()), "dn_ddim_step")
+    return x
+
+
+def ddpm_step(x, eps_hat, noise, coef_table, t_idx, x_bf16=None):
+    _chk(x, f32, "x"), _chk(eps_hat, f32, "eps_hat"), _chk(noise, f32, "noise"), _chk(coef_table, f32, "coef")
+    z = x.shape[-1]
+    rows = x.numel() // z
+    ldx = 0 if x_bf16 is None else x_bf16.shape[-1]
+    check(lib.dn_ddpm_step(_p(x), _p(eps_hat), eps_hat.shape[-1], _p(noise), _p(coef_table), _p(t_idx), rows, z,
+                           _p(x_bf16), ldx, _stream()), "dn_ddpm_step")
+    return x
+
+
+def advance_step(t_idx, delta: int):
+    check(lib.dn_advance_step(_p(t_idx), delta, _stream()), "dn_advance_step")
+
+
+def adarmsnorm(x, out, B: int, T: int, gamma_p=None, gb=None, gb_t_stride: int = 0, t_idx=None, t_idx_stride: int = 0):
+    _chk(x, f32, "x"), _chk(out, bf16, "out")
+    Cc = x.shape[-1]
+    check(lib.dn_adarmsnorm(_p(x), _p(out), B, T, Cc, _p(gamma_p), _p(gb), gb_t_stride, _p(t_idx), t_idx_stride,
+                            _stream()), "dn_adarmsnorm")
+    return out
+
+
+def wavenet_gate(u, res, y, B: int, T: int, gb=None, gb_t_stride: int = 0, t_idx=None, t_idx_stride: int = 0):
+    _chk(u, bf16, "u"), _chk(res, bf16, "res"), _chk(y, bf16, "y")
+    check(lib.dn_wavenet_gate(_p(u), _p(res), _p(y), B, T, u.shape[-1], _p(gb), gb_t_stride, _p(t_idx), t_idx_stride,
+                              _stream()), "dn_wavenet_gate")
+    return y
+
+
+def linear_f32(inp, W, bias=None, act: int = 0, out=None):
+    _chk(inp, f32, "in"), _chk(W, f32, "W")
+    M, K = inp.shape
+    N = W.shape[0]
+    assert W.shape[1] == K
+    if out is None:
+        out = torch.empty(M, N, dtype=f32, device=inp.device)
+    check(lib.dn_linear_f32(_p(inp), _p(W), _p(bias), _p(out), M, N, K, act, _stream()), "dn_linear_f32")
+    return out
+
+
+def time_features(steps, w):
+    _chk(steps, i32, "steps"), _chk(w, f32, "w")
+    M, half = steps.shape[0], w.shape[0]
+    out = torch.empty(M, 2 * half + 1, dtype=f32, device=w.device)
+    check(lib.dn_time_features(_p(steps), _p(w), M, half, _p(out), _stream()), "dn_time_features")
+    return out
+
+
+def attention(qkv, out, lengths, B: int, T: int, H: int, dh: int):
+    _chk(qkv, bf16, "qkv"), _chk(out, bf16, "out")
+    check(lib.dn_attention(_p(qkv), _p(out), _p(lengths), B, T, H, dh, _stream()), "dn_attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+class GemmPlan:
+    """A packed weight (bf16 [w_rows, ldw], 256 rows per N tile) + its K-segment program + epilogue vectors.
+    Built once per layer by diffnorm_b200.packing; `run` fills a dn_gemm_desc and calls dn_gemm."""
+
+    def __init__(self, W, segs: Sequence[Sequence[int]], n_out: int, n_tiles: int, epi: int, bias=None, bias2=None,
+                 groups: int = 1, g_w_row: int = 0, g_bias: int = 0, dilation: int = 1, dilation_shl_group: int = 0,
+                 name: str = ""):
+        self.W, self.segs, self.n_out, self.n_tiles, self.epi = W, [tuple(s) for s in segs], n_out, n_tiles, epi
+        self.bias, self.bias2, self.groups, self.g_w_row, self.g_bias = bias, bias2, groups, g_w_row, g_bias
+        self.dilation, self.dilation_shl_group, self.name = dilation, dilation_shl_group, name
+
+    def to(self, device):
+        self.W = self.W.to(device)
+        self.bias = None if self.bias is None else self.bias.to(device)
+        self.bias2 = None if self.bias2 is None else self.bias2.to(device)
+        return self
+
+    def run(self, A, out, B: int, T: int, *, g_a_col: int = 0, g_out_col: int = 0, gb=None, gb_t_stride: int = 0,
+            g_gb: int = 0, gb_half: int = 0, t_idx=None, t_idx_stride: int = 0, pe=None, lengths=None,
+            epi: Optional[int] = None, impl: int = _lib.GEMM_TCGEN05, a_cols: Optional[int] = None):
+        epi = self.epi if epi is None else epi
+        _chk(A, bf16, "A")
+        _chk(out, f32 if epi in (_lib.EPI_F32, _lib.EPI_RESID) else bf16, "out")
+        d = GemmDesc()
+        d.B, d.T, d.groups = B, T, self.groups
+        lda = A.shape[-1]
+        d.A, d.lda, d.a_cols, d.a_batch_stride, d.g_a_col = _p(A), lda, (lda if a_cols is None else a_cols), T * lda, g_a_col
+        d.W, d.ldw, d.w_rows, d.g_w_row = _p(self.W), self.W.shape[1], self.W.shape[0], self.g_w_row
+        d.num_segs = len(self.segs)
+        for i, s in enumerate(self.segs):
+            d.seg[i] = GemmSeg(*s)
+        d.dilation, d.dilation_shl_group = self.dilation, self.dilation_shl_group
+        d.n_tiles, d.n_out, d.epi = self.n_tiles, self.n_out, epi
+        d.bias, d.bias2, d.g_bias = _p(self.bias), _p(self.bias2), self.g_bias
+        d.gb, d.gb_t_stride, d.g_gb, d.gb_half = _p(gb), gb_t_stride, g_gb, gb_half
+        d.t_idx, d.t_idx_stride = _p(t_idx), t_idx_stride
+        ldo = out.shape[-1]
+        d.out, d.ldo, d.out_batch_stride, d.g_out_col = _p(out), ldo, T * ldo, g_out_col
+        d.pe, d.lengths = _p(pe), _p(lengths)
+        check(lib.dn_gemm(C.byref(d), impl, _stream()), f"dn_gemm[{self.name}]")
+        return out

@@ -1,0 +1,186 @@
+/* diffnorm_b200 — C ABI of the sm_100a kernels behind DiffNorm's latent-diffusion normalization pass.
+ *
+ * One shared library (diffnorm_b200/csrc/libdiffnorm_b200.so), loaded with ctypes by the Python host layer
+ * (diffnorm_b200/_lib.py).  Conventions for EVERY entry point:
+ *   - raw device pointers + plain integer sizes; no torch / C++ types cross the boundary;
+ *   - asynchronous w.r.t. the host: work is enqueued on `stream` (a cudaStream_t passed as void*), the caller
+ *     synchronises; no allocation, no ownership transfer, no global state (except a launch counter);
+ *   - returns 0 on success, a positive cudaError_t, or a negative DN_E* argument error;
+ *   - activations are row-major [B, T, C] ("frames x channels"), C contiguous; bf16 where noted.
+ * "LM" below = fairseq/models/text_to_speech/latent_module.py of the reference; every function cites the
+ * reference code it replaces.
+ */
+#ifndef DIFFNORM_B200_H
+#define DIFFNORM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_OK 0
+#define DN_EINVAL (-1)   /* bad argument (null pointer, misaligned, unsupported size) */
+#define DN_EDRIVER (-2)  /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+/* ---- library info ------------------------------------------------------------------------------------ */
+int dn_abi_version(void);                 /* = 1 */
+unsigned long long dn_launch_count(void); /* kernels launched by this library so far (bench.py gpu_launches) */
+
+/* ---- integer kernels --------------------------------------------------------------------------------- */
+
+/* Run-length reduction of unit streams, batched over utterances.
+ * Replaces research/TranSpeech/diff_norm_synthesis.py:25-46 (reduce_token) ==
+ * fairseq/data/audio/repr_to_repr_unit_dataset.py:92-113 (_reduce_tgt), called twice per utterance
+ * (diff_norm_synthesis.py:150 and :216).
+ * units [B, T] int64 (row stride T), lengths [B] int32 valid tokens per row.
+ * Outputs (row stride T): dedup[b, j], duration[b, j], index_to_keep[b, j] for j < counts[b].
+ * lengths[b] == 0 gives counts[b] = 0 and duration[b,0] = 1 (the reference's quirk, :45), needs T >= 1. */
+int dn_reduce_tgt(const int64_t* units, const int32_t* lengths, int32_t B, int32_t T, int64_t* dedup,
+                  int64_t* duration, int64_t* index_to_keep, int32_t* counts, void* stream);
+
+/* units[r] = argmax_c logits[r, c] - offset, first maximum wins (torch.argmax tie rule), NaN counts as max.
+ * Replaces LM:1450-1451.  logits [rows, ld] fp32 (logits_bf16 = 0) or bf16 (= 1), C classes (C <= ld). */
+int dn_argmax_units(const void* logits, int32_t logits_bf16, int64_t rows, int32_t C, int32_t ld, int32_t offset,
+                    int64_t* units, void* stream);
+
+/* match = #{valid (b,t): units == ref_units}, total = #valid.  Replaces LM:1453-1454 (two .item() syncs).
+ * out2[0] = match, out2[1] = total (int64, device). */
+int dn_unit_accuracy(const int64_t* units, const int64_t* ref_units, const int32_t* lengths, int32_t B, int32_t T,
+                     int64_t* out2, void* stream);
+
+/* Row gather + zero pad: dst[b, j, :] = src[src_row0[b] + index_to_keep[b, j], :] for j < counts[b], else 0.
+ * Replaces diff_norm_synthesis.py:151,164-169.  src fp32 [*, C]; dst fp32 (dst_bf16 = 0) or bf16 [B, T, ldd]
+ * (columns C..ldd are zero-filled). */
+int dn_gather_pack(const float* src, const int64_t* src_row0, const int64_t* index_to_keep, const int32_t* counts,
+                   int32_t B, int32_t T, int32_t C, void* dst, int32_t ldd, int32_t dst_bf16, void* stream);
+
+/* ---- fused elementwise kernels (HBM-bound) ------------------------------------------------------------- */
+
+/* fp32 [rows, C] -> bf16 [rows, ldo] with zero fill of the pad columns (operand staging for the GEMMs). */
+int dn_cast_pad_bf16(const float* src, int64_t rows, int32_t C, int32_t lds, void* dst, int32_t ldo, void* stream);
+
+/* VAE posterior reparameterisation.  Replaces distributions.py:24-41 + the caller's transpose LM:1397.
+ * params [B, T, ldp] fp32 row-major with mean in columns [0,z) and logvar in [z,2z) (channel-last);
+ * eps: eps_channel_first = 1 -> [B, z, T] (the reference's draw order), 0 -> [B, T, z].
+ * z_out [B, T, z] fp32 = mean + exp(0.5 * clamp(logvar, -30, 20)) * eps. */
+int dn_vae_reparam(const float* params, int32_t ldp, const float* eps, int32_t eps_channel_first, int32_t B,
+                   int32_t T, int32_t z, float* z_out, void* stream);
+
+/* Per-step coefficient table row layout (float32 x 8), built by the host from the float64 schedule:
+ *   [0] sqrt_ab  [1] sqrt_1m_ab  [2] sqrt(ab_prev)  [3] sqrt(1-ab_prev)      (DDIM, LM:1419-1438)
+ *   [4] sqrt_recip_ab  [5] sqrt_recipm1_ab  -> x0 = c4*x - c5*eps              (generic lib)
+ *   [6] unused  [7] unused
+ * DDPM rows: [0] sqrt_recip_ab [1] sqrt_recipm1_ab [2] coef1 [3] coef2 [4] exp(0.5*logvar) (0 when t == 0).
+ * `t_idx` is a DEVICE int32 holding the current table row, so one captured CUDA graph serves every step. */
+
+/* x = c0 * z + c1 * eps  (q_sample, LM:1405-1409).  Also writes the bf16 staging copy x_bf16 [n/z, ldx] if
+ * non-null (zero padded to ldx columns). */
+int dn_q_sample(const float* z_lat, const float* eps, float sqrt_ab, float sqrt_1m_ab, int64_t rows, int32_t z,
+                float* x, void* x_bf16, int32_t ldx, void* stream);
+
+/* Inline DDIM eta=0 update (LM:1419-1442), in place on x [rows, z]; eps_hat [rows, lde] fp32.
+ * mode 0: reference inline form with the 1e-10 clamps; mode 1: generic-lib form (gaussian_diffusion.py:513-560). */
+int dn_ddim_step(float* x, const float* eps_hat, int32_t lde, const float* coef_table, const int32_t* t_idx,
+                 int64_t rows, int32_t z, int32_t mode, void* x_bf16, int32_t ldx, void* stream);
+
+/* Ancestral DDPM update (gaussian_diffusion.py:232-252,295-344,402-417), in place; noise [rows, z] fp32. */
+int dn_ddpm_step(float* x, const float* eps_hat, int32_t lde, const float* noise, const float* coef_table,
+                 const int32_t* t_idx, int64_t rows, int32_t z, void* x_bf16, int32_t ldx, void* stream);
+
+/* t_idx[0] += delta (device-side step counter so the sampler loop needs no host round trip). */
+int dn_advance_step(int32_t* t_idx, int32_t delta, void* stream);
+
+/* (Adaptive) RMSNorm, LM:629-639:  out = x / max(||x||, 1e-12) * sqrt(C) * gamma_p  [* gamma_t + beta_t].
+ * x fp32 [B*T, C]; out bf16 [B*T, C]; gamma_p [C] or null; gb (null = unconditioned) points at a table whose
+ * row for utterance b is gb + t_idx[b * t_idx_stride] * gb_t_stride, holding gamma_t[0..C) then beta_t[C..2C). */
+int dn_adarmsnorm(const float* x, void* out, int32_t B, int32_t T, int32_t C, const float* gamma_p, const float* gb,
+                  int64_t gb_t_stride, const int32_t* t_idx, int32_t t_idx_stride, void* stream);
+
+/* Stand-alone WaveNet gate (LM:524-533): y = tanh(u') * sigmoid(u') + res, u' = u * gamma + beta (gb optional).
+ * u, res, y bf16 [B*T, C].  (The denoiser path uses the same math fused into dn_gemm's epilogue.) */
+int dn_wavenet_gate(const void* u, const void* res, void* y, int32_t B, int32_t T, int32_t C, const float* gb,
+                    int64_t gb_t_stride, const int32_t* t_idx, int32_t t_idx_stride, void* stream);
+
+/* Small-M fp32 linear: out[m, n] = act(sum_k in[m, k] * W[n, k] + bias[n]); act 0 = none, 1 = SiLU.
+ * Used for the time-conditioning MLP and the [T, 56, 1024] gamma/beta table (LM:741-745, :507, :624). */
+int dn_linear_f32(const float* in, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
+                  int32_t act, void* stream);
+
+/* Learned sinusoidal time features (LM:104-116): out[m, :] = [t, sin(t w 2pi), cos(t w 2pi)], t = steps[m]. */
+int dn_time_features(const int32_t* steps, const float* w, int32_t M, int32_t half, float* out, void* stream);
+
+/* ---- tensor-core GEMM / implicit causal convolution ----------------------------------------------------- */
+
+/* One K-segment of the contraction: A columns [a_col0, a_col0 + 64*k_blocks) read at rows (t - shift_mul * d),
+ * against W columns [w_k0, ...).  Rows with t - shift < 0 read as zero (causal left padding, LM:476-488). */
+typedef struct {
+    int32_t a_col0;
+    int32_t shift_mul; /* tap k of a K=3 conv: 2, 1, 0 (multiplied by the dilation) */
+    int32_t k_blocks;  /* segment length / 64 */
+    int32_t w_k0;
+    int32_t n_mma;     /* 0 = all rows of the W tile; 128 = only the first 128 rows (wavenet: taps 0,1) */
+} dn_gemm_seg;
+
+enum {
+    DN_EPI_BF16 = 0,     /* out_bf16 = acc + bias */
+    DN_EPI_F32 = 1,      /* out_f32 = acc + bias (+ pe[pos(b,t)] when pe != null; LM:867-868) */
+    DN_EPI_RESID = 2,    /* out_f32 += acc + bias   (residual stream, LM:692,704) */
+    DN_EPI_GEGLU = 3,    /* W tile = 128 "x" rows then 128 "gate" rows: out = gelu_erf(gate) * x (LM:881-885) */
+    DN_EPI_WN_GATE = 4   /* W tile = 128 conv rows then 128 res rows: y = tanh(u')sigmoid(u') + res (LM:513-536) */
+};
+enum { DN_GEMM_TCGEN05 = 0, DN_GEMM_SIMT_CHECK = 1 };
+
+typedef struct {
+    int32_t B, T;               /* utterances, frames per utterance */
+    int32_t groups;             /* independent problems in one launch (the 8 wavenet chains); >= 1 */
+    /* A: bf16 activations [B, T, lda]; tensor-map extent in columns = a_cols */
+    const void* A;
+    int32_t lda, a_cols;
+    int64_t a_batch_stride;     /* elements between utterances */
+    int32_t g_a_col;            /* + g * g_a_col columns for group g */
+    /* W: bf16 [w_rows, ldw], K contiguous (packed by the host: 256 rows per N tile) */
+    const void* W;
+    int32_t ldw, w_rows;
+    int32_t g_w_row;            /* + g * g_w_row rows for group g */
+    int32_t num_segs;
+    dn_gemm_seg seg[4];
+    int32_t dilation;           /* d for group 0 */
+    int32_t dilation_shl_group; /* 1: d << g (wavenet chain i has dilation 2^i, LM:553) */
+    int32_t n_tiles;            /* W tiles (of 256 rows) per group */
+    int32_t n_out;              /* logical output columns per group */
+    int32_t epi;
+    const float* bias;          /* per output column (GEGLU: per packed W row), may be null */
+    const float* bias2;         /* WN: res_conv bias */
+    int32_t g_bias;             /* + g * g_bias for group g */
+    const float* gb;            /* WN: gamma/beta table base (null = unconditioned) */
+    int64_t gb_t_stride;
+    int32_t g_gb, gb_half;      /* per-group offset; beta = gamma + gb_half */
+    const int32_t* t_idx;       /* device: table row per utterance */
+    int32_t t_idx_stride;       /* 0: all utterances share t_idx[0] */
+    void* out;
+    int32_t ldo;
+    int64_t out_batch_stride;
+    int32_t g_out_col;
+    const float* pe;            /* [T + 1, n_out] sinusoidal table (row 0 = zeros) or null */
+    const int32_t* lengths;     /* [B] valid frames (pe positions), may be null = all valid */
+} dn_gemm_desc;
+
+/* out = epilogue(A (*) W^T): bf16 operands, fp32 accumulation in TMEM (tcgen05.mma fed by TMA).
+ * Replaces the cuBLAS / cuDNN calls behind nn.Linear / CausalConv1d on the path.
+ * impl = DN_GEMM_SIMT_CHECK runs a slow one-thread-per-output CUDA kernel with identical semantics
+ * (test checker for the tensor-core kernel; never used by the engine). */
+int dn_gemm(const dn_gemm_desc* d, int32_t impl, void* stream);
+
+/* ---- attention ------------------------------------------------------------------------------------------ */
+
+/* Non-causal multi-head attention with key-padding mask (LM:299-343, :945-949), flash-style (no N x N matrix).
+ * qkv bf16 [B, T, 3*H*dh] = [q | k | v], each head-major (h d); out bf16 [B, T, H*dh].
+ * Keys j >= lengths[b] get exactly zero weight.  dh in {64, 96}. */
+int dn_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H, int32_t dh,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFNORM_B200_H */

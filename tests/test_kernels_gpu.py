@@ -1,0 +1,336 @@
+"""Per-kernel parity tests (B200 only): every C-ABI entry point against a plain torch fp32 statement of the same
+op / the oracle, on seeded inputs.  Integer kernels are bit-exact; bf16 tensor-core kernels carry the tolerance
+in the test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from diffnorm_b200 import _lib, ops, packing  # noqa: E402
+from diffnorm_b200.schedule import DDPMScheduler  # noqa: E402
+from oracle import diffnorm_oracle as O  # noqa: E402
+
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# --------------------------------------------------------------------------------------------------- integer kernels
+def test_reduce_tgt_golden_bit_exact():
+    g = np.load(os.path.join(GOLD, "reduce_tgt.npz"))
+    names = sorted({f[:-3] for f in g.files if f.endswith("_in")})
+    T = max(max(len(g[n + "_in"]) for n in names), 1)
+    units = torch.zeros(len(names), T, dtype=torch.int64)
+    lens = torch.zeros(len(names), dtype=torch.int32)
+    for i, n in enumerate(names):
+        a = g[n + "_in"]
+        units[i, : len(a)] = torch.from_numpy(a)
+        lens[i] = len(a)
+    d, du, kp, cnt = ops.reduce_tgt(units.to(DEV), lens.to(DEV))
+    d, du, kp, cnt = d.cpu(), du.cpu(), kp.cpu(), cnt.cpu()
+    for i, n in enumerate(names):
+        r = int(cnt[i])
+        assert d[i, :r].tolist() == g[n + "_dedup"].tolist(), n
+        assert kp[i, :r].tolist() == g[n + "_keep"].tolist(), n
+        nd = len(g[n + "_dur"])
+        assert du[i, :nd].tolist() == g[n + "_dur"].tolist(), n
+
+
+def test_reduce_tgt_large_properties():
+    rng = np.random.default_rng(0)
+    B, T = 64, 2000
+    runs = rng.geometric(0.6, size=(B, T))
+    ids = rng.integers(0, 1000, size=(B, T))
+    units = np.stack([np.repeat(ids[b], runs[b])[:T] for b in range(B)])
+    lens = rng.integers(1, T + 1, size=B).astype(np.int32)
+    lens[0], lens[1] = T, 1
+    d, du, kp, cnt = (t.cpu().numpy() for t in ops.reduce_tgt(torch.from_numpy(units).to(DEV), torch.from_numpy(lens).to(DEV)))
+    for b in range(B):
+        e_d, e_du, e_k = O.reduce_tgt_np(units[b, : lens[b]])
+        r = cnt[b]
+        assert r == len(e_d)
+        assert (d[b, :r] == e_d).all() and (du[b, :r] == e_du).all() and (kp[b, :r] == e_k).all()
+        assert du[b, :r].sum() == lens[b]                       # durations partition the utterance
+        assert (np.repeat(d[b, :r], du[b, :r]) == units[b, : lens[b]]).all()  # expand(reduce(x)) == x
+    # idempotence: reducing the reduced stream changes nothing
+    d2, du2, kp2, cnt2 = ops.reduce_tgt(torch.from_numpy(d).to(DEV), torch.from_numpy(cnt.astype(np.int32)).to(DEV))
+    assert (cnt2.cpu().numpy() == cnt).all()
+    assert all((du2[b, : cnt[b]].cpu().numpy() == 1).all() for b in range(B))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_argmax_units(dtype):
+    x = rnd(3, 50, 1008, seed=1).to(dtype)
+    x[0, 0, :] = 0.0                 # all ties -> index 0
+    x[0, 1, 7] = x[0, 1, 900] = 50   # tie -> first
+    x[0, 2, 1003] = 60               # last valid class
+    x[0, 3, 1005] = 99               # pad column must be ignored
+    x[0, 4, 2] = 70                  # special symbol wins -> negative unit
+    got = ops.argmax_units(x.contiguous(), 1004, 4).cpu()
+    want = (torch.argmax(x[..., :1004].float(), dim=-1) - 4).cpu()
+    assert torch.equal(got, want)
+    assert got[0, 0] == -4 and got[0, 1] == 3 and got[0, 2] == 999 and got[0, 4] == -2
+
+
+def test_unit_accuracy_and_gather():
+    B, T = 5, 77
+    g = torch.Generator().manual_seed(2)
+    u = torch.randint(0, 5, (B, T), generator=g)
+    r = torch.randint(0, 5, (B, T), generator=g)
+    lens = torch.tensor([77, 1, 30, 64, 65], dtype=torch.int32)
+    out = ops.unit_accuracy(u.to(DEV), r.to(DEV), lens.to(DEV)).cpu()
+    m = torch.arange(T)[None] < lens[:, None]
+    assert out.tolist() == [int(((u == r) & m).sum()), int(m.sum())]
+    # gather + pad
+    C = 768
+    src = rnd(400, C, seed=3)
+    row0 = torch.tensor([0, 100, 150, 200, 300], dtype=torch.int64)
+    keep = torch.zeros(B, T, dtype=torch.int64)
+    cnt = torch.tensor([10, 0, 5, 77, 3], dtype=torch.int32)
+    for b in range(B):
+        keep[b, : cnt[b]] = torch.sort(torch.randperm(90, generator=g)[: cnt[b]]).values
+    for dt in (torch.float32, torch.bfloat16):
+        dst = ops.gather_pack(src, row0.to(DEV), keep.to(DEV), cnt.to(DEV), T, dst_dtype=dt).float().cpu()
+        for b in range(B):
+            want = src.cpu()[row0[b] + keep[b, : cnt[b]]]
+            if dt == torch.bfloat16:
+                want = want.bfloat16().float()
+            assert torch.equal(dst[b, : cnt[b]], want)
+            assert (dst[b, cnt[b]:] == 0).all()
+
+
+# --------------------------------------------------------------------------------------------------- elementwise
+def test_diffusion_steps_match_oracle():
+    sch_o, sch = O.Schedule(200), DDPMScheduler(200)
+    B, T, z = 3, 50, 16
+    x, e, n = rnd(B, T, z, seed=4), rnd(B, T, z, seed=5), rnd(B, T, z, seed=6)
+    ddim_rows = torch.from_numpy(sch.ddim_rows()).to(DEV)
+    t_idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for t in (150, 99, 1):
+        t_idx.fill_(t)
+        xx = x.clone()
+        xb = torch.full((B * T, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+        ops.ddim_step(xx, e, ddim_rows, t_idx, 0, xb)
+        want = O.ddim_step(sch_o, x.cpu(), e.cpu(), t)
+        torch.testing.assert_close(xx.cpu(), want, rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(xb[:, :z].float().cpu().view(B, T, z), want.bfloat16().float(), rtol=1e-2, atol=1e-2)
+        xx = x.clone()
+        ops.ddim_step(xx, e, ddim_rows, t_idx, 1, None)
+        torch.testing.assert_close(xx.cpu(), O.ddim_generic_step(sch_o, x.cpu(), e.cpu(), t), rtol=2e-5, atol=2e-6)
+        for large in (False, True):
+            rows = torch.from_numpy(sch.ddpm_rows(large)).to(DEV)
+            xx = x.clone()
+            ops.ddpm_step(xx, e, n, rows, t_idx, None)
+            torch.testing.assert_close(xx.cpu(), O.ddpm_step(sch_o, x.cpu(), e.cpu(), t, n.cpu(), large), rtol=2e-5, atol=2e-6)
+    ops.advance_step(t_idx, -1)
+    assert int(t_idx) == 0
+    # q_sample + bf16 staging with zero pad
+    zl, eq = rnd(B, T, z, seed=7), rnd(B, T, z, seed=8)
+    xo = torch.empty(B * T, z, device=DEV)
+    xb = torch.full((B * T, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.q_sample(zl, eq, float(np.float32(sch.sqrt_alphas_cumprod[100])), float(np.float32(sch.sqrt_one_minus_alphas_cumprod[100])), xo, xb)
+    torch.testing.assert_close(xo.view(B, T, z).cpu(), O.q_sample(sch_o, zl.cpu(), 100, eq.cpu()), rtol=1e-6, atol=1e-6)
+    assert (xb[:, z:] == 0).all()
+
+
+def test_vae_reparam_and_cast():
+    B, T, z = 2, 33, 16
+    params = rnd(B, T, 2 * z, seed=9, scale=3.0)
+    params[0, 0, z] = 100.0   # clamp high
+    params[0, 1, z] = -100.0  # clamp low
+    eps_cf = rnd(B, z, T, seed=10)
+    got = ops.vae_reparam(params, eps_cf, z, True).cpu()
+    want = O.vae_sample(params.cpu().transpose(1, 2), eps_cf.cpu()).transpose(1, 2)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    got2 = ops.vae_reparam(params, eps_cf.transpose(1, 2).contiguous(), z, False).cpu()
+    torch.testing.assert_close(got2, want, rtol=1e-5, atol=1e-5)
+    src = rnd(70, 20, seed=11)
+    out = ops.cast_pad_bf16(src, 64)
+    assert torch.equal(out[:, :20].float(), src.bfloat16().float()) and (out[:, 20:] == 0).all()
+
+
+@pytest.mark.parametrize("C", [512, 768])
+def test_adarmsnorm(C):
+    B, T = 3, 41
+    x = rnd(B * T, C, seed=12, scale=2.0)
+    x[5] = 0.0  # zero row: eps clamp
+    gp = rnd(C, seed=13) + 1
+    table = rnd(4, 3, 2 * C, seed=14)
+    t_idx = torch.tensor([2, 0, 3], dtype=torch.int32, device=DEV)
+    out = torch.empty(B * T, C, dtype=torch.bfloat16, device=DEV)
+    ops.adarmsnorm(x, out, B, T, gp)
+    want = O.rmsnorm(x.cpu().view(B, T, C), gp.cpu())
+    torch.testing.assert_close(out.float().cpu().view(B, T, C), want, rtol=1e-2, atol=1e-2)
+    gb = table.view(-1)[1 * 2 * C:]  # layer 1 of 3
+    ops.adarmsnorm(x, out, B, T, None, gb, 3 * 2 * C, t_idx, 1)
+    want = O.rmsnorm(x.cpu().view(B, T, C), None, table.cpu()[t_idx.cpu().long(), 1])
+    torch.testing.assert_close(out.float().cpu().view(B, T, C), want, rtol=1e-2, atol=2e-2)
+
+
+def test_wavenet_gate_kernel():
+    B, T, C = 2, 30, 512
+    u, r = rnd(B * T, C, seed=15, scale=2.0).bfloat16(), rnd(B * T, C, seed=16).bfloat16()
+    table = rnd(5, 2 * C, seed=17)
+    t_idx = torch.tensor([4], dtype=torch.int32, device=DEV)
+    y = torch.empty_like(u)
+    ops.wavenet_gate(u, r, y, B, T, table.view(-1), 2 * C, t_idx, 0)
+    uu = u.float() * table[4, :C] + table[4, C:]
+    want = uu.tanh() * uu.sigmoid() + r.float()
+    torch.testing.assert_close(y.float(), want, rtol=1e-2, atol=1e-2)
+
+
+def test_time_table_kernels():
+    w = rnd(256, seed=18)
+    steps = torch.arange(200, dtype=torch.int32, device=DEV)
+    f = ops.time_features(steps, w).cpu()
+    tf = torch.arange(200, dtype=torch.float)[:, None]
+    fr = tf * w.cpu()[None] * 2 * np.pi
+    want = torch.cat([tf, fr.sin(), fr.cos()], -1)
+    torch.testing.assert_close(f, want, rtol=1e-4, atol=2e-3)  # sin/cos of arguments up to ~4e3 rad in fp32
+    W, b, x = rnd(300, 513, seed=19, scale=0.05), rnd(300, seed=20), rnd(37, 513, seed=21)
+    got = ops.linear_f32(x, W, b, act=1).cpu()
+    want = torch.nn.functional.silu(x.cpu() @ W.cpu().T + b.cpu())
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+# --------------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("dh,T,lens", [(64, 200, [200, 131]), (96, 77, [77, 1]), (64, 1000, [1000, 640])])
+def test_attention(dh, T, lens):
+    B, H = 2, 8
+    qkv = rnd(B, T, 3 * H * dh, seed=22).bfloat16()
+    lengths = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    out = torch.empty(B, T, H * dh, dtype=torch.bfloat16, device=DEV)
+    ops.attention(qkv, out, lengths, B, T, H, dh)
+    q, k, v = (t.float().view(B, T, H, dh).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+    sim = torch.einsum("bhid,bhjd->bhij", q, k) * dh ** -0.5
+    mask = torch.arange(T, device=DEV)[None] < lengths[:, None]
+    sim = sim.masked_fill(~mask[:, None, None, :], -torch.finfo(torch.float32).max)
+    want = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), v).transpose(1, 2).reshape(B, T, H * dh)
+    torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
+
+
+# --------------------------------------------------------------------------------------------------- GEMM
+def _gemm_case(plan, A, out_shape, out_dtype, B, T, **kw):
+    outs = []
+    for impl in (_lib.GEMM_SIMT_CHECK, _lib.GEMM_TCGEN05):
+        torch.manual_seed(0)
+        out = torch.randn(out_shape, device=DEV).to(out_dtype).contiguous()  # RESID adds in place: same start
+        plan.run(A, out, B, T, impl=impl, **kw)
+        outs.append(out.float())
+    torch.cuda.synchronize()
+    return outs
+
+
+def test_gemm_linear_epilogues():
+    B, T, K, N = 2, 200, 192, 272
+    A = rnd(B * T, K, seed=30).bfloat16()
+    W, b = rnd(N, K, seed=31, scale=0.1), rnd(N, seed=32)
+    want = (A.float() @ W.bfloat16().float().T + b).view(B * T, N)
+    for epi, dt in ((_lib.EPI_BF16, torch.bfloat16), (_lib.EPI_F32, torch.float32), (_lib.EPI_RESID, torch.float32)):
+        plan = packing.pack_linear(W.cpu(), b.cpu(), epi=epi).to(DEV)
+        chk, tc = _gemm_case(plan, A, (B * T, N), dt, B, T)
+        ref = want
+        if epi == _lib.EPI_RESID:
+            torch.manual_seed(0)
+            ref = want + torch.randn((B * T, N), device=DEV)
+        torch.testing.assert_close(chk, ref, rtol=1e-2, atol=2e-2)
+        torch.testing.assert_close(tc, ref, rtol=1e-2, atol=2e-2)
+        torch.testing.assert_close(tc, chk, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_positional_epilogue():
+    B, T, K, N = 2, 150, 64, 512
+    A = rnd(B * T, K, seed=33).bfloat16()
+    W, b = rnd(N, K, seed=34, scale=0.1), rnd(N, seed=35)
+    lengths = torch.tensor([150, 90], dtype=torch.int32, device=DEV)
+    pe = O.sinusoid_table(T + 1, N).to(DEV).contiguous()
+    plan = packing.pack_linear(W.cpu(), b.cpu(), epi=_lib.EPI_F32).to(DEV)
+    chk, tc = _gemm_case(plan, A, (B * T, N), torch.float32, B, T, pe=pe, lengths=lengths)
+    mask = torch.arange(T, device=DEV)[None] < lengths[:, None]
+    want = (A.float() @ W.bfloat16().float().T + b).view(B, T, N) + O.pos_embed(mask.cpu(), N).to(DEV)
+    torch.testing.assert_close(tc.view(B, T, N), want, rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(tc, chk, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("dil", [1, 4, 128])
+def test_gemm_causal_conv(dil):
+    B, T, Cin, N = 2, 300, 128, 144
+    x = rnd(B, T, Cin, seed=36).bfloat16()
+    W, b = rnd(N, Cin, 3, seed=37, scale=0.1), rnd(N, seed=38)
+    plan = packing.pack_conv3(W.cpu(), b.cpu(), dilation=dil).to(DEV)
+    chk, tc = _gemm_case(plan, x.view(B * T, Cin), (B * T, N), torch.bfloat16, B, T)
+    want = O.causal_conv1d(x.float().transpose(1, 2), W.bfloat16().float(), b, dil).transpose(1, 2).reshape(B * T, N)
+    torch.testing.assert_close(tc, want, rtol=2e-2, atol=3e-2)
+    torch.testing.assert_close(tc, chk, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_geglu():
+    B, T, K, inner = 2, 130, 128, 200
+    A = rnd(B * T, K, seed=39).bfloat16()
+    W, b = rnd(2 * inner, K, seed=40, scale=0.1), rnd(2 * inner, seed=41)
+    plan = packing.pack_geglu(W.cpu(), b.cpu()).to(DEV)
+    assert plan.n_out == 256
+    chk, tc = _gemm_case(plan, A, (B * T, 256), torch.bfloat16, B, T)
+    h = A.float() @ W.bfloat16().float().T + b
+    want = torch.nn.functional.gelu(h[:, inner:]) * h[:, :inner]
+    torch.testing.assert_close(tc[:, :inner], want, rtol=2e-2, atol=2e-2)
+    assert (tc[:, inner:] == 0).all()
+    torch.testing.assert_close(tc, chk, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("cond", [False, True])
+def test_gemm_wavenet_level(cond):
+    B, T, C, G = 2, 260, 192, 3
+    Cp = 256
+    x = torch.zeros(B, T, Cp, device=DEV)
+    x[..., :C] = rnd(B, T, C, seed=42)
+    x = x.bfloat16()
+    cw = [rnd(C, C, 3, seed=43 + g, scale=0.08) for g in range(G)]
+    cb = [rnd(C, seed=50 + g) for g in range(G)]
+    rw = [rnd(C, C, 1, seed=60 + g, scale=0.08) for g in range(G)]
+    rb = [rnd(C, seed=70 + g) for g in range(G)]
+    plan = packing.pack_wavenet_level([w.cpu() for w in cw], [w.cpu() for w in cb], [w.cpu() for w in rw],
+                                      [w.cpu() for w in rb], Cp).to(DEV)
+    kw = {}
+    if cond:  # only meaningful when C == Cp; emulate with a table whose pad lanes are (gamma=1, beta=0)
+        table = torch.zeros(4, G, 2 * Cp, device=DEV)
+        table[..., :Cp] = 1.0
+        table[..., :C] = rnd(4, G, C, seed=80) + 1
+        table[..., Cp:Cp + C] = rnd(4, G, C, seed=81)
+        t_idx = torch.tensor([3, 1], dtype=torch.int32, device=DEV)
+        kw = dict(gb=table.view(-1), gb_t_stride=G * 2 * Cp, g_gb=2 * Cp, gb_half=Cp, t_idx=t_idx, t_idx_stride=1)
+    chk, tc = _gemm_case(plan, x.view(B * T, Cp), (B * T, G * Cp), torch.bfloat16, B, T, g_a_col=0, g_out_col=Cp, **kw)
+    xf = x.float()[..., :C].transpose(1, 2)
+    for g in range(G):
+        u = O.causal_conv1d(xf, cw[g].bfloat16().float(), cb[g], 2 ** g)
+        if cond:
+            gam = table[t_idx.long(), g, :C][:, :, None]
+            bet = table[t_idx.long(), g, Cp:Cp + C][:, :, None]
+            u = u * gam + bet
+        want = (u.tanh() * u.sigmoid() + O.causal_conv1d(xf, rw[g].bfloat16().float(), rb[g])).transpose(1, 2)
+        got = tc.view(B, T, G * Cp)[..., g * Cp:g * Cp + C]
+        torch.testing.assert_close(got, want, rtol=2e-2, atol=3e-2)
+        assert (tc.view(B, T, G * Cp)[..., g * Cp + C:(g + 1) * Cp] == 0).all()
+    torch.testing.assert_close(tc, chk, rtol=1e-2, atol=2e-2)
+
+
+def test_gemm_persistent_many_tiles():
+    # > 148 tiles per launch: exercises the smem ring wrap-around and both TMEM accumulator stages
+    B, T, K, N = 8, 1000, 512, 1536
+    A = rnd(B * T, K, seed=90).bfloat16()
+    W = rnd(N, K, seed=91, scale=0.05)
+    plan = packing.pack_linear(W.cpu(), None).to(DEV)
+    out = torch.empty(B * T, N, dtype=torch.bfloat16, device=DEV)
+    plan.run(A, out, B, T)
+    want = A.float() @ W.bfloat16().float().T
+    torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
