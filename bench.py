@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — normalized frames/s of DiffNorm's latent-diffusion normalization pass on N B200s of one node.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` (torchrun for N > 1) prints ONE JSON line.
+A "step" = one full pass of the hot path over one batch of synthetic 768-d features (BASELINE.json configs[1]:
+batch 64 x 1000 frames, paper-size VAE + denoiser, start_step 100 => 99 denoiser calls, then decode, argmax,
+_reduce_tgt).  Work is sharded by utterance: every rank processes its own batch, no data-path collective
+("scaling": "weak"); `value` = frames all ranks normalized / max-over-ranks device time.
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port; the reference itself is
+Python and cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "normalized frames/sec"
+UNIT = "frames/s"
+
+
+def flops_per_frame(z: int, n: int, calls: int) -> float:
+    """SURVEY.md §8(d) algorithmic FLOPs per valid frame (padding and masked keys excluded)."""
+    venc = {16: 1_660_928, 32: 1_626_112, 128: 2_424_832}[z]
+    vw = {16: 18_144_256, 32: 18_008_064, 128: 16_809_984}[z]
+    d = 141_780_996 + 1024 * z + 12_288 * n
+    vdec = vw + 118_554_624 + 771_072 + 9_216 * n
+    return 2.0 * (venc + calls * d + vdec)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU (reference) arm
+def cpu_pass_sample(z: int, B: int, T: int, start_step: int, calls_timed: int, threads: int):
+    """Times the oracle port of the reference path on the host: encode + `calls_timed` denoiser calls + decode +
+    argmax + reduce, and extrapolates the loop to start_step-1 calls.  Returns (frames/s, description, seconds)."""
+    from oracle import diffnorm_oracle as O
+    torch.set_num_threads(threads)
+    arch = O.Arch(latent_dim=z)
+    sd = O.init_state_dict(arch, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    feat = torch.randn(B, T, 768, generator=g)
+    mask = torch.ones(B, T, dtype=torch.bool)
+    ev, eq = torch.randn(B, z, T, generator=g), torch.randn(B, T, z, generator=g)
+    sch = O.Schedule(arch.timesteps)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        zl = O.vae_encode(sd, arch, feat, ev)
+        x = O.q_sample(sch, zl, start_step, eq)
+        t1 = time.perf_counter()
+        for k in range(calls_timed):
+            t = start_step - 1 - k
+            eh = O.denoiser(sd, arch, x, torch.full((B,), t, dtype=torch.long), mask)
+            x = O.ddim_step(sch, x, eh, t)
+        t2 = time.perf_counter()
+        rec, logits = O.vae_decode(sd, arch, x, mask)
+        units = torch.argmax(logits, -1) - O.UNIT_OFFSET
+        for b in range(B):
+            O.reduce_tgt(units[b].tolist())
+        t3 = time.perf_counter()
+    calls = start_step - 1
+    per_call = (t2 - t1) / max(calls_timed, 1)
+    total = (t1 - t0) + per_call * calls + (t3 - t2)
+    desc = (f"oracle port of the reference path, fp32 torch CPU, B {B} x T {T}, z {z}: encode + {calls_timed} of {calls} "
+            f"denoiser calls + decode + argmax + reduce timed ({t3 - t0:.1f} s), loop extrapolated x{calls}")
+    return B * T / total, desc, t3 - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, desc = [], ""
+    B, T = 8, 500  # bounded sample shape (BASELINE configs[0] shape; per-frame cost is ~shape independent on CPU)
+    for i in range(args.warmup + args.steps):
+        v, desc, _ = cpu_pass_sample(args.latent_dim, B, T, args.start_step, 1 if i < args.warmup else 2, threads)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * args.batch * args.frames / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"DiffNorm normalization pass: batch {args.batch} x {args.frames} frames of 768-d features per GPU, "
+                        f"latent_dim {args.latent_dim}, start_step {args.start_step} ({args.start_step - 1} denoiser calls, "
+                        f"DDIM eta=0 stride 1 = the reference sampler), VAE encode + decode + argmax + _reduce_tgt",
+            "batch": args.batch, "frames": args.frames, "latent_dim": args.latent_dim, "start_step": args.start_step,
+            "sharding": "by utterance, no collective", "l2": "inputs 197 MB/step and >1 GB of activations per call exceed the 126 MB L2",
+            "weights": "random init (torch default init law), bf16 operands / fp32 accumulate"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from diffnorm_b200 import _lib
+    from diffnorm_b200.plugin import compat
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    z, B, T, start = args.latent_dim, args.batch, args.frames, args.start_step
+    torch.manual_seed(0)
+    ns = argparse.Namespace(task="speech_diffusion_discrete", arch="diff_discrete", target_is_code=True,
+                            target_code_size=1000, latent_dim=z)
+    task = compat.setup_task(ns)
+    model = task.build_model(ns, from_checkpoint=True).to(dev).eval()
+    ldm = model.encoder
+    eng = ldm._engine()
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    feat_host = torch.randn(B, T, 768, generator=g).pin_memory()
+    lens_host = torch.full((B,), T, dtype=torch.int32).pin_memory()
+    feat = feat_host.to(dev)
+    lens = lens_host.to(dev)
+
+    def step():
+        return eng.normalize(feat, lens, start)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0, r0 = _lib.launch_count(), eng.replayed_kernels
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = (_lib.launch_count() - n0) + (eng.replayed_kernels - r0)
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    frames = B * T * world
+    value = frames / (ms / 1e3)
+
+    # ---- e2e: pinned host features -> H2D -> public plugin call -> D2H of the reduced units
+    def e2e_step():
+        f = feat_host.to(dev, non_blocking=True)
+        ln = lens_host.to(dev, non_blocking=True)
+        out = ldm.normalize_units(f, ln, start_step=start)
+        res = [out[k].to("cpu", non_blocking=True) for k in ("dedup", "duration", "counts")]
+        torch.cuda.synchronize()
+        return res
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    h2d = feat_host.numel() * 4 + lens_host.numel() * 4
+    d2h = sum(r.numel() * r.element_size() for r in res)
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        calls = start - 1
+        fpf = flops_per_frame(z, T, calls)
+        # ---- dominant kernel: the tcgen05 GEMM on the FFN causal conv (64 % of transformer MACs); timed live with
+        # CUDA events around each of its launches during one eager denoiser call after the timed region
+        t_idx = torch.tensor([start - 1], dtype=torch.int32, device=dev)
+        xb = eng.buf("s.xb", B * T, eng.zp)
+        times = eng.profile_launches("model.transformer.layers", lambda: eng.denoise(xb, lens, B, T, t_idx))
+        conv = [ms_ for n, ms_ in times if n.endswith("ff.conv")]
+        inner = 1365
+        conv_flops = 2.0 * B * T * inner * inner * 3
+        conv_ms = float(np.mean(conv))
+        ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        all_gemm_ms = float(np.sum([m for _, m in times]))
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<EPI_BF16> (FFN causal conv k3 1365->1365 as implicit GEMM, "
+                    "M=B*T, N=1365, K=4095)", "achieved": ach, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained bf16",
+                    "launch_ms": conv_ms, "launches_timed": len(conv),
+                    "transformer_gemm_ms_per_call": all_gemm_ms,
+                    "whole_pass_tflops": fpf * B * T / (ms * 1e-3) / 1e12,
+                    "whole_pass_frac": fpf * B * T / (ms * 1e-3) / 1e12 / peaks["sustained"]}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, desc, _ = cpu_pass_sample(z, 8, 500, start, 2, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--latent-dim", type=int, default=16)
+    ap.add_argument("--start-step", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device for the product arm (there is no CPU fallback); "
+                             "use --impl reference for the CPU baseline")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

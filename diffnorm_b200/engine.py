@@ -62,6 +62,9 @@ class DiffNormEngine:
         self.ws: Dict[tuple, torch.Tensor] = {}
         self.gemm_impl = _lib.GEMM_TCGEN05
         self._graphs: Dict[tuple, object] = {}
+        self._graph_kernels: Dict[tuple, int] = {}
+        self.replayed_kernels = 0   # kernels executed through CUDA-graph replays (not visible to dn_launch_count)
+        self._prof = None
         c = self.cfg
         self.zp = rup(c.latent_dim, 64)        # latent staging width (K of the first GEMMs)
         self.zn = rup(c.latent_dim, 16)        # eps_hat row width
@@ -196,7 +199,26 @@ class DiffNormEngine:
 
     # ------------------------------------------------------------------------------------------------ sub-networks
     def _run(self, plan, A, out, B, T, **kw):
+        prof = self._prof
+        if prof is not None and prof["match"] in plan.name:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.run(A, out, B, T, impl=self.gemm_impl, **kw)
+            e1.record()
+            prof["events"].append((plan.name, e0, e1))
+            return out
         return plan.run(A, out, B, T, impl=self.gemm_impl, **kw)
+
+    def profile_launches(self, match: str, fn):
+        """Run fn() eagerly with CUDA events around every dn_gemm launch whose plan name contains `match`;
+        returns [(name, ms)] (bench.py's live per-launch timing of the dominant kernel)."""
+        self._prof = {"match": match, "events": []}
+        try:
+            fn()
+            torch.cuda.synchronize()
+            return [(n, a.elapsed_time(b)) for n, a, b in self._prof["events"]]
+        finally:
+            self._prof = None
 
     def _wavenet(self, wn: _Wavenet, A, out, B, T, tag: str, gb_layer0: Optional[int] = None, t_idx=None,
                  t_idx_stride=0, pe=None, lengths=None):
@@ -325,8 +347,10 @@ class DiffNormEngine:
             self._ddim_step(B, T)  # warm-up outside capture: function attributes, workspace allocation
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._ddim_step(B, T)
+            self._graph_kernels[key] = _lib.launch_count() - n0
             self._graphs[key] = g
         return g
 
@@ -370,6 +394,7 @@ class DiffNormEngine:
             for _ in range(n):
                 if graph is not None:
                     graph.replay()
+                    self.replayed_kernels += self._graph_kernels[("ddim", B, T)]
                 else:
                     self._ddim_step(B, T)
             calls = n
