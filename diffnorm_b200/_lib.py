@@ -70,7 +70,7 @@ _SIGS = {
     "dn_gemm": [C.POINTER(GemmDesc), i32, vp],
     "dn_attention": [vp, vp, vp, i32, i32, i32, i32, vp],
 }
-EXPORTS = sorted(list(_SIGS) + ["dn_abi_version", "dn_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["dn_abi_version", "dn_launch_count", "dn_batch_by_size"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -80,6 +80,8 @@ lib.dn_abi_version.restype = C.c_int
 lib.dn_abi_version.argtypes = []
 lib.dn_launch_count.restype = C.c_ulonglong
 lib.dn_launch_count.argtypes = []
+lib.dn_batch_by_size.restype = C.c_int64
+lib.dn_batch_by_size.argtypes = [vp, i64, i64, i64, i32, vp]
 
 
 def check(status: int, what: str):

@@ -3,6 +3,8 @@
 // matrix is ever written to HBM (the reference materialises [B, 8, N, N] fp32 per layer).
 // Round-1 implementation: 64-query x 64-key tiles, bf16 mma.sync.m16n8k16 with fp32 accumulation and online
 // softmax in registers (exp2 domain), cp.async double-buffered K/V.  (tcgen05/TMEM version: see DESIGN.md roadmap.)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dn {
@@ -207,13 +209,22 @@ static int launch_attention(const void* qkv, void* out, const int32_t* lengths, 
     return 0;
 }
 
+int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st);
+
 }  // namespace dn
 
 extern "C" int dn_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H,
                             int32_t dh, void* stream) {
     if (!qkv || !out || B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535) return DN_EINVAL;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (dh == 64) return dn::launch_attention<64>(qkv, out, lengths, B, T, H, st);
+    if (dh == 64) {
+        // tcgen05/TMEM kernel (attention_tc.cu); DN_ATTN_IMPL=mma selects the mma.sync kernel (bring-up / A-B timing)
+        const char* e = getenv("DN_ATTN_IMPL");
+        const bool use_mma = e && e[0] == 'm';
+        if (!use_mma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+            return dn::launch_attention_tc(qkv, out, lengths, B, T, H, st);
+        return dn::launch_attention<64>(qkv, out, lengths, B, T, H, st);
+    }
     if (dh == 96) return dn::launch_attention<96>(qkv, out, lengths, B, T, H, st);
     if (dh == 32) return dn::launch_attention<32>(qkv, out, lengths, B, T, H, st);
     return DN_EINVAL;

@@ -27,7 +27,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_COLS = 256;   // TMEM columns per accumulator stage
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int UNIT_BYTES = 128 * 128;  // epilogue staging unit: 128 rows x 128 B (one TMA store box)
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 2 * UNIT_BYTES + 1024 /*align slack*/;
 
 struct TileCoord {
     int g, b, t0, n;
@@ -53,7 +54,8 @@ __device__ __forceinline__ const float* gb_row(const dn_gemm_desc& p, int b, int
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmW128, const dn_gemm_desc p) {
+               const __grid_constant__ CUtensorMap tmW128, const __grid_constant__ CUtensorMap tmOut,
+               const dn_gemm_desc p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -73,6 +75,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmW128);
+        tma_prefetch_desc(&tmOut);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
@@ -163,103 +166,149 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4) {
-        // -------------------------------------------------------------------- epilogue (8 warps)
+        // -------------------------------------------------------------------- epilogue (2 warpgroups x 4 warps)
+        // Each thread owns one accumulator row (tcgen05.ld 32x32b).  Results are staged in a 16 KB smem "unit"
+        // (128 rows x 128 B, 128B-swizzled = the TMA box layout) per warpgroup and written with ONE TMA store
+        // (EPI_RESID: TMA reduce-add into the fp32 residual stream), so global writes are fully coalesced,
+        // asynchronous, and clipped at the tensor edge (t >= T, col >= n_out) by the hardware.
         const int q = warp & 3;            // TMEM lane quadrant this warp may access
-        const int half = (warp - 4) >> 2;  // which half of the column chunks
+        const int half = (warp - 4) >> 2;  // warpgroup: which units of the tile it handles
         const int row = q * 32 + lane;
+        const bool issuer = (warp == 4 + 4 * half) && lane == 0;
+        uint8_t* stage_buf = smem + STAGES * STAGE_BYTES + 1024 + half * UNIT_BYTES;
+        uint8_t* srow = stage_buf + row * 128;
+        const int sw = row & 7;
+        const int bar_id = 1 + half;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             TileCoord c = decode_tile(p, tile, tiles_t);
             const int t = c.t0 + row;
-            const bool valid = t < p.T;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
-            const long long orow = (long long)c.b * p.out_batch_stride + (long long)t * p.ldo + c.g * p.g_out_col;
+            const int ocol0 = c.g * p.g_out_col;
 
             if constexpr (EPI == DN_EPI_BF16 || EPI == DN_EPI_F32 || EPI == DN_EPI_RESID) {
+                constexpr int UCOLS = (EPI == DN_EPI_BF16) ? 64 : 32;   // columns per 16 KB unit
                 const float* bias = p.bias ? p.bias + c.g * p.g_bias : nullptr;
                 long long pe_row = -1;
-                if (EPI == DN_EPI_F32 && p.pe) {
+                if (EPI == DN_EPI_F32 && p.pe && t < p.T) {
                     int pos = t + 1;
                     if (p.lengths && t >= p.lengths[c.b]) pos = 0;
                     pe_row = (long long)pos * p.n_out;
                 }
-                for (int ch = half; ch < WT / 32; ch += 2) {
-                    const int col = c.n * WT + ch * 32;
+                for (int u = half; u < WT / UCOLS; u += 2) {
+                    const int col = c.n * WT + u * UCOLS;
                     if (col >= p.n_out) break;
-                    float v[32];
-                    tmem_ld32(taddr + ch * 32, v);
-                    tmem_ld_wait();
-                    if (valid) {
+                    if (issuer) bulk_wait_read0();          // previous store has finished reading the unit
+                    named_bar_sync(bar_id, 128);
+#pragma unroll
+                    for (int sub = 0; sub < UCOLS / 32; ++sub) {
+                        float v[32];
+                        tmem_ld32(taddr + u * UCOLS + sub * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int cj = col + j * 8;
-                            if (cj + 8 > p.n_out) break;
+                            const int cj = col + sub * 32 + j * 8;
                             float o[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) o[i] = v[j * 8 + i] + (bias ? __ldg(bias + cj + i) : 0.f);
+                            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                            if (bias && cj + 8 <= p.n_out) {
+                                b0 = __ldg(reinterpret_cast<const float4*>(bias + cj));
+                                b1 = __ldg(reinterpret_cast<const float4*>(bias + cj + 4));
+                            }
+                            o[0] = v[j * 8 + 0] + b0.x; o[1] = v[j * 8 + 1] + b0.y; o[2] = v[j * 8 + 2] + b0.z;
+                            o[3] = v[j * 8 + 3] + b0.w; o[4] = v[j * 8 + 4] + b1.x; o[5] = v[j * 8 + 5] + b1.y;
+                            o[6] = v[j * 8 + 6] + b1.z; o[7] = v[j * 8 + 7] + b1.w;
                             if constexpr (EPI == DN_EPI_BF16) {
-                                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + cj;
-                                uint4 w = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
-                                                     pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-                                *reinterpret_cast<uint4*>(op) = w;
+                                const int chunk = sub * 4 + j;  // 16-byte chunk = 8 bf16
+                                *reinterpret_cast<uint4*>(srow + ((chunk ^ sw) << 4)) =
+                                    make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                               pack_bf16(o[6], o[7]));
                             } else {
-                                float* op = reinterpret_cast<float*>(p.out) + orow + cj;
-                                if constexpr (EPI == DN_EPI_RESID) {
-                                    float4 r0 = *reinterpret_cast<float4*>(op);
-                                    float4 r1 = *reinterpret_cast<float4*>(op + 4);
-                                    o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
-                                    o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
-                                } else if (pe_row >= 0) {
+                                if (EPI == DN_EPI_F32 && pe_row >= 0 && cj + 8 <= p.n_out) {
                                     const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.pe + pe_row + cj));
                                     const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.pe + pe_row + cj + 4));
                                     o[0] += e0.x; o[1] += e0.y; o[2] += e0.z; o[3] += e0.w;
                                     o[4] += e1.x; o[5] += e1.y; o[6] += e1.z; o[7] += e1.w;
                                 }
-                                *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
-                                *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                                const int chunk = j * 2;        // 16-byte chunk = 4 fp32
+                                *reinterpret_cast<float4*>(srow + ((chunk ^ sw) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+                                *reinterpret_cast<float4*>(srow + (((chunk + 1) ^ sw) << 4)) =
+                                    make_float4(o[4], o[5], o[6], o[7]);
                             }
                         }
                     }
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (issuer) {
+                        if constexpr (EPI == DN_EPI_RESID)
+                            tma_reduce_add_3d(&tmOut, stage_buf, ocol0 + col, c.t0, c.b);
+                        else
+                            tma_store_3d(&tmOut, stage_buf, ocol0 + col, c.t0, c.b);
+                        bulk_commit();
+                    }
                 }
             } else {
-                // GEGLU / WN_GATE: two 128-column accumulator halves -> 128 output columns per tile
+                // GEGLU / WN_GATE: two 128-column accumulator halves -> 128 bf16 output columns per tile = 2 units
                 const float* gbr = (EPI == DN_EPI_WN_GATE) ? gb_row(p, c.b, c.g) : nullptr;
-                for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
-                    const int col = c.n * 128 + ch * 32;  // logical output column
-                    if (col >= p.n_out) break;
-                    float lo[32], hi[32];
-                    tmem_ld32(taddr + ch * 32, lo);
-                    tmem_ld32(taddr + 128 + ch * 32, hi);
-                    tmem_ld_wait();
-                    if (valid) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + col;
+                const int col = c.n * 128 + half * 64;  // logical output column of this warpgroup's unit
+                if (col < p.n_out) {
+                    if (issuer) bulk_wait_read0();
+                    named_bar_sync(bar_id, 128);
+#pragma unroll 1
+                    for (int sub = 0; sub < 2; ++sub) {
+                        float lo[32], hi[32];
+                        tmem_ld32(taddr + half * 64 + sub * 32, lo);
+                        tmem_ld32(taddr + 128 + half * 64 + sub * 32, hi);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (col + j * 8 + 8 > p.n_out) break;
+                            const int cj = col + sub * 32 + j * 8;
                             float o[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int k = j * 8 + i;
-                                if constexpr (EPI == DN_EPI_GEGLU) {
-                                    const int wr = c.g * p.g_bias + c.n * WT + ch * 32 + k;  // packed W row
-                                    const float x = lo[k] + (p.bias ? __ldg(p.bias + wr) : 0.f);
-                                    const float gt = hi[k] + (p.bias ? __ldg(p.bias + wr + 128) : 0.f);
-                                    o[i] = gelu_erf(gt) * x;
+                            float pa[8], pb[8];  // per-column parameters of the two accumulator halves
+                            auto ld8 = [&](const float* qq, float (&d)[8], float fill) {
+                                if (qq && cj + 8 <= p.n_out) {
+                                    const float4 x0 = __ldg(reinterpret_cast<const float4*>(qq));
+                                    const float4 x1 = __ldg(reinterpret_cast<const float4*>(qq + 4));
+                                    d[0] = x0.x; d[1] = x0.y; d[2] = x0.z; d[3] = x0.w;
+                                    d[4] = x1.x; d[5] = x1.y; d[6] = x1.z; d[7] = x1.w;
                                 } else {
-                                    const int oc = col + k;
-                                    float u = lo[k] + (p.bias ? __ldg(p.bias + c.g * p.g_bias + oc) : 0.f);
-                                    const float r = hi[k] + (p.bias2 ? __ldg(p.bias2 + c.g * p.g_bias + oc) : 0.f);
-                                    if (gbr) u = u * __ldg(gbr + oc) + __ldg(gbr + p.gb_half + oc);
-                                    o[i] = wn_gate(u) + r;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) d[i] = fill;
+                                }
+                            };
+                            if constexpr (EPI == DN_EPI_GEGLU) {
+                                const int wr = c.g * p.g_bias + c.n * WT + half * 64 + sub * 32 + j * 8;  // packed W row
+                                ld8(p.bias ? p.bias + wr : nullptr, pa, 0.f);
+                                ld8(p.bias ? p.bias + wr + 128 : nullptr, pb, 0.f);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    o[i] = gelu_erf_fast(hi[j * 8 + i] + pb[i]) * (lo[j * 8 + i] + pa[i]);
+                            } else {
+                                const int oc = c.g * p.g_bias + cj;
+                                float ga[8], be[8];
+                                ld8(p.bias ? p.bias + oc : nullptr, pa, 0.f);
+                                ld8(p.bias2 ? p.bias2 + oc : nullptr, pb, 0.f);
+                                ld8(gbr ? gbr + cj : nullptr, ga, 1.f);
+                                ld8(gbr ? gbr + p.gb_half + cj : nullptr, be, 0.f);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float uu = fmaf(lo[j * 8 + i] + pa[i], ga[i], be[i]);
+                                    o[i] = wn_gate(uu) + hi[j * 8 + i] + pb[i];
                                 }
                             }
-                            uint4 w = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                                 pack_bf16(o[6], o[7]));
-                            *reinterpret_cast<uint4*>(op + j * 8) = w;
+                            const int chunk = sub * 4 + j;
+                            *reinterpret_cast<uint4*>(srow + ((chunk ^ sw) << 4)) =
+                                make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                           pack_bf16(o[6], o[7]));
                         }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (issuer) {
+                        tma_store_3d(&tmOut, stage_buf, ocol0 + col, c.t0, c.b);
+                        bulk_commit();
                     }
                 }
             }
@@ -269,6 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
+        if (issuer) bulk_wait_all0();  // smem must stay valid (and writes complete) until the bulk stores are done
     }
 
     tc_fence_before();
@@ -360,12 +410,18 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
-                           const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box);
+int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return DN_EDRIVER;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+    CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : DN_EINVAL;
@@ -383,14 +439,14 @@ int num_sms() {
 }
 
 template <int EPI>
-static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& w128, const dn_gemm_desc& d,
-                     int grid, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& w128, const CUtensorMap& o,
+                     const dn_gemm_desc& d, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         DN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_set = true;
     }
-    gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, w, w128, d);
+    gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, w, w128, o, d);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -442,15 +498,27 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
         r = encode_bf16_map(&mw128, d.W, 2, dims, str, box2);
         if (r) return r;
     }
+    CUtensorMap mo;
+    {
+        // output map: columns are clipped at the logical extent so partial tiles never touch neighbouring data
+        const int esz = f32out ? 4 : 2;
+        const long long ocols = d.groups > 1 ? (long long)(d.groups - 1) * d.g_out_col + d.n_out : d.n_out;
+        cuuint64_t dims[3] = {(cuuint64_t)ocols, (cuuint64_t)d.T, (cuuint64_t)d.B};
+        cuuint64_t str[2] = {(cuuint64_t)d.ldo * esz, (cuuint64_t)d.out_batch_stride * esz};
+        cuuint32_t box[3] = {(cuuint32_t)(f32out ? 32 : 64), BM, 1};
+        int r = encode_map(&mo, f32out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.out, 3,
+                           dims, str, box);
+        if (r) return r;
+    }
     const int tiles_t = (d.T + BM - 1) / BM;
     const long long total = (long long)d.groups * d.B * tiles_t * d.n_tiles;
     const int grid = (int)(total < num_sms() ? total : num_sms());
     switch (d.epi) {
-        case DN_EPI_BF16: return launch_tc<DN_EPI_BF16>(ma, mw, mw128, d, grid, st);
-        case DN_EPI_F32: return launch_tc<DN_EPI_F32>(ma, mw, mw128, d, grid, st);
-        case DN_EPI_RESID: return launch_tc<DN_EPI_RESID>(ma, mw, mw128, d, grid, st);
-        case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU>(ma, mw, mw128, d, grid, st);
-        case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE>(ma, mw, mw128, d, grid, st);
+        case DN_EPI_BF16: return launch_tc<DN_EPI_BF16>(ma, mw, mw128, mo, d, grid, st);
+        case DN_EPI_F32: return launch_tc<DN_EPI_F32>(ma, mw, mw128, mo, d, grid, st);
+        case DN_EPI_RESID: return launch_tc<DN_EPI_RESID>(ma, mw, mw128, mo, d, grid, st);
+        case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU>(ma, mw, mw128, mo, d, grid, st);
+        case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE>(ma, mw, mw128, mo, d, grid, st);
         default: return DN_EINVAL;
     }
 }

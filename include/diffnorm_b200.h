@@ -180,6 +180,16 @@ int dn_gemm(const dn_gemm_desc* d, int32_t impl, void* stream);
 int dn_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H, int32_t dh,
                  void* stream);
 
+/* ---- host-side helper (no CUDA) --------------------------------------------------------------------------- */
+
+/* Length-bucketed batching under a padded-token budget; same contract and results as the reference's Cython
+ * batch_by_size_vec (fairseq/data/data_utils_fast.pyx:20-101).  num_tokens[i] = length of the i-th utterance in
+ * iteration (normally length-sorted) order; batch k = [batch_ends[k-1], batch_ends[k]) with batch_ends[-1] = 0.
+ * batch_ends must hold n + 1 entries.  Returns the number of batches, or DN_EINVAL (an utterance longer than
+ * max_tokens, bad arguments).  max_tokens / max_sentences <= 0 disable that limit. */
+int64_t dn_batch_by_size(const int64_t* num_tokens, int64_t n, int64_t max_tokens, int64_t max_sentences,
+                         int32_t bsz_mult, int64_t* batch_ends);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,6 +219,22 @@ def test_attention(dh, T, lens):
     torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
 
 
+def test_attention_tcgen05_matches_mma_kernel():
+    """dh = 64 runs on the tcgen05/TMEM kernel; DN_ATTN_IMPL=mma selects the mma.sync kernel: both must agree."""
+    B, T, H, dh = 3, 700, 8, 64
+    qkv = rnd(B, T, 3 * H * dh, seed=23, scale=1.5).bfloat16()
+    lengths = torch.tensor([700, 129, 1], dtype=torch.int32, device=DEV)
+    outs = []
+    for impl in ("mma", "tc"):
+        os.environ["DN_ATTN_IMPL"] = impl
+        out = torch.full((B, T, H * dh), 9.0, dtype=torch.bfloat16, device=DEV)
+        ops.attention(qkv, out, lengths, B, T, H, dh)
+        torch.cuda.synchronize()
+        outs.append(out.float())
+    os.environ.pop("DN_ATTN_IMPL")
+    torch.testing.assert_close(outs[1], outs[0], rtol=2e-2, atol=2e-2)
+
+
 # --------------------------------------------------------------------------------------------------- GEMM
 def _gemm_case(plan, A, out_shape, out_dtype, B, T, **kw):
     outs = []

@@ -106,3 +106,72 @@ def test_stages_and_pass_against_golden(name):
             assert out["dedup"][b, :r].cpu().tolist() == dd
             assert out["duration"][b, :r].cpu().tolist() == du
             assert out["index_to_keep"][b, :r].cpu().tolist() == kp
+
+
+def test_sampler_variants_against_reference_generic_lib():
+    """Config-3 samplers: ancestral DDPM (fixed-small / fixed-large variance) and strided DDIM against outputs of the
+    reference's generic diffusion lib (gaussian_diffusion.py p_sample / ddim_sample + respace.SpacedDiffusion) minted
+    with the reference denoiser as model_fn (tests/golden/samplers_z16_parity.npz)."""
+    from diffnorm_b200 import ops
+    g, arch, sd, eng = setup_case("pass_z16_parity")
+    s = np.load(os.path.join(GOLD, "samplers_z16_parity.npz"))
+    t = lambda k: torch.from_numpy(s[k])
+    x0 = t("x")
+    B, T, z = x0.shape
+    lens = torch.from_numpy(g["lengths"]).to(torch.int32).to(DEV)
+    mask_cpu = O.lengths_to_mask(torch.from_numpy(g["lengths"]), T)
+    t_idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for tag, large in (("small", False), ("large", True)):
+        rows = torch.from_numpy(eng.sched.ddpm_rows(large)).to(DEV)
+        for step in (37, 1, 0):
+            xb = eng.stage_latent(x0.to(DEV))
+            x = x0.to(DEV).clone().view(B * T, z)
+            t_idx.fill_(step)
+            eh = eng.denoise(xb, lens, B, T, t_idx)
+            d = stats(f"ddpm_{tag}_t{step}_eps", eh.view(B, T, -1)[..., :z].cpu()[mask_cpu], t(f"ddpm_{tag}_t{step}_eps")[mask_cpu])
+            assert d.max() <= 5e-2 * t(f"ddpm_{tag}_t{step}_eps").std() + 2e-2
+            ops.ddpm_step(x, eh, t(f"ddpm_{tag}_t{step}_noise").to(DEV).view(B * T, z).contiguous(), rows, t_idx, xb)
+            want = t(f"ddpm_{tag}_t{step}_sample")
+            d = stats(f"ddpm_{tag}_t{step}_sample", x.view(B, T, z).cpu()[mask_cpu], want[mask_cpu])
+            assert d.max() <= 3e-2 * (1 + want.abs().max())
+    # strided DDIM through the engine's own sampler loop: 3 steps from the top of range(0, 40, 4)
+    keep = s["strided_keep"].tolist()
+    sp, tmap = eng.sched.spaced(keep)
+    rows = torch.from_numpy(sp.ddim_rows()).to(DEV)
+    x = x0.to(DEV).clone().view(B * T, z)
+    xb = eng.stage_latent(x0.to(DEV))
+    r_idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for i in range(len(tmap) - 1, len(tmap) - 4, -1):
+        t_idx.fill_(tmap[i])
+        r_idx.fill_(i)
+        eh = eng.denoise(xb, lens, B, T, t_idx)
+        ops.ddim_step(x, eh, rows, r_idx, 1, xb)
+    want = t("strided_after3")
+    d = stats("strided_after3", x.view(B, T, z).cpu()[mask_cpu], want[mask_cpu])
+    assert d.max() <= 3e-2 * (1 + want.abs().max())
+
+
+def test_pass_sampler_modes_run_and_agree_with_oracle():
+    """engine.normalize with sampler='ddpm' (replayed per-step noise) and 'ddim_strided' vs the oracle pass."""
+    g, arch, sd, eng = setup_case("pass_z16_parity")
+    t = lambda k: torch.from_numpy(g[k])
+    feat, eps_vae, eps_q = t("feat"), t("eps_vae"), t("eps_q")
+    B, T, _ = feat.shape
+    z = arch.latent_dim
+    lens = torch.from_numpy(g["lengths"]).to(torch.int32).to(DEV)
+    mask_cpu = O.lengths_to_mask(torch.from_numpy(g["lengths"]), T)
+    start = 6
+    gen = torch.Generator().manual_seed(5)
+    noises = [torch.randn(B, T, z, generator=gen) for _ in range(start - 1)]
+    ref = O.normalize_pass(sd, arch, feat, mask_cpu, start, eps_vae, eps_q, sampler="ddpm", step_noise=noises)
+    out = eng.normalize(feat.to(DEV), lens, start, eps_vae.to(DEV), eps_q.to(DEV), sampler="ddpm",
+                        step_noise=[n.to(DEV) for n in noises])
+    d = stats("ddpm_pass_x0", out["x0"].cpu()[mask_cpu], ref["x0"][mask_cpu])
+    assert out["calls"] == ref["calls"] == start - 1
+    assert d.max() <= 3e-2 * (1 + ref["x0"].abs().max())
+    keep = list(range(0, 12, 3))
+    ref = O.normalize_pass(sd, arch, feat, mask_cpu, 12, eps_vae, eps_q, sampler="ddim_strided", timesteps=keep)
+    out = eng.normalize(feat.to(DEV), lens, 12, eps_vae.to(DEV), eps_q.to(DEV), sampler="ddim_strided", timesteps=keep)
+    d = stats("strided_pass_x0", out["x0"].cpu()[mask_cpu], ref["x0"][mask_cpu])
+    assert out["calls"] == ref["calls"] == len(keep) - 1
+    assert d.max() <= 3e-2 * (1 + ref["x0"].abs().max())
