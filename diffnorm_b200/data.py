@@ -1,0 +1,185 @@
+"""The caller side of the normalization pass: manifest / unit-TSV reader, native length-bucketed
+batching, utterance sharding across GPUs, the batched GPU pre/post-processing around ``ddim_sample`` and the
+output TSV writer.  Mirrors research/TranSpeech/diff_norm_synthesis.py:70-222 (file formats: SURVEY Appendix B)
+but replaces its fixed 100-utterance file-order batches and per-utterance Python loops:
+
+  reference (per utterance, Python)                     here (per batch, device)
+  reduce_token(full_unit) -> index_to_keep   :150       dn_reduce_tgt on the padded original units
+  tgt_feat[index_to_keep]; zero pad          :151-169   dn_gather_pack from the packed feature rows
+  ddim_sample                                :204       DiffNormEngine.normalize
+  .cpu().tolist(); reduce_token again        :213-216   dn_reduce_tgt on the predicted units, one D2H per batch
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+HEADER = "id\tsrc_audio\tsrc_n_frames\ttgt_audio\ttgt_n_frames"
+
+
+@dataclass
+class UtteranceItem:  # diff_norm_synthesis.py:57-67 AllDataItem
+    audio_id: str
+    src_audio: str
+    src_n_frames: int
+    tgt_unit: str
+    tgt_n_frames: int
+    reduce_tgt_unit: str
+    reduce_tgt_n_frames: int
+    feature_file: str
+
+
+def read_unit_tsv(path: str) -> "OrderedDict[str, Tuple[str, int, str, int]]":
+    """Header line skipped; rows with != 5 tab-separated fields skipped (diff_norm_synthesis.py:79-88)."""
+    out: "OrderedDict[str, Tuple[str, int, str, int]]" = OrderedDict()
+    with open(path, "r") as f:
+        f.readline()
+        for line in f:
+            parts = line.strip().split("\t")
+            if len(parts) != 5:
+                continue
+            audio_id, src_audio, src_n, tgt_audio, tgt_n = parts
+            out[audio_id] = (src_audio, int(src_n), tgt_audio, int(tgt_n))
+    return out
+
+
+def prepare_data(reduce_tsv_dir: str, orig_tsv_dir: str, feature_dir: str, split: str) -> Tuple[List[UtteranceItem], int]:
+    """Join the reduced and original unit TSVs and keep utterances whose ``{id}.feat.npy`` exists
+    (diff_norm_synthesis.py:70-116).  Order = order of the original TSV.  Returns (items, unfound)."""
+    reduce_map = read_unit_tsv(os.path.join(reduce_tsv_dir, f"{split}.tsv"))
+    items: "OrderedDict[str, UtteranceItem]" = OrderedDict()
+    unfound = 0
+    for audio_id, (_, _, tgt_audio, tgt_n) in read_unit_tsv(os.path.join(orig_tsv_dir, f"{split}.tsv")).items():
+        feat = os.path.join(feature_dir, split, f"{audio_id}.feat.npy")
+        if audio_id not in reduce_map or not os.path.exists(feat):
+            unfound += 1
+            continue
+        r_src, r_src_n, r_units, r_n = reduce_map[audio_id]
+        items[audio_id] = UtteranceItem(audio_id, r_src, r_src_n, tgt_audio, tgt_n, r_units, r_n, feat)
+    return list(items.values()), unfound
+
+
+def read_manifest(path: str) -> Tuple[str, List[Tuple[str, int]]]:
+    """``{split}.manifest.tsv``: line 1 = feature dir, then ``{id}.feat.npy \\t N_full``
+    (speech2unit/pretrained/utils.py:131-141, repr_to_repr_unit_dataset.py:311-323)."""
+    with open(path) as f:
+        root = f.readline().strip()
+        rows = []
+        for line in f:
+            parts = line.strip().split("\t")
+            if len(parts) == 2:
+                rows.append((parts[0], int(parts[1])))
+    return root, rows
+
+
+# ------------------------------------------------------------------------------------------------ batching
+def batch_by_size(num_tokens: Sequence[int], max_tokens: int = 0, max_sentences: int = 0, bsz_mult: int = 1) -> List[Tuple[int, int]]:
+    """Native (C++) equivalent of fairseq's ``batch_by_size_vec`` (data_utils_fast.pyx:20-101): half-open index
+    ranges over ``num_tokens`` in the given order."""
+    from ._lib import DiffNormLibraryError, lib
+    toks = np.ascontiguousarray(num_tokens, dtype=np.int64)
+    n = len(toks)
+    ends = np.zeros(n + 1, dtype=np.int64)
+    k = lib.dn_batch_by_size(toks.ctypes.data_as(ctypes.c_void_p), n, int(max_tokens), int(max_sentences), int(bsz_mult),
+                             ends.ctypes.data_as(ctypes.c_void_p))
+    if k < 0:
+        raise DiffNormLibraryError(f"dn_batch_by_size failed ({k}): an utterance exceeds max_tokens={max_tokens}?")
+    starts = np.concatenate([[0], ends[: k - 1]]) if k > 0 else np.zeros(0, dtype=np.int64)
+    return [(int(s), int(e)) for s, e in zip(starts, ends[:k])]
+
+
+def pass_cost(n: np.ndarray) -> np.ndarray:
+    """Relative device cost of normalizing an utterance of n frames: GEMM/conv work is linear in n, attention is
+    quadratic (D(z, N) = 141.78 M + 12,288 N MAC per frame)."""
+    n = np.asarray(n, dtype=np.float64)
+    return n * (141.78e6 + 12288.0 * n)
+
+
+def plan_batches(lengths: Sequence[int], max_tokens: int, max_sentences: int = 0, bsz_mult: int = 1, world_size: int = 1,
+                 pad_multiple: int = 1) -> List[List[np.ndarray]]:
+    """Sort utterances by length, cut them into batches under a padded-token budget, and assign the batches to
+    `world_size` ranks by longest-processing-time-first on the cost model (no collective is ever needed:
+    utterances are independent).  Returns, per rank, a list of index arrays (indices into `lengths`)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    order = np.argsort(lengths, kind="stable")
+    padded = (lengths[order] + pad_multiple - 1) // pad_multiple * pad_multiple
+    ranges = batch_by_size(padded, max_tokens, max_sentences, bsz_mult)
+    batches = [order[s:e] for s, e in ranges]
+    costs = np.array([len(b) * float(pass_cost(padded[s:e].max())) for b, (s, e) in zip(batches, ranges)])
+    load = np.zeros(world_size)
+    per_rank: List[List[np.ndarray]] = [[] for _ in range(world_size)]
+    for bi in np.argsort(-costs, kind="stable"):
+        r = int(np.argmin(load))
+        per_rank[r].append(batches[bi])
+        load[r] += costs[bi]
+    return per_rank
+
+
+# ------------------------------------------------------------------------------------------------ runner
+class NormalizationRunner:
+    """Drives DiffNormEngine over lists of utterances (features + original unit strings) and returns TSV rows."""
+
+    def __init__(self, engine, start_step: int = 50, max_tokens: int = 64000, max_sentences: int = 0, sampler: str = "ddim"):
+        self.eng, self.start_step, self.max_tokens, self.max_sentences, self.sampler = engine, start_step, max_tokens, max_sentences, sampler
+
+    def normalize_batch(self, feats: List[np.ndarray], full_units: List[np.ndarray], expect_reduced: Optional[List[int]] = None):
+        """feats[i] fp32 [N_full_i, 768], full_units[i] int64 [N_full_i] -> per utterance (reduced units, n_frames)
+        where n_frames = frames fed to the model = length BEFORE the second reduce (diff_norm_synthesis.py:211-222)."""
+        import torch
+
+        from . import ops
+        dev = self.eng.dev
+        B = len(feats)
+        n_full = np.array([len(u) for u in full_units], dtype=np.int64)
+        for f, u in zip(feats, full_units):
+            if f.shape[0] != len(u):
+                raise ValueError(f"feature rows {f.shape[0]} != number of original units {len(u)}")
+        Tf = int(n_full.max())
+        units_h = torch.zeros(B, Tf, dtype=torch.int64).pin_memory()
+        for i, u in enumerate(full_units):
+            units_h[i, : len(u)] = torch.from_numpy(np.asarray(u, dtype=np.int64))
+        packed_h = torch.from_numpy(np.concatenate([np.asarray(f, dtype=np.float32) for f in feats], axis=0)).pin_memory()
+        row0_h = torch.from_numpy(np.concatenate([[0], np.cumsum(n_full)[:-1]]).astype(np.int64))
+        units_d = units_h.to(dev, non_blocking=True)
+        packed = packed_h.to(dev, non_blocking=True)
+        lens_full = torch.from_numpy(n_full.astype(np.int32)).to(dev)
+        # first reduce: index_to_keep of the ORIGINAL units (:150)
+        _, _, keep, counts = ops.reduce_tgt(units_d, lens_full)
+        counts_h = counts.cpu().numpy()
+        if expect_reduced is not None and list(counts_h) != list(expect_reduced):  # the reference's assert (:152)
+            raise AssertionError("reduced length from the original units does not match reduce_tgt_n_frames")
+        T = int(counts_h.max())
+        keep_t = keep[:, :T].contiguous()
+        feat = ops.gather_pack(packed, row0_h.to(dev), keep_t, counts, T)  # [B, T, 768] fp32, zero padded (:164-169)
+        out = self.eng.normalize(feat, counts, self.start_step, sampler=self.sampler)
+        dedup = out["dedup"].cpu().numpy()
+        cnt2 = out["counts"].cpu().numpy()
+        return [(dedup[i, : cnt2[i]].copy(), int(counts_h[i])) for i in range(B)]
+
+    def run_items(self, items: List[UtteranceItem], rank: int = 0, world_size: int = 1, progress=None) -> Dict[int, str]:
+        """Normalizes this rank's share of `items`; returns {item index: TSV line}."""
+        lengths = [it.reduce_tgt_n_frames for it in items]
+        plan = plan_batches(lengths, self.max_tokens, self.max_sentences, world_size=world_size)[rank]
+        lines: Dict[int, str] = {}
+        for idx in plan:
+            feats = [np.load(items[i].feature_file) for i in idx]
+            units = [np.array([int(x) for x in items[i].tgt_unit.split(" ")], dtype=np.int64) for i in idx]
+            res = self.normalize_batch(feats, units, [items[i].reduce_tgt_n_frames for i in idx])
+            for i, (red, n_frames) in zip(idx, res):
+                it = items[i]
+                lines[int(i)] = f"{it.audio_id}\t{it.src_audio}\t{it.src_n_frames}\t{' '.join(str(int(v)) for v in red)}\t{n_frames}"
+            if progress is not None:
+                progress(len(idx))
+        return lines
+
+
+def write_tsv(path: str, lines: Iterable[str]):
+    with open(path, "w") as f:
+        f.write(HEADER + "\n")
+        for ln in lines:
+            f.write(ln + "\n")

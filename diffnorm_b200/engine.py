@@ -65,6 +65,7 @@ class DiffNormEngine:
         self._graph_kernels: Dict[tuple, int] = {}
         self.replayed_kernels = 0   # kernels executed through CUDA-graph replays (not visible to dn_launch_count)
         self._prof = None
+        self._reserve_rows = 0
         c = self.cfg
         self.zp = rup(c.latent_dim, 64)        # latent staging width (K of the first GEMMs)
         self.zn = rup(c.latent_dim, 16)        # eps_hat row width
@@ -174,13 +175,25 @@ class DiffNormEngine:
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------------------------------------ workspace
-    def buf(self, name: str, rows: int, width: int, dtype=bf16) -> torch.Tensor:
-        key = (name, rows, width, dtype)
+    def buf(self, name: str, rows: int, width: int, dtype=bf16, frames: bool = True) -> torch.Tensor:
+        """Named workspace buffer [rows, width].  One allocation per (name, width, dtype) is shared by every batch
+        shape: a request returns the leading `rows` rows of the largest buffer allocated so far (row-major, so the
+        prefix is contiguous).  Buffers are zero-initialised and the GEMM pad columns are only ever written with
+        zeros, so the padding invariants survive sharing.  Growing a buffer drops the captured CUDA graphs (they hold
+        the old pointers); call `reserve(max_rows)` first to avoid re-capturing."""
+        key = (name, width, dtype)
         t = self.ws.get(key)
-        if t is None:
-            t = torch.zeros(rows, width, dtype=dtype, device=self.dev)
+        want = max(rows, self._reserve_rows) if frames else rows  # frames=True: rows scale with B*T
+        if t is None or t.shape[0] < rows:
+            t = torch.zeros(want, width, dtype=dtype, device=self.dev)
             self.ws[key] = t
-        return t
+            self._graphs.clear()
+            self._graph_kernels.clear()
+        return t[:rows]
+
+    def reserve(self, max_rows: int):
+        """Size the shared workspace for batches of up to `max_rows` = B*T frames."""
+        self._reserve_rows = max(self._reserve_rows, int(max_rows))
 
     def pe_table(self, T: int) -> torch.Tensor:
         """Sinusoidal table rows 0..T (row 0 = padding = zeros), sinusoidal_positional_embedding.py:36-58."""
@@ -330,7 +343,7 @@ class DiffNormEngine:
     def _ddim_step(self, B, T):
         M, z = B * T, self.cfg.latent_dim
         x, xb = self.buf("s.x", M, z, f32), self.buf("s.xb", M, self.zp)
-        t_idx, lens = self.buf("s.t", 1, 1, i32).view(-1), self.buf("s.len", B, 1, i32).view(-1)
+        t_idx, lens = self.buf("s.t", 1, 1, i32, frames=False).view(-1), self.buf("s.len", B, 1, i32, frames=False).view(-1)
         eh = self.denoise(xb, lens, B, T, t_idx)
         ops.ddim_step(x, eh, self.ddim_rows, t_idx, 0, xb)
         ops.advance_step(t_idx, -1)
@@ -341,7 +354,7 @@ class DiffNormEngine:
         key = ("ddim", B, T)
         g = self._graphs.get(key)
         if g is None:
-            t_idx, lens = self.buf("s.t", 1, 1, i32).view(-1), self.buf("s.len", B, 1, i32).view(-1)
+            t_idx, lens = self.buf("s.t", 1, 1, i32, frames=False).view(-1), self.buf("s.len", B, 1, i32, frames=False).view(-1)
             t_idx.fill_(1)
             lens.fill_(T)
             self._ddim_step(B, T)  # warm-up outside capture: function attributes, workspace allocation
@@ -372,7 +385,7 @@ class DiffNormEngine:
         if eps_q is None:
             eps_q = torch.randn(B, T, z, device=self.dev, dtype=f32)
         graph = self._ddim_graph(B, T) if (use_graph and sampler == "ddim" and start_step > 2) else None
-        lens = self.buf("s.len", B, 1, i32).view(-1)
+        lens = self.buf("s.len", B, 1, i32, frames=False).view(-1)
         lens.copy_(lengths)
         out = {}
         zlat = self.encode(feat, eps_vae)
@@ -384,7 +397,7 @@ class DiffNormEngine:
         if collect:
             out["z"] = zlat.clone()
             out["x_start"] = x.view(B, T, z).clone()
-        t_idx = self.buf("s.t", 1, 1, i32).view(-1)
+        t_idx = self.buf("s.t", 1, 1, i32, frames=False).view(-1)
         calls = 0
         if sampler == "ddim":
             t_idx.fill_(start_step - 1)
@@ -411,7 +424,7 @@ class DiffNormEngine:
         elif sampler == "ddim_strided":
             sp, tmap = s.spaced(timesteps)
             rows = torch.from_numpy(sp.ddim_rows()).to(self.dev)
-            r_idx = self.buf("s.r", 1, 1, i32).view(-1)
+            r_idx = self.buf("s.r", 1, 1, i32, frames=False).view(-1)
             for i in range(len(tmap) - 1, 0, -1):
                 t_idx.fill_(tmap[i])          # the model sees the original step (respace.py:117-129)
                 r_idx.fill_(i)                # the update uses the respaced table row

@@ -178,9 +178,39 @@ def make_reduce():
     print("reduce cases", len(cases))
 
 
+def make_batcher():
+    """Golden vectors from the reference's OWN compiled Cython batcher (oracle/_ref/data_utils_fast*.so, built by
+    `make -C oracle ref` from /root/reference/fairseq/data/data_utils_fast.pyx)."""
+    sys.path.insert(0, os.path.join(HERE, "_ref"))
+    import data_utils_fast as ref
+    rng = np.random.default_rng(7)
+    out, n_cases = {}, 0
+    for trial in range(300):
+        n = int(rng.integers(1, 80))
+        toks = rng.integers(1, 60, size=n).astype(np.int64)
+        if rng.random() < 0.6:
+            toks = np.sort(toks)
+        mt, ms, bm = int(rng.choice([0, 60, 64, 100, 200, 400])), int(rng.choice([0, 1, 3, 8])), int(rng.choice([1, 2, 4, 8]))
+        if mt and toks.max() > mt:
+            mt = int(toks.max())
+        sizes = [len(b) for b in ref.batch_by_size_vec(np.arange(n, dtype=np.int64), toks, mt, ms, bm)]
+        out[f"toks_{n_cases}"], out[f"args_{n_cases}"], out[f"sizes_{n_cases}"] = toks, np.array([mt, ms, bm]), np.array(sizes)
+        n_cases += 1
+    # dataset-like case: 20k log-normal lengths, length-sorted, --max-tokens 12000 (scripts/diffusion/train.sh:31)
+    lens = np.sort(np.clip(np.round(np.exp(rng.normal(np.log(600), 0.5, size=20000))), 200, 2000).astype(np.int64))
+    sizes = [len(b) for b in ref.batch_by_size_vec(np.arange(len(lens), dtype=np.int64), lens, 12000, 0, 1)]
+    out[f"toks_{n_cases}"], out[f"args_{n_cases}"], out[f"sizes_{n_cases}"] = lens, np.array([12000, 0, 1]), np.array(sizes)
+    n_cases += 1
+    np.savez_compressed(os.path.join(GOLD, "batch_by_size.npz"), n_cases=n_cases, **out)
+    print("batcher cases", n_cases)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
+    if "--batcher-only" in sys.argv:
+        return make_batcher()
+    make_batcher()
     make_reduce()
     for name in PASS_CASES:
         sd, arch, ldm, inputs = make_pass(name)
