@@ -23,7 +23,7 @@ def _ensure_built():
 def test_library_exports_every_declared_symbol():
     so = _ensure_built()
     hdr = open(os.path.join(ROOT, "include", "diffnorm_b200.h")).read()
-    declared = sorted(set(re.findall(r"^\s*(?:int|unsigned long long)\s+(dn_[a-z0-9_]+)\s*\(", hdr, flags=re.M)))
+    declared = sorted(set(re.findall(r"^\s*(?:int|int64_t|unsigned long long)\s+(dn_[a-z0-9_]+)\s*\(", hdr, flags=re.M)))
     assert len(declared) >= 18
     lib = ctypes.CDLL(so)
     for name in declared:
