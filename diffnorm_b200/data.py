@@ -127,7 +127,8 @@ class NormalizationRunner:
     def __init__(self, engine, start_step: int = 50, max_tokens: int = 64000, max_sentences: int = 0, sampler: str = "ddim"):
         self.eng, self.start_step, self.max_tokens, self.max_sentences, self.sampler = engine, start_step, max_tokens, max_sentences, sampler
 
-    def normalize_batch(self, feats: List[np.ndarray], full_units: List[np.ndarray], expect_reduced: Optional[List[int]] = None):
+    def normalize_batch(self, feats: List[np.ndarray], full_units: List[np.ndarray], expect_reduced: Optional[List[int]] = None,
+                        return_units: bool = False):
         """feats[i] fp32 [N_full_i, 768], full_units[i] int64 [N_full_i] -> per utterance (reduced units, n_frames)
         where n_frames = frames fed to the model = length BEFORE the second reduce (diff_norm_synthesis.py:211-222)."""
         import torch
@@ -159,7 +160,11 @@ class NormalizationRunner:
         out = self.eng.normalize(feat, counts, self.start_step, sampler=self.sampler)
         dedup = out["dedup"].cpu().numpy()
         cnt2 = out["counts"].cpu().numpy()
-        return [(dedup[i, : cnt2[i]].copy(), int(counts_h[i])) for i in range(B)]
+        res = [(dedup[i, : cnt2[i]].copy(), int(counts_h[i])) for i in range(B)]
+        if return_units:
+            units = out["units"].cpu().numpy()
+            return res, [units[i, : counts_h[i]].copy() for i in range(B)], feat.cpu()
+        return res
 
     def run_items(self, items: List[UtteranceItem], rank: int = 0, world_size: int = 1, progress=None) -> Dict[int, str]:
         """Normalizes this rank's share of `items`; returns {item index: TSV line}."""

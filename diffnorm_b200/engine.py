@@ -185,10 +185,11 @@ class DiffNormEngine:
         t = self.ws.get(key)
         want = max(rows, self._reserve_rows) if frames else rows  # frames=True: rows scale with B*T
         if t is None or t.shape[0] < rows:
+            if t is not None:  # replacing a buffer: captured graphs hold the old pointer
+                self._graphs.clear()
+                self._graph_kernels.clear()
             t = torch.zeros(want, width, dtype=dtype, device=self.dev)
             self.ws[key] = t
-            self._graphs.clear()
-            self._graph_kernels.clear()
         return t[:rows]
 
     def reserve(self, max_rows: int):
@@ -385,6 +386,7 @@ class DiffNormEngine:
         if eps_q is None:
             eps_q = torch.randn(B, T, z, device=self.dev, dtype=f32)
         graph = self._ddim_graph(B, T) if (use_graph and sampler == "ddim" and start_step > 2) else None
+        graph_kernels = self._graph_kernels.get(("ddim", B, T), 0)
         lens = self.buf("s.len", B, 1, i32, frames=False).view(-1)
         lens.copy_(lengths)
         out = {}
@@ -407,7 +409,7 @@ class DiffNormEngine:
             for _ in range(n):
                 if graph is not None:
                     graph.replay()
-                    self.replayed_kernels += self._graph_kernels[("ddim", B, T)]
+                    self.replayed_kernels += graph_kernels
                 else:
                     self._ddim_step(B, T)
             calls = n
