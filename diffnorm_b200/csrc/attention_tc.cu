@@ -4,19 +4,23 @@
 //   warp 0      TMA producer : Q once, then K_j / V_j tiles (box {64 dh, 128 frames, 1 utt} of the [3*H*dh, T, B] map)
 //   warp 1      MMA issuer   : S_j = Q K_j^T  (M128 N128 K64, both K-major)  ->  TMEM cols [0,128)
 //                              O_j = P_j V_j  (M128 N64 K128, A = P from smem, B = V MN-major) -> TMEM cols [128,192)
-//   warps 2..5  softmax      : one query row per thread (tcgen05.ld 32x32b): no shuffles; two passes over S_j in
-//                              TMEM (row max, then exp2 / row sum / bf16 P written to smem in the UMMA 128B-swizzle
-//                              layout); running (m, l) and the fp32 output row live in registers:
-//                              O = O * alpha_j + O_j after each block.
+//   warps 2..9  softmax      : two threads per query row (tcgen05.ld 32x32b; warps w and w+4 share rows and split the
+//                              128 key columns / 64 output columns): two passes over S_j in TMEM (row max with one
+//                              smem exchange, then exp2 / row sum / bf16 P written to smem in the UMMA 128B-swizzle
+//                              layout, packed f32x2 FFMA2/FADD2 + FMNMX3 + MUFU.EX2); running (m, l) and the fp32
+//                              output half-row live in registers: O = O * alpha_j + O_j after each block.
 // Keys j >= lengths[b] get exactly zero weight (LM:333-335); key blocks past the length are skipped.
 #include "common.cuh"
 
 namespace dn {
 
+struct FalseTag { static constexpr bool value = false; };
+struct TrueTag { static constexpr bool value = true; };
+
 constexpr int TA_BM = 128, TA_BN = 128, TA_DH = 64;
-constexpr int TA_THREADS = 192;
+constexpr int TA_THREADS = 320;                           // TMA warp + MMA warp + 8 softmax warps
 constexpr int TA_TILE = TA_BM * TA_DH * 2;                  // 16 KB: Q, K, V tiles and each 64-key half of P
-constexpr int TA_SMEM = 5 * TA_TILE + 1024 + 128;           // Q, K, V, P(2) + align slack + barriers
+constexpr int TA_SMEM = 5 * TA_TILE + 1024 + 128 + 6 * 128 * 4;  // Q, K, V, P(2) + align slack + barriers + exchange
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -73,6 +77,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     uint64_t* o_full = bars + 7;
     uint64_t* o_empty = bars + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* xmax = reinterpret_cast<float*>(bars + 16);   // [2 parities][2 halves][128 rows] partial row maxima
+    float* lsum = xmax + 4 * TA_BM;                      // [2 halves][128 rows] partial row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * TA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -89,9 +95,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         mbar_init(v_full, 1);
         mbar_init(v_empty, 1);
         mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(p_full, 256);
         mbar_init(o_full, 1);
-        mbar_init(o_empty, 128);
+        mbar_init(o_empty, 256);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -154,50 +160,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             }
         }
     } else {
-        // ------------------------------------------------------------------ softmax + output: one row per thread
+        // ------------------------------------------------------------------ softmax + output: two threads per row
+        // warps 2..5 own key columns [0,64) of each block and output columns [0,32); warps 6..9 the other halves.
+        // (A warp may only touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 share rows and split columns.)
         const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        uint64_t o2[TA_DH / 2];  // fp32 output row as packed f32x2 pairs (FFMA2)
+        uint64_t o2[TA_DH / 4];  // this thread's 32 fp32 output columns as packed f32x2 pairs (FFMA2)
 #pragma unroll
-        for (int i = 0; i < TA_DH / 2; ++i) o2[i] = 0ull;
+        for (int i = 0; i < TA_DH / 4; ++i) o2[i] = 0ull;
         float m = -INFINITY, l = 0.f;
-        uint8_t* prow = sP + row * 128;
+        uint8_t* prow = sP + half * TA_TILE + row * 128;  // my 64-key half of the P tile
         const int sw = row & 7;
         const uint64_t scale2 = pack2(scale_log2, scale_log2);
-        for (int j = 0; j < nkb; ++j) {
+        // Only the last key block of an utterance can contain masked keys: the block body is instantiated twice so
+        // the hot (unmasked) copy carries no predicated compare/select instructions at all.
+        auto block = [&](const int j, auto masked_tag) {
+            constexpr bool masked = decltype(masked_tag)::value;
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            const int kbase = j * TA_BN;
-            const bool masked = kbase + TA_BN > len;  // only the last key block of an utterance needs masking
-            // pass 1: row max (4 independent FMNMX3 chains)
+            const int kbase = j * TA_BN + half * 64;
+            // pass 1: max over my 64 columns, then exchange with the partner thread of this row
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
-                float s[64];
-                tmem_ld64(tS + lane_off + c * 64, s);
+                float s[32];
+                tmem_ld32(tS + lane_off + half * 64 + c * 32, s);
                 tmem_ld_wait();
-                if (masked) {
+                if constexpr (masked) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) s[i] = (kbase + c * 64 + i < len) ? s[i] : -INFINITY;
+                    for (int i = 0; i < 32; ++i) s[i] = (kbase + c * 32 + i < len) ? s[i] : -INFINITY;
                 }
 #pragma unroll
-                for (int i = 0; i < 64; i += 2) mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], s[i], s[i + 1]);
+                for (int i = 0; i < 32; i += 2) mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], s[i], s[i + 1]);
             }
-            const float mxx = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            float mxx = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            xmax[((j & 1) * 2 + half) * TA_BM + row] = mxx;
+            named_bar_sync(1, 256);
+            mxx = fmaxf(mxx, xmax[((j & 1) * 2 + (half ^ 1)) * TA_BM + row]);
             const float mn = fmaxf(m, mxx * scale_log2);   // finite: every processed block has a valid key
             const float alpha = ex2_approx(m - mn);
             m = mn;
             const uint64_t nmn2 = pack2(-mn, -mn);
-            // pass 2: p = exp2(s * scale - m), row sum, bf16 P into the swizzled A-operand tile
+            // pass 2: p = exp2(s * scale - m), partial row sum, bf16 P into the swizzled A-operand tile
             uint64_t rs2[2] = {0ull, 0ull};
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
-                float s[64];
-                tmem_ld64(tS + lane_off + c * 64, s);
+                float s[32];
+                tmem_ld32(tS + lane_off + half * 64 + c * 32, s);
                 tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
+                for (int g = 0; g < 4; ++g) {
                     uint32_t w[4];
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
@@ -205,17 +219,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                         unpack2(ffma2(pack2(s[g * 8 + i], s[g * 8 + i + 1]), scale2, nmn2), e0, e1);
                         e0 = ex2_approx(e0);
                         e1 = ex2_approx(e1);
-                        if (masked) {
-                            const int key = kbase + c * 64 + g * 8 + i;
+                        if constexpr (masked) {
+                            const int key = kbase + c * 32 + g * 8 + i;
                             e0 = (key < len) ? e0 : 0.f;
                             e1 = (key + 1 < len) ? e1 : 0.f;
                         }
                         rs2[(i >> 1) & 1] = fadd2(rs2[(i >> 1) & 1], pack2(e0, e1));
                         w[i >> 1] = pack_bf16(e0, e1);
                     }
-                    const int chunk = c * 8 + g;  // 16-byte chunk (8 keys) within the 128-key row
-                    uint8_t* dst = prow + (chunk >> 3) * TA_TILE + (((chunk & 7) ^ sw) << 4);
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                    const int chunk = c * 4 + g;  // 16-byte chunk (8 keys) within my 64-key half row
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
             float r0, r1, r2, r3;
@@ -225,26 +238,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             tc_fence_before();          // S_j reads done before the next S MMA overwrites it
             fence_proxy_async_smem();   // generic-proxy P stores -> visible to the tensor core (async proxy)
             mbar_arrive(p_full);
-            // accumulate O_j
+            // accumulate my 32 columns of O_j
             const uint64_t alpha2 = pack2(alpha, alpha);
             mbar_wait(o_full, j & 1);
             tc_fence_after();
             {
-                float pv[TA_DH];
-                tmem_ld64(tO + lane_off, pv);
+                float pv[32];
+                tmem_ld32(tO + lane_off + half * 32, pv);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < TA_DH; i += 2) o2[i >> 1] = ffma2(o2[i >> 1], alpha2, pack2(pv[i], pv[i + 1]));
+                for (int i = 0; i < 32; i += 2) o2[i >> 1] = ffma2(o2[i >> 1], alpha2, pack2(pv[i], pv[i + 1]));
             }
             tc_fence_before();
             mbar_arrive(o_empty);
-        }
+        };
+        const int n_full = len / TA_BN;  // key blocks without any masked key
+        for (int j = 0; j < n_full; ++j) block(j, FalseTag{});
+        if (n_full < nkb) block(n_full, TrueTag{});
+        // combine the two partial row sums, normalise, store my 32 output columns
+        lsum[half * TA_BM + row] = l;
+        named_bar_sync(2, 256);
+        l += lsum[(half ^ 1) * TA_BM + row];
         const int t = q0 + row;
         if (t < T) {
             const float inv = l > 0.f ? 1.f / l : 0.f;
-            __nv_bfloat16* op = out + ((long long)b * T + t) * (H * TA_DH) + h * TA_DH;
+            __nv_bfloat16* op = out + ((long long)b * T + t) * (H * TA_DH) + h * TA_DH + half * 32;
 #pragma unroll
-            for (int i = 0; i < TA_DH / 2; i += 4) {
+            for (int i = 0; i < TA_DH / 4; i += 4) {
                 uint32_t w[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {

@@ -187,6 +187,7 @@ class GemmPlan:
         self.W, self.segs, self.n_out, self.n_tiles, self.epi = W, [tuple(s) for s in segs], n_out, n_tiles, epi
         self.bias, self.bias2, self.groups, self.g_w_row, self.g_bias = bias, bias2, groups, g_w_row, g_bias
         self.dilation, self.dilation_shl_group, self.name = dilation, dilation_shl_group, name
+        self._flat_ok = groups == 1 and all(sg[1] == 0 for sg in self.segs)
 
     def to(self, device):
         self.W = self.W.to(device)
@@ -198,6 +199,10 @@ class GemmPlan:
             g_gb: int = 0, gb_half: int = 0, t_idx=None, t_idx_stride: int = 0, pe=None, lengths=None,
             epi: Optional[int] = None, impl: int = _lib.GEMM_TCGEN05, a_cols: Optional[int] = None):
         epi = self.epi if epi is None else epi
+        if self._flat_ok and gb is None and pe is None:
+            # no frame shifts and no per-utterance epilogue inputs: treat the batch as one long utterance so M tiles
+            # run across utterance boundaries (T = 1000 would otherwise waste 24 of every 1024 tile rows)
+            B, T = 1, B * T
         _chk(A, bf16, "A")
         _chk(out, f32 if epi in (_lib.EPI_F32, _lib.EPI_RESID) else bf16, "out")
         d = GemmDesc()
