@@ -72,10 +72,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     uint64_t* k_empty = bars + 2;
     uint64_t* v_full = bars + 3;
     uint64_t* v_empty = bars + 4;
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;
-    uint64_t* o_full = bars + 7;
-    uint64_t* o_empty = bars + 8;
+    uint64_t* s_full = bars + 5;   // S_j complete in TMEM
+    uint64_t* s_free = bars + 6;   // S_j copied to registers by all softmax threads -> S_{j+1} may overwrite it
+    uint64_t* p_full = bars + 7;   // P_j in smem (and O rescaled if needed) -> PV_j may be issued
+    uint64_t* p_empty = bars + 8;  // PV_j complete: P buffer reusable, O stable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     float* xmax = reinterpret_cast<float*>(bars + 16);   // [2 parities][2 halves][128 rows] partial row maxima
     float* lsum = xmax + 4 * TA_BM;                      // [2 halves][128 rows] partial row sums
@@ -95,9 +95,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         mbar_init(v_full, 1);
         mbar_init(v_empty, 1);
         mbar_init(s_full, 1);
+        mbar_init(s_free, 256);
         mbar_init(p_full, 256);
-        mbar_init(o_full, 1);
-        mbar_init(o_empty, 256);
+        mbar_init(p_empty, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -142,8 +142,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             mbar_wait(q_full, 0);
             issue_s(0);
             for (int j = 0; j < nkb; ++j) {
-                mbar_wait(p_full, j & 1);            // P_j written, S_j fully read
-                if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+                if (j + 1 < nkb) {
+                    // S_{j+1} as soon as the softmax threads hold S_j in registers: it runs under their exp phase
+                    mbar_wait(s_free, j & 1);
+                    issue_s(j + 1);
+                }
+                mbar_wait(p_full, j & 1);            // P_j written (and O rescaled when the row max jumped)
                 mbar_wait(v_full, j & 1);
                 tc_fence_after();
 #pragma unroll
@@ -152,24 +156,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                     const uint64_t a = dp + (uint64_t)(((k >> 2) * TA_TILE + (k & 3) * 32) >> 4);
                     // B = V (MN-major): 16 keys = 16 rows of 128 B per k-step
                     const uint64_t bb = dv + (uint64_t)((k * 16 * 128) >> 4);
-                    umma_bf16(tO, a, bb, id_o, k > 0);
+                    umma_bf16(tO, a, bb, id_o, (j > 0) || (k > 0));   // O accumulates in TMEM over all key blocks
                 }
                 umma_commit(v_empty);
-                umma_commit(o_full);
-                if (j + 1 < nkb) issue_s(j + 1);
+                umma_commit(p_empty);
             }
         }
     } else {
-        // ------------------------------------------------------------------ softmax + output: two threads per row
+        // ------------------------------------------------------------------ softmax: two threads per query row
         // warps 2..5 own key columns [0,64) of each block and output columns [0,32); warps 6..9 the other halves.
         // (A warp may only touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 share rows and split columns.)
+        // TMEM reads are the scarce resource here (64 B/clk/SM): S_j is read ONCE into 64 registers per thread, and
+        // O stays in TMEM, accumulated by the MMA itself.  The running max m is only raised when a block's max
+        // exceeds it by more than 2^RESCALE_LOG2 (P then stays <= 2^8, exact in fp32 sums / bf16 relative
+        // precision); only then is O rescaled in TMEM (tcgen05.ld -> mul -> tcgen05.st), which is rare.
+        constexpr float RESCALE_LOG2 = 8.f;
         const int qd = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        uint64_t o2[TA_DH / 4];  // this thread's 32 fp32 output columns as packed f32x2 pairs (FFMA2)
-#pragma unroll
-        for (int i = 0; i < TA_DH / 4; ++i) o2[i] = 0ull;
         float m = -INFINITY, l = 0.f;
         uint8_t* prow = sP + half * TA_TILE + row * 128;  // my 64-key half of the P tile
         const int sw = row & 7;
@@ -178,79 +183,84 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         // the hot (unmasked) copy carries no predicated compare/select instructions at all.
         auto block = [&](const int j, auto masked_tag) {
             constexpr bool masked = decltype(masked_tag)::value;
+            float s0[32], s1[32];
             mbar_wait(s_full, j & 1);
             tc_fence_after();
+            tmem_ld32(tS + lane_off + half * 64, s0);
+            tmem_ld32(tS + lane_off + half * 64 + 32, s1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
             const int kbase = j * TA_BN + half * 64;
-            // pass 1: max over my 64 columns, then exchange with the partner thread of this row
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float s[32];
-                tmem_ld32(tS + lane_off + half * 64 + c * 32, s);
-                tmem_ld_wait();
-                if constexpr (masked) {
+            if constexpr (masked) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) s[i] = (kbase + c * 32 + i < len) ? s[i] : -INFINITY;
+                for (int i = 0; i < 32; ++i) {
+                    s0[i] = (kbase + i < len) ? s0[i] : -INFINITY;
+                    s1[i] = (kbase + 32 + i < len) ? s1[i] : -INFINITY;
                 }
+            }
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) mx[(i >> 1) & 3] = max3(mx[(i >> 1) & 3], s[i], s[i + 1]);
+            for (int i = 0; i < 32; i += 2) {
+                mx[(i >> 1) & 1] = max3(mx[(i >> 1) & 1], s0[i], s0[i + 1]);
+                mx[2 + ((i >> 1) & 1)] = max3(mx[2 + ((i >> 1) & 1)], s1[i], s1[i + 1]);
             }
             float mxx = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
             xmax[((j & 1) * 2 + half) * TA_BM + row] = mxx;
             named_bar_sync(1, 256);
             mxx = fmaxf(mxx, xmax[((j & 1) * 2 + (half ^ 1)) * TA_BM + row]);
-            const float mn = fmaxf(m, mxx * scale_log2);   // finite: every processed block has a valid key
-            const float alpha = ex2_approx(m - mn);
-            m = mn;
-            const uint64_t nmn2 = pack2(-mn, -mn);
-            // pass 2: p = exp2(s * scale - m), partial row sum, bf16 P into the swizzled A-operand tile
-            uint64_t rs2[2] = {0ull, 0ull};
+            const float mxs = mxx * scale_log2;            // finite: every processed block has a valid key
+            const bool raise = mxs > m + RESCALE_LOG2;     // j == 0: m = -inf -> true
+            if (j > 0) {
+                mbar_wait(p_empty, (j - 1) & 1);           // PV_{j-1} done: P buffer free, O stable
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, raise)) {
+                    const float a = raise ? ex2_approx(m - mxs) : 1.f;
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float s[32];
-                tmem_ld32(tS + lane_off + half * 64 + c * 32, s);
-                tmem_ld_wait();
+                    for (int c8 = 0; c8 < 32; c8 += 8) {
+                        float o[8];
+                        tmem_ld8(tO + lane_off + half * 32 + c8, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] *= a;
+                        tmem_st8(tO + lane_off + half * 32 + c8, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            if (raise) {
+                l *= ex2_approx(m - mxs);                  // j == 0: l = 0 * 0
+                m = mxs;
+            }
+            const uint64_t nm2 = pack2(-m, -m);
+            // p = exp2(s * scale - m), partial row sum, bf16 P into the swizzled A-operand tile
+            uint64_t rs2[2] = {0ull, 0ull};
+            auto half_row = [&](const float (&s)[32], const int c) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t w[4];
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
                         float e0, e1;
-                        unpack2(ffma2(pack2(s[g * 8 + i], s[g * 8 + i + 1]), scale2, nmn2), e0, e1);
-                        e0 = ex2_approx(e0);
+                        unpack2(ffma2(pack2(s[g * 8 + i], s[g * 8 + i + 1]), scale2, nm2), e0, e1);
+                        e0 = ex2_approx(e0);   // masked keys: ex2(-inf) = +0
                         e1 = ex2_approx(e1);
-                        if constexpr (masked) {
-                            const int key = kbase + c * 32 + g * 8 + i;
-                            e0 = (key < len) ? e0 : 0.f;
-                            e1 = (key + 1 < len) ? e1 : 0.f;
-                        }
                         rs2[(i >> 1) & 1] = fadd2(rs2[(i >> 1) & 1], pack2(e0, e1));
                         w[i >> 1] = pack_bf16(e0, e1);
                     }
                     const int chunk = c * 4 + g;  // 16-byte chunk (8 keys) within my 64-key half row
                     *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-            }
+            };
+            half_row(s0, 0);
+            half_row(s1, 1);
             float r0, r1, r2, r3;
             unpack2(rs2[0], r0, r1);
             unpack2(rs2[1], r2, r3);
-            l = fmaf(l, alpha, (r0 + r1) + (r2 + r3));
-            tc_fence_before();          // S_j reads done before the next S MMA overwrites it
+            l += (r0 + r1) + (r2 + r3);
+            tc_fence_before();          // TMEM reads / O rescale ordered before the MMA that follows the barrier
             fence_proxy_async_smem();   // generic-proxy P stores -> visible to the tensor core (async proxy)
             mbar_arrive(p_full);
-            // accumulate my 32 columns of O_j
-            const uint64_t alpha2 = pack2(alpha, alpha);
-            mbar_wait(o_full, j & 1);
-            tc_fence_after();
-            {
-                float pv[32];
-                tmem_ld32(tO + lane_off + half * 32, pv);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) o2[i >> 1] = ffma2(o2[i >> 1], alpha2, pack2(pv[i], pv[i + 1]));
-            }
-            tc_fence_before();
-            mbar_arrive(o_empty);
         };
         const int n_full = len / TA_BN;  // key blocks without any masked key
         for (int j = 0; j < n_full; ++j) block(j, FalseTag{});
@@ -260,20 +270,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         named_bar_sync(2, 256);
         l += lsum[(half ^ 1) * TA_BM + row];
         const int t = q0 + row;
-        if (t < T) {
-            const float inv = l > 0.f ? 1.f / l : 0.f;
+        if (nkb > 0) {
+            mbar_wait(p_empty, (nkb - 1) & 1);   // last PV complete
+            tc_fence_after();
+            float o[32];
+            tmem_ld32(tO + lane_off + half * 32, o);
+            tmem_ld_wait();
+            if (t < T) {
+                const float inv = l > 0.f ? 1.f / l : 0.f;
+                __nv_bfloat16* op = out + ((long long)b * T + t) * (H * TA_DH) + h * TA_DH + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    *reinterpret_cast<uint4*>(op + i) =
+                        make_uint4(pack_bf16(o[i] * inv, o[i + 1] * inv), pack_bf16(o[i + 2] * inv, o[i + 3] * inv),
+                                   pack_bf16(o[i + 4] * inv, o[i + 5] * inv), pack_bf16(o[i + 6] * inv, o[i + 7] * inv));
+                }
+            }
+        } else if (t < T) {
             __nv_bfloat16* op = out + ((long long)b * T + t) * (H * TA_DH) + h * TA_DH + half * 32;
 #pragma unroll
-            for (int i = 0; i < TA_DH / 4; i += 4) {
-                uint32_t w[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float a, bb;
-                    unpack2(o2[i + k], a, bb);
-                    w[k] = pack_bf16(a * inv, bb * inv);
-                }
-                *reinterpret_cast<uint4*>(op + i * 2) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(op + i) = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     tc_fence_before();
