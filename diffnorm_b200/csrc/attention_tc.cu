@@ -2,13 +2,15 @@
 //
 // One CTA = 128 queries of one (utterance, head); 2 CTAs per SM hide each other's softmax / MMA latency.
 //   warp 0      TMA producer : Q once, then K_j / V_j tiles (box {64 dh, 128 frames, 1 utt} of the [3*H*dh, T, B] map)
-//   warp 1      MMA issuer   : S_j = Q K_j^T  (M128 N128 K64, both K-major)  ->  TMEM cols [0,128)
-//                              O_j = P_j V_j  (M128 N64 K128, A = P from smem, B = V MN-major) -> TMEM cols [128,192)
-//   warps 2..9  softmax      : two threads per query row (tcgen05.ld 32x32b; warps w and w+4 share rows and split the
-//                              128 key columns / 64 output columns): two passes over S_j in TMEM (row max with one
-//                              smem exchange, then exp2 / row sum / bf16 P written to smem in the UMMA 128B-swizzle
-//                              layout, packed f32x2 FFMA2/FADD2 + FMNMX3 + MUFU.EX2); running (m, l) and the fp32
-//                              output half-row live in registers: O = O * alpha_j + O_j after each block.
+//   warp 1      MMA issuer   : S_j = Q K_j^T  (M128 N128 K64, both K-major)            -> TMEM cols [0,128)
+//                              O  += P_j V_j  (M128 N64 K128, A = P from TMEM, B = V MN-major) -> TMEM cols [128,192)
+//                              S_{j+1} is issued as soon as the softmax threads hold S_j in registers.
+//   warps 2..9  softmax      : two threads per query row (warps w and w+4 share rows and split the 128 key columns /
+//                              64 output columns).  S_j is read from TMEM once (TMEM reads are 64 B/clk/SM); row max
+//                              with one smem exchange; exp2 / row sum with packed f32x2 FFMA2/FADD2 + FMNMX3 +
+//                              MUFU.EX2; P_j goes back to TMEM as packed bf16 (cols [192,256)); O accumulates in TMEM
+//                              and is only rescaled when the running max jumps by more than 2^8 (lazy rescale).
+//   K and V tiles are double buffered in smem (5 x 16 KB with Q).
 // Keys j >= lengths[b] get exactly zero weight (LM:333-335); key blocks past the length are skipped.
 #include "common.cuh"
 
@@ -19,8 +21,8 @@ struct TrueTag { static constexpr bool value = true; };
 
 constexpr int TA_BM = 128, TA_BN = 128, TA_DH = 64;
 constexpr int TA_THREADS = 320;                           // TMA warp + MMA warp + 8 softmax warps
-constexpr int TA_TILE = TA_BM * TA_DH * 2;                  // 16 KB: Q, K, V tiles and each 64-key half of P
-constexpr int TA_SMEM = 5 * TA_TILE + 1024 + 128 + 6 * 128 * 4;  // Q, K, V, P(2) + align slack + barriers + exchange
+constexpr int TA_TILE = TA_BM * TA_DH * 2;                  // 16 KB: Q and each K / V stage
+constexpr int TA_SMEM = 5 * TA_TILE + 1024 + 128 + 6 * 128 * 4;  // Q, K(2), V(2) + align slack + barriers + exchange
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -63,20 +65,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     extern __shared__ uint8_t ta_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ta_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;
-    uint8_t* sK = smem + TA_TILE;
-    uint8_t* sV = smem + 2 * TA_TILE;
-    uint8_t* sP = smem + 3 * TA_TILE;  // two 64-key halves, 16 KB each
+    uint8_t* sK = smem + TA_TILE;      // two stages
+    uint8_t* sV = smem + 3 * TA_TILE;  // two stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TA_TILE);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;
-    uint64_t* k_empty = bars + 2;
-    uint64_t* v_full = bars + 3;
-    uint64_t* v_empty = bars + 4;
-    uint64_t* s_full = bars + 5;   // S_j complete in TMEM
-    uint64_t* s_free = bars + 6;   // S_j copied to registers by all softmax threads -> S_{j+1} may overwrite it
-    uint64_t* p_full = bars + 7;   // P_j in smem (and O rescaled if needed) -> PV_j may be issued
-    uint64_t* p_empty = bars + 8;  // PV_j complete: P buffer reusable, O stable
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;    // S_j complete in TMEM
+    uint64_t* s_free = bars + 10;   // S_j copied to registers by all softmax threads -> S_{j+1} may overwrite it
+    uint64_t* p_full = bars + 11;   // P_j in TMEM (and O rescaled if needed) -> PV_j may be issued
+    uint64_t* p_empty = bars + 12;  // PV_j complete: P columns reusable, O stable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     float* xmax = reinterpret_cast<float*>(bars + 16);   // [2 parities][2 halves][128 rows] partial row maxima
     float* lsum = xmax + 4 * TA_BM;                      // [2 halves][128 rows] partial row sums
 
@@ -90,10 +91,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         mbar_init(q_full, 1);
-        mbar_init(k_full, 1);
-        mbar_init(k_empty, 1);
-        mbar_init(v_full, 1);
-        mbar_init(v_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(k_full + i, 1);
+            mbar_init(k_empty + i, 1);
+            mbar_init(v_full + i, 1);
+            mbar_init(v_empty + i, 1);
+        }
         mbar_init(s_full, 1);
         mbar_init(s_free, 256);
         mbar_init(p_full, 256);
@@ -108,35 +111,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+    // TMEM columns: S fp32 [0,128) | O fp32 [128,192) | P bf16x2 [192,256) (two keys per 32-bit column)
+    const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
 
     if (warp == 0) {
         if (lane == 0 && nkb > 0) {
             mbar_expect_tx(q_full, TA_TILE);
             tma_load_3d(&tmQKV, q_full, sQ, qcol, q0, b);
             for (int j = 0; j < nkb; ++j) {
-                const uint32_t ph = j & 1;
-                mbar_wait(k_empty, ph ^ 1);
-                mbar_expect_tx(k_full, TA_TILE);
-                tma_load_3d(&tmQKV, k_full, sK, kcol, j * TA_BN, b);
-                mbar_wait(v_empty, ph ^ 1);
-                mbar_expect_tx(v_full, TA_TILE);
-                tma_load_3d(&tmQKV, v_full, sV, vcol, j * TA_BN, b);
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(k_empty + st, ph ^ 1);
+                mbar_expect_tx(k_full + st, TA_TILE);
+                tma_load_3d(&tmQKV, k_full + st, sK + st * TA_TILE, kcol, j * TA_BN, b);
+                mbar_wait(v_empty + st, ph ^ 1);
+                mbar_expect_tx(v_full + st, TA_TILE);
+                tma_load_3d(&tmQKV, v_full + st, sV + st * TA_TILE, vcol, j * TA_BN, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
             const uint32_t id_s = ta_idesc(TA_BN, 0), id_o = ta_idesc(TA_DH, 1);
             const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
-            const uint64_t dk = umma_desc_sw128(smem_u32(sK));
-            const uint64_t dv = umma_desc_sw128(smem_u32(sV));   // MN-major: 8-key groups 1024 B apart (SBO)
-            const uint64_t dp = umma_desc_sw128(smem_u32(sP));
             auto issue_s = [&](int j) {
-                mbar_wait(k_full, j & 1);
+                const int st = j & 1;
+                mbar_wait(k_full + st, (j >> 1) & 1);
                 tc_fence_after();
+                const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * TA_TILE));
 #pragma unroll
                 for (int k = 0; k < TA_DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, id_s, k > 0);
-                umma_commit(k_empty);
+                umma_commit(k_empty + st);
                 umma_commit(s_full);
             };
             mbar_wait(q_full, 0);
@@ -147,18 +151,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                     mbar_wait(s_free, j & 1);
                     issue_s(j + 1);
                 }
-                mbar_wait(p_full, j & 1);            // P_j written (and O rescaled when the row max jumped)
-                mbar_wait(v_full, j & 1);
+                const int st = j & 1;
+                mbar_wait(p_full, j & 1);            // P_j in TMEM (and O rescaled when the row max jumped)
+                mbar_wait(v_full + st, (j >> 1) & 1);
                 tc_fence_after();
+                const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * TA_TILE));  // MN-major: 8-key groups 1 KB apart
 #pragma unroll
                 for (int k = 0; k < TA_BN / 16; ++k) {
-                    // A = P: 64-key halves 16 KB apart, 32 B per k-step inside a half
-                    const uint64_t a = dp + (uint64_t)(((k >> 2) * TA_TILE + (k & 3) * 32) >> 4);
-                    // B = V (MN-major): 16 keys = 16 rows of 128 B per k-step
-                    const uint64_t bb = dv + (uint64_t)((k * 16 * 128) >> 4);
-                    umma_bf16(tO, a, bb, id_o, (j > 0) || (k > 0));   // O accumulates in TMEM over all key blocks
+                    // A = P from TMEM: 16 keys = 8 columns per k-step; B = V (MN-major): 16 rows of 128 B per k-step
+                    umma_bf16_ts(tO, tP + 8 * k, dv + (uint64_t)((k * 16 * 128) >> 4), id_o, (j > 0) || (k > 0));
                 }
-                umma_commit(v_empty);
+                umma_commit(v_empty + st);
                 umma_commit(p_empty);
             }
         }
@@ -166,18 +169,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         // ------------------------------------------------------------------ softmax: two threads per query row
         // warps 2..5 own key columns [0,64) of each block and output columns [0,32); warps 6..9 the other halves.
         // (A warp may only touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 share rows and split columns.)
-        // TMEM reads are the scarce resource here (64 B/clk/SM): S_j is read ONCE into 64 registers per thread, and
-        // O stays in TMEM, accumulated by the MMA itself.  The running max m is only raised when a block's max
-        // exceeds it by more than 2^RESCALE_LOG2 (P then stays <= 2^8, exact in fp32 sums / bf16 relative
-        // precision); only then is O rescaled in TMEM (tcgen05.ld -> mul -> tcgen05.st), which is rare.
+        // S_j is read ONCE into 64 registers per thread; P_j goes back to TMEM as packed bf16 (the PV MMA reads its
+        // A operand from TMEM, so there is no smem round trip and no proxy fence); O stays in TMEM, accumulated by the
+        // MMA itself.  The running max m is only raised when a block's max exceeds it by more than 2^RESCALE_LOG2
+        // (P then stays <= 2^8: exact in fp32 sums, same relative precision in bf16); only then is O rescaled in
+        // TMEM (tcgen05.ld -> mul -> tcgen05.st), which is rare after the first block.
         constexpr float RESCALE_LOG2 = 8.f;
         const int qd = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         float m = -INFINITY, l = 0.f;
-        uint8_t* prow = sP + half * TA_TILE + row * 128;  // my 64-key half of the P tile
-        const int sw = row & 7;
         const uint64_t scale2 = pack2(scale_log2, scale_log2);
         // Only the last key block of an utterance can contain masked keys: the block body is instantiated twice so
         // the hot (unmasked) copy carries no predicated compare/select instructions at all.
@@ -211,11 +213,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             mxx = fmaxf(mxx, xmax[((j & 1) * 2 + (half ^ 1)) * TA_BM + row]);
             const float mxs = mxx * scale_log2;            // finite: every processed block has a valid key
             const bool raise = mxs > m + RESCALE_LOG2;     // j == 0: m = -inf -> true
+            const float m_old = m;
+            if (raise) {
+                l *= ex2_approx(m - mxs);                  // j == 0: l = 0 * 0
+                m = mxs;
+            }
+            const uint64_t nm2 = pack2(-m, -m);
+            // p = exp2(s * scale - m), partial row sum, packed bf16 pairs
+            uint64_t rs2[2] = {0ull, 0ull};
+            auto half_row = [&](const float (&s)[32], uint32_t (&w)[16]) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float e0, e1;
+                    unpack2(ffma2(pack2(s[i], s[i + 1]), scale2, nm2), e0, e1);
+                    e0 = ex2_approx(e0);   // masked keys: ex2(-inf) = +0
+                    e1 = ex2_approx(e1);
+                    rs2[(i >> 1) & 1] = fadd2(rs2[(i >> 1) & 1], pack2(e0, e1));
+                    w[i >> 1] = pack_bf16(e0, e1);
+                }
+            };
+            uint32_t w0[16], w1[16];
+            half_row(s0, w0);
             if (j > 0) {
-                mbar_wait(p_empty, (j - 1) & 1);           // PV_{j-1} done: P buffer free, O stable
+                mbar_wait(p_empty, (j - 1) & 1);           // PV_{j-1} done: P columns free, O stable
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, raise)) {
-                    const float a = raise ? ex2_approx(m - mxs) : 1.f;
+                    const float a = raise ? ex2_approx(m_old - m) : 1.f;
 #pragma unroll 1
                     for (int c8 = 0; c8 < 32; c8 += 8) {
                         float o[8];
@@ -225,41 +248,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                         for (int i = 0; i < 8; ++i) o[i] *= a;
                         tmem_st8(tO + lane_off + half * 32 + c8, o);
                     }
-                    tmem_st_wait();
                 }
             }
-            if (raise) {
-                l *= ex2_approx(m - mxs);                  // j == 0: l = 0 * 0
-                m = mxs;
-            }
-            const uint64_t nm2 = pack2(-m, -m);
-            // p = exp2(s * scale - m), partial row sum, bf16 P into the swizzled A-operand tile
-            uint64_t rs2[2] = {0ull, 0ull};
-            auto half_row = [&](const float (&s)[32], const int c) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int i = 0; i < 8; i += 2) {
-                        float e0, e1;
-                        unpack2(ffma2(pack2(s[g * 8 + i], s[g * 8 + i + 1]), scale2, nm2), e0, e1);
-                        e0 = ex2_approx(e0);   // masked keys: ex2(-inf) = +0
-                        e1 = ex2_approx(e1);
-                        rs2[(i >> 1) & 1] = fadd2(rs2[(i >> 1) & 1], pack2(e0, e1));
-                        w[i >> 1] = pack_bf16(e0, e1);
-                    }
-                    const int chunk = c * 4 + g;  // 16-byte chunk (8 keys) within my 64-key half row
-                    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            };
-            half_row(s0, 0);
-            half_row(s1, 1);
+            tmem_st16(tP + lane_off + half * 32, w0);
+            half_row(s1, w1);
+            tmem_st16(tP + lane_off + half * 32 + 16, w1);
             float r0, r1, r2, r3;
             unpack2(rs2[0], r0, r1);
             unpack2(rs2[1], r2, r3);
             l += (r0 + r1) + (r2 + r3);
-            tc_fence_before();          // TMEM reads / O rescale ordered before the MMA that follows the barrier
-            fence_proxy_async_smem();   // generic-proxy P stores -> visible to the tensor core (async proxy)
+            tmem_st_wait();
+            tc_fence_before();          // TMEM reads / writes ordered before the MMA that follows the barrier
             mbar_arrive(p_full);
         };
         const int n_full = len / TA_BN;  // key blocks without any masked key
