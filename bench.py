@@ -26,6 +26,11 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# ncu --set full, gemm_tc_kernel<EPI_BF16> on the FFN causal conv at B 64 x T 1000 (profiles/r01_u1_gemm_layer_ncu_summary.txt):
+# dram__bytes_read.sum 192.19 MB + dram__bytes_write.sum 147.37 MB per launch (part of the 180 MB output is still in L2
+# when the kernel ends); algorithmic bytes = 180 MB bf16 A + 180 MB bf16 out + 12 MB weights.
+NCU_CONV_DRAM_BYTES = 192_193_024 + 147_372_032
+
 METRIC = "normalized frames/sec"
 UNIT = "frames/s"
 
@@ -259,7 +264,10 @@ def run_ours(args):
         all_gemm_ms = float(np.sum([m for _, m in times]))
         roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<EPI_BF16> (FFN causal conv k3 1365->1365 as implicit GEMM, "
                     "M=B*T, N=1365, K=4095)", "achieved": ach, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained bf16",
+                    "frac": ach / peaks["sustained"], "traffic": NCU_CONV_DRAM_BYTES if (B, T, z) == (64, 1000, 16) else None,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one ncu --set "
+                                      "full capture (profiles/r01_u1_gemm_layer_ncu_summary.txt); algorithmic A + out = 360 MB",
+                    "peak_source": peaks["source"] + " sustained bf16",
                     "launch_ms": conv_ms, "launches_timed": len(conv),
                     "transformer_gemm_ms_per_call": all_gemm_ms,
                     "whole_pass_tflops": fpf * B * T / (ms * 1e-3) / 1e12,

@@ -31,6 +31,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, i
 }
 
 // ---------------------------------------------------------------------------------------------- VAE reparam
+// Generic form (any z, either eps layout): one element per thread.
 __global__ void vae_reparam_kernel(const float* __restrict__ params, int ldp, const float* __restrict__ eps,
                                    int eps_cf, int B, int T, int z, float* __restrict__ out) {
     const long long total = (long long)B * T * z;
@@ -47,39 +48,64 @@ __global__ void vae_reparam_kernel(const float* __restrict__ params, int ldp, co
     }
 }
 
-// ---------------------------------------------------------------------------------------------- diffusion updates
-__device__ __forceinline__ void store_bf16_pad(__nv_bfloat16* xb, int ldx, long long r, int c, int z, float v) {
-    if (xb) xb[r * ldx + c] = __float2bfloat16(v);
-}
-
-__global__ void q_sample_kernel(const float* __restrict__ z_lat, const float* __restrict__ eps, float ca, float cb,
-                                long long rows, int z, float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int ldx) {
-    const int zc = xb ? ldx : z;  // iterate over padded width so the pad columns get zeroed
-    const long long total = rows * zc;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / zc;
-        const int c = (int)(i % zc);
-        if (c < z) {
-            const float v = ca * z_lat[r * z + c] + cb * eps[r * z + c];
-            x[r * z + c] = v;
-            store_bf16_pad(xb, ldx, r, c, z, v);
-        } else {
-            xb[r * ldx + c] = __float2bfloat16(0.f);
+// Channel-first eps [B, z, T] (the reference's draw order, distributions.py:38) against channel-last params / out:
+// a block transposes a {z x 32 frames} eps tile through smem so that both the eps reads (along t) and the
+// params / out accesses (along c, float4) are coalesced.  z % 4 == 0, z <= 128.
+constexpr int RP_TT = 32;
+__global__ void __launch_bounds__(EW_THREADS)
+vae_reparam_cf_kernel(const float* __restrict__ params, int ldp, const float* __restrict__ eps, int B, int T, int z,
+                      float* __restrict__ out) {
+    __shared__ float tile[128][RP_TT + 1];
+    const int tiles_t = (T + RP_TT - 1) / RP_TT;
+    for (int blk = blockIdx.x; blk < B * tiles_t; blk += gridDim.x) {
+        const int b = blk / tiles_t, t0 = (blk % tiles_t) * RP_TT;
+        __syncthreads();
+        for (int i = threadIdx.x; i < z * RP_TT; i += EW_THREADS) {
+            const int c = i / RP_TT, tt = i % RP_TT;
+            tile[c][tt] = (t0 + tt < T) ? eps[((long long)b * z + c) * T + t0 + tt] : 0.f;
+        }
+        __syncthreads();
+        const int zg = z / 4;
+        for (int i = threadIdx.x; i < RP_TT * zg; i += EW_THREADS) {
+            const int tt = i / zg, c = (i % zg) * 4;
+            if (t0 + tt >= T) continue;
+            const long long bt = (long long)b * T + t0 + tt;
+            const float4 mean = *reinterpret_cast<const float4*>(params + bt * ldp + c);
+            const float4 lv = *reinterpret_cast<const float4*>(params + bt * ldp + z + c);
+            float4 o;
+            o.x = mean.x + expf(0.5f * fminf(fmaxf(lv.x, -30.f), 20.f)) * tile[c + 0][tt];
+            o.y = mean.y + expf(0.5f * fminf(fmaxf(lv.y, -30.f), 20.f)) * tile[c + 1][tt];
+            o.z = mean.z + expf(0.5f * fminf(fmaxf(lv.z, -30.f), 20.f)) * tile[c + 2][tt];
+            o.w = mean.w + expf(0.5f * fminf(fmaxf(lv.w, -30.f), 20.f)) * tile[c + 3][tt];
+            *reinterpret_cast<float4*>(out + bt * z + c) = o;
         }
     }
 }
 
-__global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eh, int lde,
-                                 const float* __restrict__ table, const int* __restrict__ t_idx, long long rows, int z,
-                                 int mode, __nv_bfloat16* __restrict__ xb, int ldx) {
-    const float* cf = table + (long long)t_idx[0] * 8;
-    const float c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3], c4 = cf[4], c5 = cf[5];
-    const long long total = rows * z;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / z;
-        const int c = (int)(i % z);
-        const float xv = x[i];
-        const float e = eh[r * lde + c];
+// ---------------------------------------------------------------------------------------------- diffusion updates
+// All three updates process 4 latent channels per thread (16-byte loads / stores of the fp32 state, 8-byte stores of
+// the bf16 staging copy, whose pad columns [z, ldx) are rewritten with zeros).  z % 4 == 0, lde % 4 == 0, ldx % 4 == 0.
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(a, b), pack_bf16(c, d));
+}
+
+struct QSampleOp {
+    const float* __restrict__ z_lat;
+    const float* __restrict__ eps;
+    float ca, cb;
+    __device__ __forceinline__ float4 operator()(long long r, int c, int z, const float4& /*xv*/) const {
+        const float4 a = *reinterpret_cast<const float4*>(z_lat + r * z + c);
+        const float4 e = *reinterpret_cast<const float4*>(eps + r * z + c);
+        return make_float4(ca * a.x + cb * e.x, ca * a.y + cb * e.y, ca * a.z + cb * e.z, ca * a.w + cb * e.w);
+    }
+    static constexpr bool reads_x = false;
+};
+
+struct DdimOp {
+    const float* __restrict__ eh;
+    int lde, mode;
+    float c0, c1, c2, c3, c4, c5;
+    __device__ __forceinline__ float one(float xv, float e) const {
         float x0, pn;
         if (mode == 0) {  // LM:1422-1424 incl. safe_div clamps
             x0 = (xv - c1 * e) / fmaxf(c0, 1e-10f);
@@ -88,28 +114,72 @@ __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict_
             x0 = c4 * xv - c5 * e;
             pn = (c4 * xv - x0) / c5;
         }
-        const float v = x0 * c2 + c3 * pn;
-        x[i] = v;
-        store_bf16_pad(xb, ldx, r, c, z, v);
+        return x0 * c2 + c3 * pn;
+    }
+    __device__ __forceinline__ float4 operator()(long long r, int c, int /*z*/, const float4& xv) const {
+        const float4 e = *reinterpret_cast<const float4*>(eh + r * lde + c);
+        return make_float4(one(xv.x, e.x), one(xv.y, e.y), one(xv.z, e.z), one(xv.w, e.w));
+    }
+    static constexpr bool reads_x = true;
+};
+
+struct DdpmOp {
+    const float* __restrict__ eh;
+    const float* __restrict__ noise;
+    int lde;
+    float c0, c1, c2, c3, c4;
+    __device__ __forceinline__ float one(float xv, float e, float n) const {
+        const float x0 = c0 * xv - c1 * e;
+        return c2 * x0 + c3 * xv + c4 * n;
+    }
+    __device__ __forceinline__ float4 operator()(long long r, int c, int z, const float4& xv) const {
+        const float4 e = *reinterpret_cast<const float4*>(eh + r * lde + c);
+        const float4 n = *reinterpret_cast<const float4*>(noise + r * z + c);
+        return make_float4(one(xv.x, e.x, n.x), one(xv.y, e.y, n.y), one(xv.z, e.z, n.z), one(xv.w, e.w, n.w));
+    }
+    static constexpr bool reads_x = true;
+};
+
+template <class Op>
+__device__ __forceinline__ void latent_update_loop(const Op& op, float* __restrict__ x, long long rows, int z,
+                                                   __nv_bfloat16* __restrict__ xb, int ldx) {
+    const int zc = xb ? ldx : z;  // iterate over the padded width so the pad columns get zeroed
+    const int groups = zc / 4;
+    const long long total = rows * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int c = (int)(i % groups) * 4;
+        if (c < z) {
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (Op::reads_x) xv = *reinterpret_cast<const float4*>(x + r * z + c);
+            const float4 v = op(r, c, z, xv);
+            *reinterpret_cast<float4*>(x + r * z + c) = v;
+            if (xb) store_bf16x4(xb + r * ldx + c, v.x, v.y, v.z, v.w);
+        } else {
+            store_bf16x4(xb + r * ldx + c, 0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
-__global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eh, int lde,
-                                 const float* __restrict__ noise, const float* __restrict__ table,
-                                 const int* __restrict__ t_idx, long long rows, int z, __nv_bfloat16* __restrict__ xb,
-                                 int ldx) {
+__global__ void __launch_bounds__(EW_THREADS)
+q_sample_kernel(const float* __restrict__ z_lat, const float* __restrict__ eps, float ca, float cb, long long rows, int z,
+                float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int ldx) {
+    latent_update_loop(QSampleOp{z_lat, eps, ca, cb}, x, rows, z, xb, ldx);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eh, int lde, const float* __restrict__ table,
+                 const int* __restrict__ t_idx, long long rows, int z, int mode, __nv_bfloat16* __restrict__ xb, int ldx) {
     const float* cf = table + (long long)t_idx[0] * 8;
-    const float c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3], c4 = cf[4];
-    const long long total = rows * z;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / z;
-        const int c = (int)(i % z);
-        const float xv = x[i];
-        const float x0 = c0 * xv - c1 * eh[r * lde + c];
-        const float v = c2 * x0 + c3 * xv + c4 * noise[i];
-        x[i] = v;
-        store_bf16_pad(xb, ldx, r, c, z, v);
-    }
+    latent_update_loop(DdimOp{eh, lde, mode, cf[0], cf[1], cf[2], cf[3], cf[4], cf[5]}, x, rows, z, xb, ldx);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eh, int lde, const float* __restrict__ noise,
+                 const float* __restrict__ table, const int* __restrict__ t_idx, long long rows, int z,
+                 __nv_bfloat16* __restrict__ xb, int ldx) {
+    const float* cf = table + (long long)t_idx[0] * 8;
+    latent_update_loop(DdpmOp{eh, noise, lde, cf[0], cf[1], cf[2], cf[3], cf[4]}, x, rows, z, xb, ldx);
 }
 
 __global__ void advance_step_kernel(int* t_idx, int delta) { t_idx[0] += delta; }
@@ -177,13 +247,19 @@ __global__ void wavenet_gate_kernel(const __nv_bfloat16* __restrict__ u, const _
         const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(&rr);
         const float* g = nullptr;
         if (gb) g = gb + (long long)t_idx[(r / T) * t_idx_stride] * gb_t_stride;
+        float ga[8], be[8];
+        if (g) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c)), g1 = __ldg(reinterpret_cast<const float4*>(g + c + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g + C + c)), b1 = __ldg(reinterpret_cast<const float4*>(g + C + c + 4));
+            ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+            be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { ga[k] = 1.f; be[k] = 0.f; }
+        }
         float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float uv = __bfloat162float(up[k]);
-            if (g) uv = uv * __ldg(g + c + k) + __ldg(g + C + c + k);
-            o[k] = wn_gate(uv) + __bfloat162float(rp[k]);
-        }
+        for (int k = 0; k < 8; ++k) o[k] = wn_gate(fmaf(__bfloat162float(up[k]), ga[k], be[k])) + __bfloat162float(rp[k]);
         *reinterpret_cast<uint4*>(y + r * C + c) =
             make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
     }
@@ -288,8 +364,13 @@ extern "C" int dn_cast_pad_bf16(const float* src, int64_t rows, int32_t C, int32
 extern "C" int dn_vae_reparam(const float* params, int32_t ldp, const float* eps, int32_t eps_channel_first, int32_t B,
                               int32_t T, int32_t z, float* z_out, void* stream) {
     if (!params || !eps || !z_out || B <= 0 || T <= 0 || z <= 0 || ldp < 2 * z) return DN_EINVAL;
-    vae_reparam_kernel<<<ew_grid((long long)B * T * z, EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
-        params, ldp, eps, eps_channel_first, B, T, z, z_out);
+    if (eps_channel_first && z % 4 == 0 && z <= 128 && ldp % 4 == 0 &&
+        !((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(z_out)) & 15))
+        vae_reparam_cf_kernel<<<ew_grid((long long)B * ((T + RP_TT - 1) / RP_TT), 1), EW_THREADS, 0, ST(stream)>>>(
+            params, ldp, eps, B, T, z, z_out);
+    else
+        vae_reparam_kernel<<<ew_grid((long long)B * T * z, EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
+            params, ldp, eps, eps_channel_first, B, T, z, z_out);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -297,8 +378,10 @@ extern "C" int dn_vae_reparam(const float* params, int32_t ldp, const float* eps
 
 extern "C" int dn_q_sample(const float* z_lat, const float* eps, float sqrt_ab, float sqrt_1m_ab, int64_t rows,
                            int32_t z, float* x, void* x_bf16, int32_t ldx, void* stream) {
-    if (!z_lat || !eps || !x || rows <= 0 || z <= 0 || (x_bf16 && ldx < z)) return DN_EINVAL;
-    q_sample_kernel<<<ew_grid(rows * (x_bf16 ? ldx : z), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
+    if (!z_lat || !eps || !x || rows <= 0 || z <= 0 || z % 4 || (x_bf16 && (ldx < z || ldx % 4))) return DN_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(z_lat) | reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(x)) & 15)
+        return DN_EINVAL;
+    q_sample_kernel<<<ew_grid(rows * ((x_bf16 ? ldx : z) / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
         z_lat, eps, sqrt_ab, sqrt_1m_ab, rows, z, x, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx);
     DN_LAUNCH_CHECK();
     count_launch();
@@ -308,7 +391,10 @@ extern "C" int dn_q_sample(const float* z_lat, const float* eps, float sqrt_ab, 
 extern "C" int dn_ddim_step(float* x, const float* eps_hat, int32_t lde, const float* coef_table, const int32_t* t_idx,
                             int64_t rows, int32_t z, int32_t mode, void* x_bf16, int32_t ldx, void* stream) {
     if (!x || !eps_hat || !coef_table || !t_idx || rows <= 0 || z <= 0 || lde < z) return DN_EINVAL;
-    ddim_step_kernel<<<ew_grid(rows * z, EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
+    if (z % 4 || lde % 4 || (x_bf16 && (ldx < z || ldx % 4)) ||
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps_hat)) & 15))
+        return DN_EINVAL;
+    ddim_step_kernel<<<ew_grid(rows * ((x_bf16 ? ldx : z) / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
         x, eps_hat, lde, coef_table, t_idx, rows, z, mode, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx);
     DN_LAUNCH_CHECK();
     count_launch();
@@ -318,7 +404,10 @@ extern "C" int dn_ddim_step(float* x, const float* eps_hat, int32_t lde, const f
 extern "C" int dn_ddpm_step(float* x, const float* eps_hat, int32_t lde, const float* noise, const float* coef_table,
                             const int32_t* t_idx, int64_t rows, int32_t z, void* x_bf16, int32_t ldx, void* stream) {
     if (!x || !eps_hat || !noise || !coef_table || !t_idx || rows <= 0 || z <= 0 || lde < z) return DN_EINVAL;
-    ddpm_step_kernel<<<ew_grid(rows * z, EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
+    if (z % 4 || lde % 4 || (x_bf16 && (ldx < z || ldx % 4)) ||
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps_hat) | reinterpret_cast<uintptr_t>(noise)) & 15))
+        return DN_EINVAL;
+    ddpm_step_kernel<<<ew_grid(rows * ((x_bf16 ? ldx : z) / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
         x, eps_hat, lde, noise, coef_table, t_idx, rows, z, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx);
     DN_LAUNCH_CHECK();
     count_launch();

@@ -13,7 +13,7 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
     return v > bv || (v == bv && i < bi);
 }
 
-template <bool BF16>
+template <bool BF16, bool VEC4>
 __global__ void __launch_bounds__(256)
 argmax_units_kernel(const void* __restrict__ logits, long long rows, int C, int ld, int offset,
                     long long* __restrict__ units) {
@@ -30,6 +30,33 @@ argmax_units_kernel(const void* __restrict__ logits, long long rows, int C, int 
                 const float v0 = __low2float(h), v1 = __high2float(h);
                 if (better(v0, c, bv, bi)) { bv = v0; bi = c; }
                 if (c + 1 < C && better(v1, c + 1, bv, bi)) { bv = v1; bi = c + 1; }
+            }
+        } else if (VEC4) {
+            // 16-byte loads, all of a row's loads in flight before the first compare (8 x float4 per lane at C = 1004)
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(logits) + r * ld);
+            const int n4 = C >> 2;
+            float4 v[8];
+            for (int base = 0; base < n4; base += 256) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int q = base + k * 32 + lane;
+                    v[k] = q < n4 ? __ldcs(p + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int c = (base + k * 32 + lane) * 4;
+                    if (c < C) {  // padding lanes hold -inf, which must not beat an all -inf row's index 0
+                        if (better(v[k].x, c, bv, bi)) { bv = v[k].x; bi = c; }
+                        if (better(v[k].y, c + 1, bv, bi)) { bv = v[k].y; bi = c + 1; }
+                        if (better(v[k].z, c + 2, bv, bi)) { bv = v[k].z; bi = c + 2; }
+                        if (better(v[k].w, c + 3, bv, bi)) { bv = v[k].w; bi = c + 3; }
+                    }
+                }
+            }
+            const float* ps = reinterpret_cast<const float*>(logits) + r * ld;
+            for (int c = (n4 << 2) + lane; c < C; c += 32) {
+                const float x = ps[c];
+                if (better(x, c, bv, bi)) { bv = x; bi = c; }
             }
         } else {
             const float* p = reinterpret_cast<const float*>(logits) + r * ld;
@@ -137,9 +164,11 @@ extern "C" int dn_argmax_units(const void* logits, int32_t logits_bf16, int64_t 
     long long blocks = (rows + 7) / 8;
     const int grid = (int)(blocks > 148 * 16 ? 148 * 16 : blocks);
     if (logits_bf16)
-        argmax_units_kernel<true><<<grid, 256, 0, st>>>(logits, rows, C, ld, offset, reinterpret_cast<long long*>(units));
+        argmax_units_kernel<true, false><<<grid, 256, 0, st>>>(logits, rows, C, ld, offset, reinterpret_cast<long long*>(units));
+    else if (ld % 4 == 0 && !(reinterpret_cast<uintptr_t>(logits) & 15))
+        argmax_units_kernel<false, true><<<grid, 256, 0, st>>>(logits, rows, C, ld, offset, reinterpret_cast<long long*>(units));
     else
-        argmax_units_kernel<false><<<grid, 256, 0, st>>>(logits, rows, C, ld, offset, reinterpret_cast<long long*>(units));
+        argmax_units_kernel<false, false><<<grid, 256, 0, st>>>(logits, rows, C, ld, offset, reinterpret_cast<long long*>(units));
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

@@ -72,7 +72,9 @@ int dn_vae_reparam(const float* params, int32_t ldp, const float* eps, int32_t e
  *   [4] sqrt_recip_ab  [5] sqrt_recipm1_ab  -> x0 = c4*x - c5*eps              (generic lib)
  *   [6] unused  [7] unused
  * DDPM rows: [0] sqrt_recip_ab [1] sqrt_recipm1_ab [2] coef1 [3] coef2 [4] exp(0.5*logvar) (0 when t == 0).
- * `t_idx` is a DEVICE int32 holding the current table row, so one captured CUDA graph serves every step. */
+ * `t_idx` is a DEVICE int32 holding the current table row, so one captured CUDA graph serves every step.
+ * The three update kernels move 4 latent channels per thread (16-byte accesses): z, lde and ldx must be multiples
+ * of 4 and the fp32 pointers 16-byte aligned (z is 16, 32 or 128 on this path, LM:1044-1051), else DN_EINVAL. */
 
 /* x = c0 * z + c1 * eps  (q_sample, LM:1405-1409).  Also writes the bf16 staging copy x_bf16 [n/z, ldx] if
  * non-null (zero padded to ldx columns). */
