@@ -132,6 +132,107 @@ def make_samplers(sd, arch, ldm, inputs):
     print("samplers done")
 
 
+TRAIN_CASES = {
+    # name -> (latent_dim, weight seed, B, T, lengths, times, data seed, dropout p, multitask)
+    "train_z16_dropout": (16, 3, 2, 24, [24, 17], [37, 142], 21, 0.1, False),
+    "train_z16_nodrop_multitask": (16, 3, 2, 24, [24, 17], [5, 199], 22, 0.0, True),
+}
+
+
+train_inputs = O.train_case_inputs
+
+
+class ReplayTraining:
+    """Replays every random draw of LatentDiscreteModel.forward (LM:1514-1613) in call order: torch.randint (times,
+    :1528), torch.randn on the CPU (posterior draw, distributions.py:38), two torch.randn_like (:1528, :1534) and the
+    12 attention-dropout draws (F.dropout behind nn.Dropout, LM:338)."""
+
+    def __init__(self, times, eps_vae, eps0, eps, keeps, drop_p):
+        self.times, self.randn_q, self.like_q = times, [eps_vae], [eps0, eps]
+        self.keeps, self.drop_p, self.drop_used = list(keeps or []), drop_p, 0
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._saved = (torch.randint, torch.randn, torch.randn_like, F.dropout)
+        rt = self
+
+        def randint(*a, **kw):
+            return rt.times.clone()
+
+        def randn(*shape, **kw):
+            if len(shape) == 1 and not isinstance(shape[0], int):
+                shape = tuple(shape[0])
+            t = rt.randn_q.pop(0)
+            assert tuple(t.shape) == tuple(shape)
+            return t.clone()
+
+        def randn_like(x, **kw):
+            t = rt.like_q.pop(0)
+            assert t.shape == x.shape
+            return t.clone()
+
+        def dropout(inp, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return inp
+            assert abs(p - rt.drop_p) < 1e-12
+            k = rt.keeps.pop(0)
+            rt.drop_used += 1
+            return inp * k.to(inp.dtype) / (1.0 - p)
+
+        torch.randint, torch.randn, torch.randn_like, F.dropout = randint, randn, randn_like, dropout
+        return self
+
+    def __exit__(self, *a):
+        import torch.nn.functional as F
+        torch.randint, torch.randn, torch.randn_like, F.dropout = self._saved
+
+
+grad_probe = O.grad_probe
+
+
+def make_train(name):
+    z, wseed, B, T, lengths, times, dseed, drop_p, multitask = TRAIN_CASES[name]
+    arch = O.Arch(latent_dim=z)
+    sd = O.init_state_dict(arch, seed=wseed, gains=O.PARITY_GAINS)
+    ldm = ref_loader.build_reference_model(z, multitask=multitask)
+    ldm.load_state_dict(sd)
+    ldm.train()
+    for n_, p_ in ldm.named_parameters():   # diff_discrete.py:79-81: the VAE is frozen
+        p_.requires_grad_(not n_.startswith("speech_decoder."))
+    if drop_p == 0.0:                        # dropout is a hyper-parameter of the reference modules (LM:668)
+        for m in ldm.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    audio, units, mask, eps_vae, eps0, eps, keeps = train_inputs(z, B, T, lengths, dseed, drop_p)
+    tt = torch.tensor(times, dtype=torch.long)
+    with ReplayTraining(tt, eps_vae, eps0, eps, keeps, drop_p) as rt:
+        out = ldm(audio.clone(), units.clone(), tgt_mask=mask)
+    assert rt.drop_used == (12 if drop_p > 0 else 0) and not rt.like_q and not rt.randn_q
+    out["total_loss"].backward()
+    store = dict(latent_dim=z, weight_seed=wseed, lengths=np.array(lengths), times=np.array(times), data_seed=dseed,
+                 drop_p=drop_p, multitask=int(multitask), T=T)
+    for k in ("total_loss", "nll_loss", "recon_mse_loss", "noise_loss", "acc"):
+        store[k] = np.float64(out[k].detach().double().item())
+    names, norms, samples = [], [], []
+    for n_, p_ in ldm.named_parameters():
+        if p_.grad is None:
+            continue
+        gflat = p_.grad.detach().double().flatten()
+        names.append(n_)
+        norms.append(float(gflat.norm()))
+        samples.append(gflat[torch.from_numpy(grad_probe(n_, gflat.numel()))].numpy())
+    store["grad_names"] = np.array(names)
+    store["grad_norms"] = np.array(norms)
+    store["grad_samples"] = np.stack(samples)
+    # full gradients of a few small tensors
+    for n_ in ("model.to_time_cond.0.weights", "model.final_proj.bias", "model.transformer.to_pred.0.gamma",
+               "model.wavenet.stacks.0.blocks.0.to_time_cond.bias", "model.transformer.layers.0.0.to_gamma_beta.bias"):
+        store["full:" + n_] = dict(ldm.named_parameters())[n_].grad.detach().numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **store)
+    print(name, {k: float(store[k]) for k in ("total_loss", "nll_loss", "recon_mse_loss", "noise_loss", "acc")},
+          "params with grad", len(names))
+
+
 def make_schedule(ldm):
     s = ldm.scheduler
     np.savez_compressed(
@@ -210,6 +311,10 @@ def main():
     torch.manual_seed(0)
     if "--batcher-only" in sys.argv:
         return make_batcher()
+    if "--train-only" in sys.argv:
+        for name in TRAIN_CASES:
+            make_train(name)
+        return
     make_batcher()
     make_reduce()
     for name in PASS_CASES:
@@ -217,6 +322,8 @@ def main():
         if name == "pass_z16_parity":
             make_samplers(sd, arch, ldm, inputs)
             make_schedule(ldm)
+    for name in TRAIN_CASES:
+        make_train(name)
 
 
 if __name__ == "__main__":

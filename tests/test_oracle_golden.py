@@ -129,3 +129,38 @@ def test_inline_ddim_equals_generic_ddim():
     for t in (150, 99, 1):
         a, b = O.ddim_step(sch, x, e, t), O.ddim_generic_step(sch, x, e, t)
         assert (a - b).abs().max() < 5e-5 * (1 + a.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------- training step (a11)
+@pytest.mark.parametrize("name", ["train_z16_dropout", "train_z16_nodrop_multitask"])
+def test_oracle_train_loss_and_grads_match_reference(name):
+    """LatentDiscreteModel.forward + autograd of the live reference (oracle/make_golden.py make_train: every random
+    draw replayed, incl. the 12 attention-dropout masks) vs the oracle's functional restatement under autograd."""
+    g = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    z, T = int(g["latent_dim"]), int(g["T"])
+    lengths, times = g["lengths"].tolist(), g["times"].tolist()
+    drop_p, multitask = float(g["drop_p"]), bool(int(g["multitask"]))
+    arch = O.Arch(latent_dim=z)
+    sd = O.init_state_dict(arch, seed=int(g["weight_seed"]), gains=O.PARITY_GAINS)
+    train_keys = [k for k in sd if k.startswith("model.") and sd[k].is_floating_point() and "pos_embed" not in k]
+    for k in train_keys:
+        sd[k].requires_grad_(True)
+    audio, units, mask, eps_vae, eps0, eps, keeps = O.train_case_inputs(z, len(lengths), T, lengths, int(g["data_seed"]), drop_p)
+    out = O.train_loss(sd, arch, audio, units, mask, torch.tensor(times), eps_vae, eps0, eps, keeps, drop_p, multitask)
+    for k in ("total_loss", "nll_loss", "recon_mse_loss", "noise_loss", "acc"):
+        assert abs(float(out[k]) - float(g[k])) <= 2e-5 * max(1.0, abs(float(g[k]))), (k, float(out[k]), float(g[k]))
+    out["total_loss"].backward()
+    names = [str(n) for n in g["grad_names"]]
+    assert sorted(names) == sorted(train_keys)
+    worst = 0.0
+    for n, norm, samp in zip(names, g["grad_norms"], g["grad_samples"]):
+        gr = sd[n].grad.double().flatten()
+        assert abs(float(gr.norm()) - norm) <= 1e-3 * norm + 1e-9, (n, float(gr.norm()), norm)
+        got = gr[torch.from_numpy(O.grad_probe(n, gr.numel()))].numpy()
+        err = np.abs(got - samp).max() / (np.abs(samp).max() + norm / np.sqrt(gr.numel()) + 1e-12)
+        worst = max(worst, err)
+        assert err <= 5e-3, (n, got, samp)
+    for key in g.files:
+        if key.startswith("full:"):
+            np.testing.assert_allclose(sd[key[5:]].grad.numpy(), g[key], rtol=2e-3, atol=1e-6 * float(np.abs(g[key]).max()) + 1e-9)
+    print(f"[parity] {name}: oracle autograd vs reference autograd, worst sampled-gradient error {worst:.2e}")
