@@ -48,6 +48,16 @@ class GemmDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("T", i32),
+        ("dY", vp), ("ldy", i32), ("dy_batch_stride", i64), ("dy_col0", i32),
+        ("X", vp), ("ldx", i32), ("x_batch_stride", i64), ("x_col0", i32), ("x_shift", i32),
+        ("n_rows", i32), ("k_cols", i32),
+        ("dW", vp), ("ldw", i32), ("splits", i32),
+    ]
+
+
 EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_WN_GATE = range(5)
 GEMM_TCGEN05, GEMM_SIMT_CHECK = 0, 1
 
@@ -69,6 +79,26 @@ _SIGS = {
     "dn_time_features": [vp, vp, i32, i32, vp, vp],
     "dn_gemm": [C.POINTER(GemmDesc), i32, vp],
     "dn_attention": [vp, vp, vp, i32, i32, i32, i32, vp],
+    # training step
+    "dn_wgrad": [C.POINTER(WgradDesc), vp],
+    "dn_colsum_bf16": [vp, i64, i32, i32, i32, vp, vp],
+    "dn_geglu_fwd": [vp, i64, i32, vp, vp],
+    "dn_geglu_bwd": [vp, vp, i64, i32, vp, vp],
+    "dn_wn_gate_fwd": [vp, vp, i32, i32, i32, i32, vp, i64, i32, vp, i32, vp],
+    "dn_wn_gate_bwd": [vp, vp, vp, i32, i32, i32, i32, vp, i64, i32, vp, i32, vp, i64, i32, vp],
+    "dn_adarmsnorm_bwd": [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, i32, vp, i64, vp],
+    "dn_train_noise": [vp, vp, vp, f32, vp, vp, i32, i32, i32, vp, vp, i32, vp],
+    "dn_noise_loss": [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, f32, vp],
+    "dn_pred_x1": [vp, vp, i32, vp, vp, i32, i32, i32, vp, i32, vp],
+    "dn_decode_losses": [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp, vp],
+    "dn_dropout_bits": [vp, i64, f32, C.c_uint64, C.c_uint64, vp],
+    "dn_attention_train": [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp],
+    "dn_attention_bwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
+    "dn_silu": [vp, vp, i64, vp],
+    "dn_silu_bwd": [vp, vp, vp, i64, vp],
+    "dn_linear_f32_bwd": [vp, i64, vp, vp, i32, i64, i32, vp, vp, vp, vp],
+    "dn_time_features_bwd": [vp, vp, vp, i32, i32, vp, vp],
+    "dn_add_bf16_to_f32": [vp, i64, i32, i32, i32, vp, i32, i32, vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["dn_abi_version", "dn_launch_count", "dn_batch_by_size"])
 

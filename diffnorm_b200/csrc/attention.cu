@@ -209,7 +209,8 @@ static int launch_attention(const void* qkv, void* out, const int32_t* lengths, 
     return 0;
 }
 
-int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st);
+int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
+                        float* lse2, const uint32_t* keep, float keep_scale, bool train);
 
 }  // namespace dn
 
@@ -222,10 +223,18 @@ extern "C" int dn_attention(const void* qkv, void* out, const int32_t* lengths, 
         const char* e = getenv("DN_ATTN_IMPL");
         const bool use_mma = e && e[0] == 'm';
         if (!use_mma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
-            return dn::launch_attention_tc(qkv, out, lengths, B, T, H, st);
+            return dn::launch_attention_tc(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, false);
         return dn::launch_attention<64>(qkv, out, lengths, B, T, H, st);
     }
     if (dh == 96) return dn::launch_attention<96>(qkv, out, lengths, B, T, H, st);
     if (dh == 32) return dn::launch_attention<32>(qkv, out, lengths, B, T, H, st);
     return DN_EINVAL;
+}
+
+extern "C" int dn_attention_train(const void* qkv, void* out, float* lse2, const int32_t* lengths, const uint32_t* keep_bits,
+                                  float keep_scale, int32_t B, int32_t T, int32_t H, int32_t dh, void* stream) {
+    if (!qkv || !out || !lse2 || B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535 || dh != 64) return DN_EINVAL;
+    if (reinterpret_cast<uintptr_t>(qkv) & 15) return DN_EINVAL;
+    return dn::launch_attention_tc(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
+                                   keep_scale, true);
 }

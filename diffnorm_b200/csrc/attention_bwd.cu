@@ -1,0 +1,499 @@
+// dn_attention_bwd (dh = 64): backward of the denoiser's self-attention (LM:299-343, :908-950) on tcgen05 tensor
+// cores, flash style (nothing of size N x N touches HBM).  Forward (attention_tc.cu, TRAIN form) saved, per query
+// row, L2 = m + log2(l) (log-sum-exp of the scaled scores in the log2 domain); with D[q] = sum_d dO[q,d] O[q,d]:
+//     P  = exp2(S * scale_log2 - L2[q])            (keys >= length: 0)
+//     dV = (P o keep * ks)^T dO                    (keep/ks: attention dropout, LM:338)
+//     dS = scale * P o ((dO V^T) o keep * ks - D[q])
+//     dQ = dS K        dK = dS^T Q
+// Two kernels, both with the forward's role layout (warp 0 TMA producer, warp 1 MMA issuer, 8 softmax warps = two
+// threads per TMEM lane) and operands in TMEM where the ISA allows it (A of the second GEMM of every pair):
+//   attn_bwd_dq_kernel   CTA = 128 queries: per key block  S = Q K^T, dP = dO V^T  -> dS (TMEM) -> dQ += dS K
+//   attn_bwd_dkv_kernel  CTA = 128 keys:    per query block S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (TMEM)
+//                                           -> dV += P^T dO, dK += dS^T Q
+// K / V (resp. Q / dO) blocks are double buffered in smem; the same smem tile serves as a K-major operand of the first
+// GEMM and as an MN-major operand of the second.  One CTA per SM (all 512 TMEM columns in the dKdV kernel).
+#include "common.cuh"
+
+namespace dn {
+
+constexpr int AB_T = 128;             // tile edge (queries or keys)
+constexpr int AB_DH = 64;
+constexpr int AB_THREADS = 320;
+constexpr int AB_TILE = AB_T * AB_DH * 2;   // 16 KB
+constexpr int AB_SMEM = 6 * AB_TILE + 1024 + 256 + 2 * 2 * AB_T * 4;  // resident pair + 2 stages x pair + barriers + column scalars
+
+int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box);
+
+__device__ __forceinline__ float ab_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// M = 128, runtime N, A K-major (smem) or TMEM, B K-major (0) or MN-major (1)
+__device__ __forceinline__ uint32_t ab_idesc(uint32_t n, uint32_t b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// D[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]   (one warp per (frame, head); 2 bf16 per lane)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int B, int T,
+                                  int H, float* __restrict__ delta) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)B * T * H;
+    for (long long w = warp0; w < total; w += nwarps) {
+        const int h = (int)(w % H);
+        const long long bt = w / H;
+        const long long off = (bt * H + h) * AB_DH + lane * 2;
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
+        const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_o + off));
+        const float s = warp_sum(a.x * g.x + a.y * g.y);
+        if (lane == 0) {
+            const int b = (int)(bt / T), t = (int)(bt % T);
+            delta[((long long)b * H + h) * T + t] = s;
+        }
+    }
+}
+
+struct AbBars {
+    uint64_t* r_full;      // resident pair loaded
+    uint64_t* st_full;     // [2] streamed pair loaded
+    uint64_t* st_empty;    // [2] streamed pair consumed
+    uint64_t* sdp_full;    // S and dP of block j complete in TMEM
+    uint64_t* s_free;      // S and dP of block j copied to registers (256 arrivals)
+    uint64_t* ds_full;     // P / dS of block j written to TMEM (256 arrivals)
+    uint64_t* ds_empty;    // second GEMMs of block j complete
+};
+
+// ---------------------------------------------------------------------------------------------------- dQ
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ lengths,
+                   const uint32_t* __restrict__ keep, float keep_scale, __nv_bfloat16* __restrict__ dqkv, int T, int H,
+                   float scale, float scale_log2) {
+    extern __shared__ uint8_t ab_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                     // resident: Q tile, dO tile
+    uint8_t* sDO = smem + AB_TILE;
+    uint8_t* sStage = smem + 2 * AB_TILE;   // 2 stages x (K, V)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AB_TILE);
+    AbBars bb{bars + 0, bars + 1, bars + 3, bars + 5, bars + 6, bars + 7, bars + 8};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+    int len = lengths ? lengths[b] : T;
+    len = len > T ? T : len;
+    const int nkb = (len + AB_T - 1) / AB_T;
+    const int qcol = h * AB_DH, kcol = (H + h) * AB_DH, vcol = (2 * H + h) * AB_DH;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+        mbar_init(bb.r_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bb.st_full + i, 1);
+            mbar_init(bb.st_empty + i, 1);
+        }
+        mbar_init(bb.sdp_full, 1);
+        mbar_init(bb.s_free, 256);
+        mbar_init(bb.ds_full, 256);
+        mbar_init(bb.ds_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM: S fp32 [0,128) | dP fp32 [128,256) | dS bf16x2 [256,320) | dQ fp32 [320,384)
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDS = tmem_base + 256, tDQ = tmem_base + 320;
+
+    if (warp == 0) {
+        if (lane == 0 && nkb > 0) {
+            mbar_expect_tx(bb.r_full, 2 * AB_TILE);
+            tma_load_3d(&tmQKV, bb.r_full, sQ, qcol, q0, b);
+            tma_load_3d(&tmDO, bb.r_full, sDO, h * AB_DH, q0, b);
+            for (int j = 0; j < nkb; ++j) {
+                const int st = j & 1;
+                mbar_wait(bb.st_empty + st, ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(bb.st_full + st, 2 * AB_TILE);
+                tma_load_3d(&tmQKV, bb.st_full + st, sStage + st * 2 * AB_TILE, kcol, j * AB_T, b);
+                tma_load_3d(&tmQKV, bb.st_full + st, sStage + st * 2 * AB_TILE + AB_TILE, vcol, j * AB_T, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            const uint32_t id_s = ab_idesc(AB_T, 0), id_q = ab_idesc(AB_DH, 1);
+            const uint64_t dq_ = umma_desc_sw128(smem_u32(sQ));
+            const uint64_t ddo = umma_desc_sw128(smem_u32(sDO));
+            auto issue_first = [&](int j) {
+                const int st = j & 1;
+                mbar_wait(bb.st_full + st, (j >> 1) & 1);
+                tc_fence_after();
+                const uint64_t dk = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));
+                const uint64_t dv = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE + AB_TILE));
+#pragma unroll
+                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tS, dq_ + 2 * k, dk + 2 * k, id_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tDP, ddo + 2 * k, dv + 2 * k, id_s, k > 0);
+                umma_commit(bb.sdp_full);
+            };
+            mbar_wait(bb.r_full, 0);
+            issue_first(0);
+            for (int j = 0; j < nkb; ++j) {
+                if (j + 1 < nkb) {
+                    mbar_wait(bb.s_free, j & 1);
+                    issue_first(j + 1);
+                }
+                const int st = j & 1;
+                mbar_wait(bb.ds_full, j & 1);
+                tc_fence_after();
+                const uint64_t dk = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));   // K as MN-major B operand
+#pragma unroll
+                for (int k = 0; k < AB_T / 16; ++k)
+                    umma_bf16_ts(tDQ, tDS + 8 * k, dk + (uint64_t)((k * 16 * 128) >> 4), id_q, (j > 0) || (k > 0));
+                umma_commit(bb.st_empty + st);
+                umma_commit(bb.ds_empty);
+            }
+        }
+    } else {
+        const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const int t = q0 + row;
+        const long long bh = (long long)b * H + h;
+        const float L2 = t < T ? lse2[bh * T + t] : INFINITY;   // rows past T: P = 0
+        const float Dq = t < T ? delta[bh * T + t] : 0.f;
+        const int Tw = (T + 31) >> 5;
+        const uint32_t* krow = keep ? keep + (bh * T + (t < T ? t : T - 1)) * Tw : nullptr;
+        for (int j = 0; j < nkb; ++j) {
+            float s0[32], s1[32], p0[32], p1[32];
+            mbar_wait(bb.sdp_full, j & 1);
+            tc_fence_after();
+            tmem_ld32(tS + lane_off + half * 64, s0);
+            tmem_ld32(tS + lane_off + half * 64 + 32, s1);
+            tmem_ld32(tDP + lane_off + half * 64, p0);
+            tmem_ld32(tDP + lane_off + half * 64 + 32, p1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bb.s_free);
+            const int kbase = j * AB_T + half * 64;
+            uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
+            if (krow) {
+                const int wi = kbase >> 5;
+                kw0 = wi < Tw ? krow[wi] : 0u;
+                kw1 = wi + 1 < Tw ? krow[wi + 1] : 0u;
+            }
+            uint32_t w0[16], w1[16];
+            auto half_row = [&](const float (&s)[32], const float (&dp)[32], uint32_t kw, int kb0, uint32_t (&w)[16]) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float ds[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float pr = (kb0 + i + e < len) ? ab_ex2(fmaf(s[i + e], scale_log2, -L2)) : 0.f;
+                        const float dpe = ((kw >> (i + e)) & 1u) ? dp[i + e] * keep_scale : 0.f;
+                        ds[e] = scale * pr * (dpe - Dq);
+                    }
+                    w[i >> 1] = pack_bf16(ds[0], ds[1]);
+                }
+            };
+            half_row(s0, p0, kw0, kbase, w0);
+            half_row(s1, p1, kw1, kbase + 32, w1);
+            if (j > 0) {
+                mbar_wait(bb.ds_empty, (j - 1) & 1);
+                tc_fence_after();
+            }
+            tmem_st16(tDS + lane_off + half * 32, w0);
+            tmem_st16(tDS + lane_off + half * 32 + 16, w1);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bb.ds_full);
+        }
+        if (nkb > 0) {
+            mbar_wait(bb.ds_empty, (nkb - 1) & 1);
+            tc_fence_after();
+        }
+        float o[32];
+        if (nkb > 0) {
+            tmem_ld32(tDQ + lane_off + half * 32, o);
+            tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        }
+        if (t < T) {
+            __nv_bfloat16* op = dqkv + ((long long)b * T + t) * (3 * H * AB_DH) + qcol + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+                *reinterpret_cast<uint4*>(op + i) = make_uint4(pack_bf16(o[i], o[i + 1]), pack_bf16(o[i + 2], o[i + 3]),
+                                                               pack_bf16(o[i + 4], o[i + 5]), pack_bf16(o[i + 6], o[i + 7]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------- dK, dV
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                    const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ lengths,
+                    const uint32_t* __restrict__ keep, float keep_scale, __nv_bfloat16* __restrict__ dqkv, int T, int H,
+                    float scale, float scale_log2) {
+    extern __shared__ uint8_t ab_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sK = smem;                     // resident: K tile, V tile
+    uint8_t* sV = smem + AB_TILE;
+    uint8_t* sStage = smem + 2 * AB_TILE;   // 2 stages x (Q, dO)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AB_TILE);
+    AbBars bb{bars + 0, bars + 1, bars + 3, bars + 5, bars + 6, bars + 7, bars + 8};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* colv = reinterpret_cast<float*>(bars + 32);   // [2 stages][L2 (128) | D (128)]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+    int len = lengths ? lengths[b] : T;
+    len = len > T ? T : len;
+    // queries of every frame of the padded utterance attend (padded queries are computed by the reference too, LM:333);
+    // keys past the length have P = 0, so key tiles past the length produce exact zeros.
+    const int nqb = (k0 < len) ? (T + AB_T - 1) / AB_T : 0;
+    const int qcol = h * AB_DH, kcol = (H + h) * AB_DH, vcol = (2 * H + h) * AB_DH;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+        mbar_init(bb.r_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bb.st_full + i, 1);
+            mbar_init(bb.st_empty + i, 1);
+        }
+        mbar_init(bb.sdp_full, 1);
+        mbar_init(bb.s_free, 256);
+        mbar_init(bb.ds_full, 256);
+        mbar_init(bb.ds_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM: S^T [0,128) | dP^T [128,256) | P^T bf16x2 [256,320) | dS^T bf16x2 [320,384) | dV [384,448) | dK [448,512)
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320;
+    const uint32_t tDV = tmem_base + 384, tDK = tmem_base + 448;
+
+    if (warp == 0) {
+        if (lane == 0 && nqb > 0) {
+            mbar_expect_tx(bb.r_full, 2 * AB_TILE);
+            tma_load_3d(&tmQKV, bb.r_full, sK, kcol, k0, b);
+            tma_load_3d(&tmQKV, bb.r_full, sV, vcol, k0, b);
+            for (int i = 0; i < nqb; ++i) {
+                const int st = i & 1;
+                mbar_wait(bb.st_empty + st, ((i >> 1) & 1) ^ 1);
+                mbar_expect_tx(bb.st_full + st, 2 * AB_TILE);
+                tma_load_3d(&tmQKV, bb.st_full + st, sStage + st * 2 * AB_TILE, qcol, i * AB_T, b);
+                tma_load_3d(&tmDO, bb.st_full + st, sStage + st * 2 * AB_TILE + AB_TILE, h * AB_DH, i * AB_T, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nqb > 0) {
+            const uint32_t id_s = ab_idesc(AB_T, 0), id_o = ab_idesc(AB_DH, 1);
+            const uint64_t dk = umma_desc_sw128(smem_u32(sK));
+            const uint64_t dv = umma_desc_sw128(smem_u32(sV));
+            auto issue_first = [&](int i) {
+                const int st = i & 1;
+                mbar_wait(bb.st_full + st, (i >> 1) & 1);
+                tc_fence_after();
+                const uint64_t dq_ = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));
+                const uint64_t ddo = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE + AB_TILE));
+#pragma unroll
+                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tS, dk + 2 * k, dq_ + 2 * k, id_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tDP, dv + 2 * k, ddo + 2 * k, id_s, k > 0);
+                umma_commit(bb.sdp_full);
+            };
+            mbar_wait(bb.r_full, 0);
+            issue_first(0);
+            for (int i = 0; i < nqb; ++i) {
+                if (i + 1 < nqb) {
+                    mbar_wait(bb.s_free, i & 1);
+                    issue_first(i + 1);
+                }
+                const int st = i & 1;
+                mbar_wait(bb.ds_full, i & 1);
+                tc_fence_after();
+                const uint64_t dq_ = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));            // Q, MN-major B
+                const uint64_t ddo = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE + AB_TILE));  // dO, MN-major B
+#pragma unroll
+                for (int k = 0; k < AB_T / 16; ++k)
+                    umma_bf16_ts(tDV, tP + 8 * k, ddo + (uint64_t)((k * 16 * 128) >> 4), id_o, (i > 0) || (k > 0));
+#pragma unroll
+                for (int k = 0; k < AB_T / 16; ++k)
+                    umma_bf16_ts(tDK, tDS + 8 * k, dq_ + (uint64_t)((k * 16 * 128) >> 4), id_o, (i > 0) || (k > 0));
+                umma_commit(bb.st_empty + st);
+                umma_commit(bb.ds_empty);
+            }
+        }
+    } else {
+        const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = qd * 32 + lane;                 // key row of this thread
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const int key = k0 + row;
+        const bool key_ok = key < len;
+        const long long bh = (long long)b * H + h;
+        const int Tw = (T + 31) >> 5;
+        const int kword = (k0 + qd * 32) >> 5;          // the 32 keys of this warp share one keep word per query
+        const int st_tid = threadIdx.x - 64;            // 0..255 among the softmax threads
+        for (int i = 0; i < nqb; ++i) {
+            const int qb0 = i * AB_T;
+            // per-query scalars of this block -> smem (L2 = +inf for queries past T: P = 0)
+            float* cv = colv + (i & 1) * 2 * AB_T;
+            {
+                const int qq = qb0 + (st_tid & 127);
+                float v;
+                if (st_tid < 128) v = qq < T ? lse2[bh * T + qq] : INFINITY;
+                else v = qq < T ? delta[bh * T + qq] : 0.f;
+                cv[st_tid] = v;
+            }
+            named_bar_sync(1, 256);
+            float s0[32], s1[32], p0[32], p1[32];
+            mbar_wait(bb.sdp_full, i & 1);
+            tc_fence_after();
+            tmem_ld32(tS + lane_off + half * 64, s0);
+            tmem_ld32(tS + lane_off + half * 64 + 32, s1);
+            tmem_ld32(tDP + lane_off + half * 64, p0);
+            tmem_ld32(tDP + lane_off + half * 64 + 32, p1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bb.s_free);
+            uint32_t wp0[16], wp1[16], wd0[16], wd1[16];
+            auto half_row = [&](const float (&s)[32], const float (&dp)[32], int qoff, uint32_t (&wp)[16], uint32_t (&wd)[16]) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    float pd[2], ds[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int qi = qoff + c + e;          // query index inside the block
+                        const float L2 = cv[qi], Dq = cv[AB_T + qi];
+                        const float pr = key_ok ? ab_ex2(fmaf(s[c + e], scale_log2, -L2)) : 0.f;
+                        float kf = keep_scale;
+                        if (keep) {
+                            const int qq = qb0 + qi;
+                            const uint32_t word = keep[(bh * T + (qq < T ? qq : T - 1)) * Tw + kword];
+                            kf = ((word >> lane) & 1u) ? keep_scale : 0.f;
+                        }
+                        pd[e] = pr * kf;
+                        ds[e] = scale * pr * (dp[c + e] * kf - Dq);
+                    }
+                    wp[c >> 1] = pack_bf16(pd[0], pd[1]);
+                    wd[c >> 1] = pack_bf16(ds[0], ds[1]);
+                }
+            };
+            half_row(s0, p0, half * 64, wp0, wd0);
+            half_row(s1, p1, half * 64 + 32, wp1, wd1);
+            if (i > 0) {
+                mbar_wait(bb.ds_empty, (i - 1) & 1);
+                tc_fence_after();
+            }
+            tmem_st16(tP + lane_off + half * 32, wp0);
+            tmem_st16(tP + lane_off + half * 32 + 16, wp1);
+            tmem_st16(tDS + lane_off + half * 32, wd0);
+            tmem_st16(tDS + lane_off + half * 32 + 16, wd1);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bb.ds_full);
+        }
+        if (nqb > 0) {
+            mbar_wait(bb.ds_empty, (nqb - 1) & 1);
+            tc_fence_after();
+        }
+        float ov[32], ok[32];
+        if (nqb > 0) {
+            tmem_ld32(tDV + lane_off + half * 32, ov);
+            tmem_ld32(tDK + lane_off + half * 32, ok);
+            tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { ov[c] = 0.f; ok[c] = 0.f; }
+        }
+        if (key < T) {
+            __nv_bfloat16* base = dqkv + ((long long)b * T + key) * (3 * H * AB_DH) + half * 32;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+                *reinterpret_cast<uint4*>(base + kcol + c) = make_uint4(pack_bf16(ok[c], ok[c + 1]), pack_bf16(ok[c + 2], ok[c + 3]),
+                                                                        pack_bf16(ok[c + 4], ok[c + 5]), pack_bf16(ok[c + 6], ok[c + 7]));
+                *reinterpret_cast<uint4*>(base + vcol + c) = make_uint4(pack_bf16(ov[c], ov[c + 1]), pack_bf16(ov[c + 2], ov[c + 3]),
+                                                                        pack_bf16(ov[c + 4], ov[c + 5]), pack_bf16(ov[c + 6], ov[c + 7]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" int dn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, const int32_t* lengths,
+                                const uint32_t* keep_bits, float keep_scale, void* dqkv, float* delta_ws, int32_t B, int32_t T,
+                                int32_t H, int32_t dh, void* stream) {
+    if (!qkv || !out || !dout || !lse2 || !dqkv || !delta_ws || B <= 0 || T <= 0 || H <= 0 || dh != AB_DH) return DN_EINVAL;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        attr_set = true;
+    }
+    {
+        const long long warps = (long long)B * T * H;
+        long long blocks = (warps + 7) / 8;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        attn_delta_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                       reinterpret_cast<const __nv_bfloat16*>(dout), B, T, H, delta_ws);
+        DN_LAUNCH_CHECK();
+        count_launch();
+    }
+    CUtensorMap mq, mdo;
+    {
+        const int ld = 3 * H * AB_DH;
+        cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+        cuuint32_t box[3] = {AB_DH, AB_T, 1};
+        int r = encode_bf16_map(&mq, qkv, 3, dims, str, box);
+        if (r) return r;
+    }
+    {
+        const int ld = H * AB_DH;
+        cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+        cuuint32_t box[3] = {AB_DH, AB_T, 1};
+        int r = encode_bf16_map(&mdo, dout, 3, dims, str, box);
+        if (r) return r;
+    }
+    dim3 grid((T + AB_T - 1) / AB_T, H, B);
+    const float scale = 1.0f / sqrtf((float)AB_DH);
+    const float scale_log2 = scale * 1.4426950408889634f;
+    attn_bwd_dq_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mdo, lse2, delta_ws, lengths, keep_bits, keep_scale,
+                                                          reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, scale, scale_log2);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    attn_bwd_dkv_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mdo, lse2, delta_ws, lengths, keep_bits, keep_scale,
+                                                           reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, scale, scale_log2);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}

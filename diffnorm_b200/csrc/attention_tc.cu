@@ -59,9 +59,13 @@ __device__ __forceinline__ uint32_t ta_idesc(uint32_t n, uint32_t b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// TRAIN: additionally applies the attention-dropout keep bits (LM:338; keep [B,H,T,ceil(T/32)] words, bit k%32 of word
+// k/32 = key k kept; P is scaled by keep_scale = 1/(1-p) after the row sum) and saves L2 = m + log2(l) per query row.
+template <bool TRAIN>
 __global__ void __launch_bounds__(TA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
-                    const int* __restrict__ lengths, int T, int H, float scale_log2) {
+                    const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2,
+                    const uint32_t* __restrict__ keep, float keep_scale) {
     extern __shared__ uint8_t ta_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ta_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;
@@ -181,6 +185,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         float m = -INFINITY, l = 0.f;
         const uint64_t scale2 = pack2(scale_log2, scale_log2);
+        const int Tw = (T + 31) >> 5;
+        const uint32_t* krow = nullptr;
+        if (TRAIN && keep) {
+            const int tq = q0 + row < T ? q0 + row : T - 1;
+            krow = keep + (((long long)b * H + h) * T + tq) * Tw;
+        }
         // Only the last key block of an utterance can contain masked keys: the block body is instantiated twice so
         // the hot (unmasked) copy carries no predicated compare/select instructions at all.
         auto block = [&](const int j, auto masked_tag) {
@@ -221,7 +231,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             const uint64_t nm2 = pack2(-m, -m);
             // p = exp2(s * scale - m), partial row sum, packed bf16 pairs
             uint64_t rs2[2] = {0ull, 0ull};
-            auto half_row = [&](const float (&s)[32], uint32_t (&w)[16]) {
+            uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
+            if (TRAIN && krow) {
+                const int wi = kbase >> 5;
+                kw0 = wi < Tw ? krow[wi] : 0u;
+                kw1 = wi + 1 < Tw ? krow[wi + 1] : 0u;
+            }
+            auto half_row = [&](const float (&s)[32], uint32_t (&w)[16], const uint32_t kw) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float e0, e1;
@@ -229,11 +245,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                     e0 = ex2_approx(e0);   // masked keys: ex2(-inf) = +0
                     e1 = ex2_approx(e1);
                     rs2[(i >> 1) & 1] = fadd2(rs2[(i >> 1) & 1], pack2(e0, e1));
+                    if (TRAIN && krow) {   // dropout acts on the normalised probabilities: the row sum stays un-dropped
+                        e0 = ((kw >> i) & 1u) ? e0 * keep_scale : 0.f;
+                        e1 = ((kw >> (i + 1)) & 1u) ? e1 * keep_scale : 0.f;
+                    }
                     w[i >> 1] = pack_bf16(e0, e1);
                 }
             };
             uint32_t w0[16], w1[16];
-            half_row(s0, w0);
+            half_row(s0, w0, kw0);
             if (j > 0) {
                 mbar_wait(p_empty, (j - 1) & 1);           // PV_{j-1} done: P columns free, O stable
                 tc_fence_after();
@@ -251,7 +271,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                 }
             }
             tmem_st16(tP + lane_off + half * 32, w0);
-            half_row(s1, w1);
+            half_row(s1, w1, kw1);
             tmem_st16(tP + lane_off + half * 32 + 16, w1);
             float r0, r1, r2, r3;
             unpack2(rs2[0], r0, r1);
@@ -269,6 +289,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         named_bar_sync(2, 256);
         l += lsum[(half ^ 1) * TA_BM + row];
         const int t = q0 + row;
+        if (TRAIN && lse2 && half == 0 && t < T) lse2[((long long)b * H + h) * T + t] = m + log2f(l);
         if (nkb > 0) {
             mbar_wait(p_empty, (nkb - 1) & 1);   // last PV complete
             tc_fence_after();
@@ -299,10 +320,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
 int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                     const cuuint32_t* box);
 
-int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st) {
+int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
+                        float* lse2, const uint32_t* keep, float keep_scale, bool train) {
     static bool attr_set = false;
     if (!attr_set) {
-        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         attr_set = true;
     }
     CUtensorMap m;
@@ -314,8 +337,12 @@ int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int 
     if (r) return r;
     dim3 grid((T + TA_BM - 1) / TA_BM, H, B);
     const float scale_log2 = (1.0f / sqrtf((float)TA_DH)) * 1.4426950408889634f;
-    attention_tc_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(m, reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H,
-                                                          scale_log2);
+    if (train)
+        attention_tc_kernel<true><<<grid, TA_THREADS, TA_SMEM, st>>>(m, reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H,
+                                                                    scale_log2, lse2, keep, keep_scale);
+    else
+        attention_tc_kernel<false><<<grid, TA_THREADS, TA_SMEM, st>>>(m, reinterpret_cast<__nv_bfloat16*>(out), lengths, T,
+                                                                     H, scale_log2, nullptr, nullptr, 1.f);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

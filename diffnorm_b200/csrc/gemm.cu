@@ -416,6 +416,10 @@ int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
 }
+int encode_f32_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+    return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
+}
 static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     EncodeTiledFn fn = get_encode();

@@ -53,7 +53,8 @@ class _TfLayer:
 
 
 class DiffNormEngine:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: str = "cuda", cfg: Optional[DiffNormConfig] = None):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: str = "cuda", cfg: Optional[DiffNormConfig] = None,
+                 vae_only: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("DiffNormEngine needs a CUDA device: the product has no CPU path")
         sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
@@ -70,9 +71,12 @@ class DiffNormEngine:
         self.zp = rup(c.latent_dim, 64)        # latent staging width (K of the first GEMMs)
         self.zn = rup(c.latent_dim, 16)        # eps_hat row width
         self.vp = rup(c.vocab, 16)             # logits row width
-        self._pack_denoiser(sd)
+        self.vae_only = vae_only   # training keeps a frozen-VAE engine; the denoiser weights change every step
+        if not vae_only:
+            self._pack_denoiser(sd)
         self._pack_vae(sd)
-        self._build_time_table(sd)
+        if not vae_only:
+            self._build_time_table(sd)
         self.sched = DDPMScheduler(c.timesteps)
         self.ddim_rows = torch.from_numpy(self.sched.ddim_rows()).to(self.dev)
         self._pe_cache: Dict[int, torch.Tensor] = {}

@@ -223,3 +223,138 @@ class GemmPlan:
         d.pe, d.lengths = _p(pe), _p(lengths)
         check(lib.dn_gemm(C.byref(d), impl, _stream()), f"dn_gemm[{self.name}]")
         return out
+
+
+# ------------------------------------------------------------------------------------------------ training step
+def wgrad(dY, X, dW, B: int, T: int, n_rows: int, k_cols: int, dy_col0: int = 0, x_col0: int = 0, shift: int = 0,
+          splits: int = 0):
+    """dW[n, c] += sum_{b,t} dY[b,t,dy_col0+n] * X[b,t-shift,x_col0+c].  dY, X bf16 [B*T, ld]; dW fp32 [>=n_rows, ldw]."""
+    _chk(dY, bf16, "dY"), _chk(X, bf16, "X"), _chk(dW, f32, "dW")
+    d = _lib.WgradDesc()
+    d.B, d.T = B, T
+    d.dY, d.ldy, d.dy_batch_stride, d.dy_col0 = _p(dY), dY.shape[-1], T * dY.shape[-1], dy_col0
+    d.X, d.ldx, d.x_batch_stride, d.x_col0, d.x_shift = _p(X), X.shape[-1], T * X.shape[-1], x_col0, shift
+    d.n_rows, d.k_cols, d.dW, d.ldw, d.splits = n_rows, k_cols, _p(dW), dW.shape[-1], splits
+    check(lib.dn_wgrad(C.byref(d), _stream()), "dn_wgrad")
+    return dW
+
+
+def colsum(src, col0: int, cols: int, out):
+    _chk(src, bf16, "src"), _chk(out, f32, "out")
+    ld = src.shape[-1]
+    check(lib.dn_colsum_bf16(_p(src), src.numel() // ld, ld, col0, cols, _p(out), _stream()), "dn_colsum_bf16")
+    return out
+
+
+def geglu_fwd(h, m):
+    _chk(h, bf16, "h"), _chk(m, bf16, "m")
+    check(lib.dn_geglu_fwd(_p(h), m.shape[0], m.shape[1], _p(m), _stream()), "dn_geglu_fwd")
+    return m
+
+
+def geglu_bwd(h, dm, dh):
+    _chk(h, bf16, "h"), _chk(dm, bf16, "dm"), _chk(dh, bf16, "dh")
+    check(lib.dn_geglu_bwd(_p(h), _p(dm), dm.shape[0], dm.shape[1], _p(dh), _stream()), "dn_geglu_bwd")
+    return dh
+
+
+def wn_gate_fwd(ur, y, B, T, Cc, G, gb=None, gb_t_stride=0, g_gb=0, t_idx=None, t_idx_stride=0):
+    _chk(ur, bf16, "ur"), _chk(y, bf16, "y")
+    check(lib.dn_wn_gate_fwd(_p(ur), _p(y), B, T, Cc, G, _p(gb), gb_t_stride, g_gb, _p(t_idx), t_idx_stride, _stream()),
+          "dn_wn_gate_fwd")
+    return y
+
+
+def wn_gate_bwd(ur, dy, dur, B, T, Cc, G, gb=None, gb_t_stride=0, g_gb=0, t_idx=None, t_idx_stride=0, dgb=None,
+                dgb_b_stride=0, g_dgb=0):
+    _chk(ur, bf16, "ur"), _chk(dy, bf16, "dy"), _chk(dur, bf16, "dur")
+    check(lib.dn_wn_gate_bwd(_p(ur), _p(dy), _p(dur), B, T, Cc, G, _p(gb), gb_t_stride, g_gb, _p(t_idx), t_idx_stride,
+                             _p(dgb), dgb_b_stride, g_dgb, _stream()), "dn_wn_gate_bwd")
+    return dur
+
+
+def adarmsnorm_bwd(x, dy, dx, dx_bf16, B, T, gamma_p=None, dgamma_p=None, gb=None, gb_t_stride=0, t_idx=None,
+                   t_idx_stride=0, dgb=None, dgb_b_stride=0):
+    _chk(x, f32, "x"), _chk(dy, bf16, "dy"), _chk(dx, f32, "dx")
+    check(lib.dn_adarmsnorm_bwd(_p(x), _p(dy), _p(dx), _p(dx_bf16), B, T, x.shape[-1], _p(gamma_p), _p(dgamma_p), _p(gb),
+                                gb_t_stride, _p(t_idx), t_idx_stride, _p(dgb), dgb_b_stride, _stream()), "dn_adarmsnorm_bwd")
+    return dx
+
+
+def train_noise(z_lat, eps0, eps, beta0: float, coef, t_idx, x_t, xb):
+    B, T, z = z_lat.shape
+    check(lib.dn_train_noise(_p(_chk(z_lat, f32, "z")), _p(_chk(eps0, f32, "eps0")), _p(_chk(eps, f32, "eps")), beta0,
+                             _p(coef), _p(t_idx), B, T, z, _p(x_t), _p(xb), xb.shape[-1], _stream()), "dn_train_noise")
+    return x_t
+
+
+def noise_loss(pred, eps, lengths, coef, t_idx, B, T, z, loss, dpred=None, grad_scale: float = 1.0):
+    _chk(pred, f32, "pred"), _chk(eps, f32, "eps"), _chk(loss, f32, "loss")
+    check(lib.dn_noise_loss(_p(pred), pred.shape[-1], _p(eps), _p(lengths), _p(coef), _p(t_idx), B, T, z, _p(loss),
+                            _p(dpred), 0 if dpred is None else dpred.shape[-1], grad_scale, _stream()), "dn_noise_loss")
+    return loss
+
+
+def pred_x1(x_t, pred, coef, t_idx, B, T, z, xb):
+    check(lib.dn_pred_x1(_p(x_t), _p(pred), pred.shape[-1], _p(coef), _p(t_idx), B, T, z, _p(xb), xb.shape[-1], _stream()),
+          "dn_pred_x1")
+    return xb
+
+
+def decode_losses(recon, audio, logits, vocab: int, units, lengths, B, T):
+    _chk(recon, f32, "recon"), _chk(audio, f32, "audio"), _chk(logits, f32, "logits"), _chk(units, i64, "units")
+    out = torch.empty(6, dtype=torch.float64, device=recon.device)
+    check(lib.dn_decode_losses(_p(recon), _p(audio), recon.shape[-1], _p(logits), logits.shape[-1], vocab, _p(units),
+                               _p(lengths), B, T, _p(out), _stream()), "dn_decode_losses")
+    return out
+
+
+def dropout_bits(bits, p: float, seed: int, offset: int):
+    check(lib.dn_dropout_bits(_p(bits), bits.numel(), p, seed, offset, _stream()), "dn_dropout_bits")
+    return bits
+
+
+def attention_train(qkv, out, lse2, lengths, keep_bits, keep_scale: float, B, T, H, dh):
+    _chk(qkv, bf16, "qkv"), _chk(out, bf16, "out"), _chk(lse2, f32, "lse2")
+    check(lib.dn_attention_train(_p(qkv), _p(out), _p(lse2), _p(lengths), _p(keep_bits), keep_scale, B, T, H, dh, _stream()),
+          "dn_attention_train")
+    return out
+
+
+def attention_bwd(qkv, out, dout, lse2, lengths, keep_bits, keep_scale: float, dqkv, delta_ws, B, T, H, dh):
+    _chk(qkv, bf16, "qkv"), _chk(out, bf16, "out"), _chk(dout, bf16, "dout"), _chk(dqkv, bf16, "dqkv")
+    check(lib.dn_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse2), _p(lengths), _p(keep_bits), keep_scale, _p(dqkv),
+                               _p(delta_ws), B, T, H, dh, _stream()), "dn_attention_bwd")
+    return dqkv
+
+
+def silu(pre, out):
+    check(lib.dn_silu(_p(pre), _p(out), pre.numel(), _stream()), "dn_silu")
+    return out
+
+
+def silu_bwd(pre, dout, dpre):
+    check(lib.dn_silu_bwd(_p(pre), _p(dout), _p(dpre), pre.numel(), _stream()), "dn_silu_bwd")
+    return dpre
+
+
+def linear_f32_bwd(dY, X, W, dW=None, db=None, dX=None):
+    """dY fp32 [M, N] (row stride dY.stride(0)); dW[N,K] += dY^T X, db[N] += sum_m dY; dX[M,K] += dY W."""
+    M, N = dY.shape
+    K = X.shape[1] if X is not None else W.shape[1]
+    check(lib.dn_linear_f32_bwd(_p(dY), dY.stride(0), _p(X), _p(W), M, N, K, _p(dW), _p(db), _p(dX), _stream()),
+          "dn_linear_f32_bwd")
+
+
+def time_features_bwd(steps, w, dfeat, dw):
+    check(lib.dn_time_features_bwd(_p(steps), _p(w), _p(dfeat), steps.shape[0], w.shape[0], _p(dw), _stream()),
+          "dn_time_features_bwd")
+    return dw
+
+
+def add_bf16_to_f32(src, col0: int, Cc: int, dst, accumulate: bool):
+    _chk(src, bf16, "src"), _chk(dst, f32, "dst")
+    ld = src.shape[-1]
+    check(lib.dn_add_bf16_to_f32(_p(src), src.numel() // ld, ld, col0, Cc, _p(dst), dst.shape[-1], int(accumulate), _stream()),
+          "dn_add_bf16_to_f32")
+    return dst

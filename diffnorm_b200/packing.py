@@ -38,30 +38,32 @@ def pack_linear(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.E
     N, K = W.shape
     Kp = rup(K, BK) if k_pad is None else k_pad
     Np = rup(N, 16) if n_pad is None else n_pad
-    Wp = torch.zeros(Np, Kp)
+    Wp = torch.zeros(Np, Kp, device=W.device)
     Wp[:N, :K] = W
     bp = None
     if bias is not None:
-        bp = torch.zeros(Np)
+        bp = torch.zeros(Np, device=W.device)
         bp[:N] = bias.float()
     return GemmPlan(_bf(Wp), [(0, 0, Kp // BK, 0, 0)], Np, (Np + WT - 1) // WT, epi, bias=bp, name=name)
 
 
 def pack_conv3(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.EPI_BF16, cin_pad: Optional[int] = None,
-               n_pad: Optional[int] = None, dilation: int = 1, name: str = "") -> GemmPlan:
-    """W [N, Cin, 3] causal conv -> K = [tap0 | tap1 | tap2], shifts (2d, d, 0)."""
+               n_pad: Optional[int] = None, dilation: int = 1, name: str = "", shift_sign: int = 1) -> GemmPlan:
+    """W [N, Cin, 3] causal conv -> K = [tap0 | tap1 | tap2], shifts (2d, d, 0).
+    shift_sign = -1 reads x[t + (2-k) d] instead: the data-gradient of the conv when W is the (Cin, Cout)-transposed
+    kernel (dx[t] = sum_k W_k^T dy[t + (2-k) d]; frames past the utterance read as zero)."""
     N, Cin, Kk = W.shape
     assert Kk == 3
     Cp = rup(Cin, BK) if cin_pad is None else cin_pad
     Np = rup(N, 16) if n_pad is None else n_pad
-    Wp = torch.zeros(Np, 3 * Cp)
+    Wp = torch.zeros(Np, 3 * Cp, device=W.device)
     for k in range(3):
         Wp[:N, k * Cp:k * Cp + Cin] = W[:, :, k].float()
     bp = None
     if bias is not None:
-        bp = torch.zeros(Np)
+        bp = torch.zeros(Np, device=W.device)
         bp[:N] = bias.float()
-    segs = [(0, 2 - k, Cp // BK, k * Cp, 0) for k in range(3)]
+    segs = [(0, shift_sign * (2 - k), Cp // BK, k * Cp, 0) for k in range(3)]
     return GemmPlan(_bf(Wp), segs, Np, (Np + WT - 1) // WT, epi, bias=bp, dilation=dilation, name=name)
 
 
@@ -73,8 +75,8 @@ def pack_geglu(W: torch.Tensor, bias: torch.Tensor, name: str = "") -> GemmPlan:
     Kp = rup(K, BK)
     ip = rup(inner, 128)
     tiles = ip // 128
-    Wp = torch.zeros(tiles * WT, Kp)
-    bp = torch.zeros(tiles * WT)
+    Wp = torch.zeros(tiles * WT, Kp, device=W.device)
+    bp = torch.zeros(tiles * WT, device=W.device)
     for j in range(tiles):
         lo, hi = j * 128, min((j + 1) * 128, inner)
         if hi <= lo:
@@ -98,23 +100,34 @@ def pack_wavenet_level(convs: List[torch.Tensor], conv_b: List[torch.Tensor], re
     assert Cp % 128 == 0 and Cp >= Cc
     tiles = Cp // 128
     rows_g = tiles * WT
-    Wp = torch.zeros(G * rows_g, 3 * Cp)
-    bc = torch.zeros(G * Cp)
-    br = torch.zeros(G * Cp)
+    dev = convs[0].device
+    Wp = torch.zeros(G * rows_g, 3 * Cp, device=dev)
+    bc = torch.zeros(G * Cp, device=dev)
+    br = torch.zeros(G * Cp, device=dev)
     order = (2, 0, 1)  # K position -> conv tap
-    for g in range(G):
-        cw, rw = convs[g].float(), ress[g].float().reshape(Cc, Cc)
-        for j in range(tiles):
-            lo, hi = j * 128, min((j + 1) * 128, Cc)
-            if hi <= lo:
-                continue
-            n = hi - lo
-            r0 = g * rows_g + j * WT
-            for pos, tap in enumerate(order):
-                Wp[r0:r0 + n, pos * Cp:pos * Cp + Cc] = cw[lo:hi, :, tap]
-            Wp[r0 + 128:r0 + 128 + n, 0:Cc] = rw[lo:hi]
-        bc[g * Cp:g * Cp + Cc] = conv_b[g].float()
-        br[g * Cp:g * Cp + Cc] = res_b[g].float()
+    if Cc == Cp:  # vectorised form (denoiser: C = 512); same layout as the loop below
+        cw = torch.stack([c.float() for c in convs])                       # [G, C, C, 3]
+        rw = torch.stack([r.float().reshape(Cc, Cc) for r in ress])        # [G, C, C]
+        v = Wp.view(G, tiles, 2, 128, 3 * Cp)
+        for pos, tap in enumerate(order):
+            v[:, :, 0, :, pos * Cp:(pos + 1) * Cp] = cw[..., tap].reshape(G, tiles, 128, Cc)
+        v[:, :, 1, :, 0:Cp] = rw.reshape(G, tiles, 128, Cc)
+        bc = torch.cat([b.float() for b in conv_b])
+        br = torch.cat([b.float() for b in res_b])
+    else:
+        for g in range(G):
+            cw, rw = convs[g].float(), ress[g].float().reshape(Cc, Cc)
+            for j in range(tiles):
+                lo, hi = j * 128, min((j + 1) * 128, Cc)
+                if hi <= lo:
+                    continue
+                n = hi - lo
+                r0 = g * rows_g + j * WT
+                for pos, tap in enumerate(order):
+                    Wp[r0:r0 + n, pos * Cp:pos * Cp + Cc] = cw[lo:hi, :, tap]
+                Wp[r0 + 128:r0 + 128 + n, 0:Cc] = rw[lo:hi]
+            bc[g * Cp:g * Cp + Cc] = conv_b[g].float()
+            br[g * Cp:g * Cp + Cc] = res_b[g].float()
     kb = Cp // BK
     segs = [(0, 0, kb, 0, 0), (0, 2, kb, Cp, 128), (0, 1, kb, 2 * Cp, 128)]
     return GemmPlan(_bf(Wp), segs, Cp, tiles, _lib.EPI_WN_GATE, bias=bc, bias2=br, groups=G, g_w_row=rows_g,
@@ -126,10 +139,44 @@ def pack_skip_sum(skips: List[torch.Tensor], skip_b: List[torch.Tensor], c_pad: 
     Writes all c_pad output columns (the pad columns get exact zeros)."""
     G = len(skips)
     Cc = skips[0].shape[0]
-    Wp = torch.zeros(c_pad, G * c_pad)
+    Wp = torch.zeros(c_pad, G * c_pad, device=skips[0].device)
     for g in range(G):
         Wp[:Cc, g * c_pad:g * c_pad + Cc] = skips[g].float().reshape(Cc, Cc)
-    bp = torch.zeros(c_pad)
+    bp = torch.zeros(c_pad, device=skips[0].device)
     bp[:Cc] = torch.stack([b.float() for b in skip_b]).sum(0)
     Np = Wp.shape[0]
     return GemmPlan(_bf(Wp), [(0, 0, G * c_pad // BK, 0, 0)], Np, (Np + WT - 1) // WT, _lib.EPI_BF16, bias=bp, name=name)
+
+
+# ------------------------------------------------------------------------------------------------ training-step packings
+def geglu_row_map(inner: int) -> torch.Tensor:
+    """Packed GEGLU row r (tile j: 128 x rows, 128 gate rows) -> row of the reference Linear weight [2*inner, K], or -1
+    for a padding row."""
+    ip = rup(inner, 128)
+    m = torch.full((2 * ip,), -1, dtype=torch.long)
+    for j in range(ip // 128):
+        lo, hi = j * 128, min((j + 1) * 128, inner)
+        if hi > lo:
+            m[j * WT:j * WT + hi - lo] = torch.arange(lo, hi)
+            m[j * WT + 128:j * WT + 128 + hi - lo] = inner + torch.arange(lo, hi)
+    return m
+
+
+def pack_wavenet_level_dgrad(convs: List[torch.Tensor], ress: List[torch.Tensor], c_pad: int, name: str = "") -> GemmPlan:
+    """Data-gradient of one WaveNet level for all chains: input dur [.., G*2C] per chain [du | dres], output da_g =
+    sum_k conv_k^T du[t + (2-k) d_g] + res^T dres[t].  K layout per chain: [conv_2^T | res^T | conv_0^T | conv_1^T]."""
+    G = len(convs)
+    Cc, Cp = convs[0].shape[0], c_pad
+    dev = convs[0].device
+    Wp = torch.zeros(G, Cp, 4 * Cp, device=dev)
+    cw = torch.stack([c.float() for c in convs])                       # [G, Cout, Cin, 3]
+    rw = torch.stack([r.float().reshape(Cc, Cc) for r in ress])
+    Wp[:, :Cc, 0:Cc] = cw[..., 2].transpose(1, 2)
+    Wp[:, :Cc, Cp:Cp + Cc] = rw.transpose(1, 2)
+    Wp[:, :Cc, 2 * Cp:2 * Cp + Cc] = cw[..., 0].transpose(1, 2)
+    Wp[:, :Cc, 3 * Cp:3 * Cp + Cc] = cw[..., 1].transpose(1, 2)
+    Wp = Wp.view(G * Cp, 4 * Cp)
+    kb = Cp // BK
+    segs = [(0, 0, 2 * kb, 0, 0), (0, -2, kb, 2 * Cp, 0), (0, -1, kb, 3 * Cp, 0)]
+    return GemmPlan(_bf(Wp), segs, Cp, (Cp + WT - 1) // WT, _lib.EPI_BF16, groups=G, g_w_row=Cp, g_bias=0, dilation=1,
+                    dilation_shl_group=1, name=name)

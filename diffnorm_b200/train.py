@@ -1,0 +1,386 @@
+"""Training step of the denoiser: ``LatentDiscreteModel.forward`` (LM:1514-1613, multitask=False:
+the latent-noise MSE) and its backward, hand-scheduled over the sm_100a kernels.  torch is memory / streams only.
+
+Per step (one batch of B utterances x T frames, per-utterance timestep t_b):
+  forward   frozen VAE encode (inference engine) -> x_t -> time MLP -> gamma/beta of the 56 conditioned modules ->
+            WaveNet (GEMM -> un-fused FiLM/gate so u and res are kept) -> 12 transformer layers (norm, QKV GEMM,
+            attention with dropout + saved row statistics, out GEMM; norm, GEGLU GEMM -> un-fused GEGLU, conv GEMM,
+            out GEMM) -> to_pred -> eps_hat -> weighted masked MSE (+ the decode branch's logging losses).
+  backward  the same GEMM kernel over transposed weight packings (data gradients; conv taps read t + shift),
+            dn_wgrad (weight gradients straight from the row-major activations), column sums (biases), the
+            elementwise backward kernels, the two attention-backward kernels, and the fp32 time-MLP backward.
+Gradients are returned as fp32 tensors keyed like ``Model.named_parameters()``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .config import DiffNormConfig
+from .ops import GemmPlan
+from .packing import (BK, WT, geglu_row_map, pack_conv3, pack_geglu, pack_linear, pack_skip_sum, pack_wavenet_level,
+                      pack_wavenet_level_dgrad, rup)
+from .schedule import DDPMScheduler
+
+bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
+
+
+def pack_keep_bits(keep: torch.Tensor) -> torch.Tensor:
+    """bool [B,H,T,T] (True = kept) -> int32 words [B,H,T,ceil(T/32)]: bit k%32 of word k/32 = key k."""
+    B, H, T, _ = keep.shape
+    Tw = (T + 31) // 32
+    k = torch.zeros(B, H, T, Tw * 32, dtype=torch.int64)
+    k[..., :T] = keep.to(torch.int64).cpu()
+    w = (k.view(B, H, T, Tw, 32) << torch.arange(32, dtype=torch.int64)).sum(-1)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.to(torch.int32).contiguous()
+
+
+class _Plans:
+    pass
+
+
+class DenoiserTrainer:
+    def __init__(self, ldm, drop_p: float = 0.1, seed: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DenoiserTrainer needs a CUDA device: the product has no CPU path")
+        if getattr(ldm, "multitask", False):
+            raise NotImplementedError("multitask=True back-propagates through decode_feature (LM:1572-1604); only the "
+                                      "latent-noise loss (multitask=False, BASELINE config 5) is built")
+        self.ldm = ldm
+        self.cfg: DiffNormConfig = ldm.cfg
+        self.P: Dict[str, torch.nn.Parameter] = dict(ldm.model.named_parameters())
+        self.dev = next(iter(self.P.values())).device
+        self.drop_p, self.seed, self.step_no = drop_p, seed, 0
+        from .engine import DiffNormEngine
+        sd = {k: v for k, v in ldm.state_dict().items()}
+        self.vae = DiffNormEngine(sd, device=str(self.dev), cfg=self.cfg, vae_only=True)   # frozen VAE
+        c = self.cfg
+        s = DDPMScheduler(c.timesteps)
+        self.sched = s
+        coef = np.zeros((c.timesteps, 4), dtype=np.float32)
+        sa, s1 = s.sqrt_alphas_cumprod.astype(np.float32), s.sqrt_one_minus_alphas_cumprod.astype(np.float32)
+        snr = (sa ** 2) / (s1 ** 2)                       # LM:1283-1286, fp32 like the reference
+        coef[:, 0], coef[:, 1], coef[:, 2] = sa, s1, np.minimum(snr, np.float32(5.0)) / snr
+        self.coef = torch.from_numpy(coef).to(self.dev)
+        self.beta0 = float(np.float32(s.betas[0]))
+        self.ws: Dict[tuple, torch.Tensor] = {}
+        self.cond_names = [f"wavenet.stacks.{st}.blocks.{i}.to_time_cond" for st in range(c.wn_stacks)
+                           for i in range(c.wn_layers)]
+        for l in range(c.depth):
+            self.cond_names += [f"transformer.layers.{l}.0.to_gamma_beta", f"transformer.layers.{l}.4.to_gamma_beta"]
+        self.n_cond, self.gbw = len(self.cond_names), 2 * c.hid
+        self.inner = DiffNormConfig.ff_inner(c.hid)
+        self.ip = rup(self.inner, 128)
+        self.row_map = geglu_row_map(self.inner).to(self.dev)
+        self.zp, self.zn = rup(c.latent_dim, 64), rup(c.latent_dim, 16)
+        self._pe: Dict[int, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def buf(self, name: str, rows: int, width: int, dtype=bf16, zero: bool = False) -> torch.Tensor:
+        key = (name, width, dtype)
+        t = self.ws.get(key)
+        if t is None or t.shape[0] < rows:
+            t = torch.zeros(rows, width, dtype=dtype, device=self.dev)
+            self.ws[key] = t
+        v = t[:rows]
+        if zero:
+            v.zero_()
+        return v
+
+    def _run(self, plan: GemmPlan, A, out, B, T, **kw):
+        return plan.run(A, out, B, T, **kw)
+
+    # ------------------------------------------------------------------------------------------------ packing (per step)
+    def _pack(self) -> _Plans:
+        c, P, ip, dev = self.cfg, self.P, self.ip, self.dev
+        C = c.hid
+        pl = _Plans()
+        w = lambda k: P[k].detach()
+        pl.init = pack_linear(w("init_conv.weight"), w("init_conv.bias"), k_pad=self.zp, name="init_conv")
+        pl.wn_init = pack_conv3(w("wavenet.init_conv.weight"), w("wavenet.init_conv.bias"), cin_pad=C, n_pad=C, name="wn.init")
+        pl.wn_init_T = pack_conv3(w("wavenet.init_conv.weight").permute(1, 0, 2), None, cin_pad=C, n_pad=C, shift_sign=-1,
+                                  name="wn.init^T")
+        pl.lvl, pl.lvl_T = [], []
+        G = c.wn_layers
+        for s in range(c.wn_stacks):
+            blk = [f"wavenet.stacks.{s}.blocks.{i}." for i in range(G)]
+            convs, ress = [w(b + "conv.weight") for b in blk], [w(b + "res_conv.weight") for b in blk]
+            lv = pack_wavenet_level(convs, [w(b + "conv.bias") for b in blk], ress, [w(b + "res_conv.bias") for b in blk], C,
+                                    name=f"wn.lvl{s}")
+            # un-fused form: plain +bias epilogue over the same packed tiles -> [conv 128 | res 128] column blocks
+            tiles = C // 128
+            bi = torch.stack([lv.bias.view(G, tiles, 128), lv.bias2.view(G, tiles, 128)], dim=2).reshape(-1).contiguous()
+            fwd = GemmPlan(lv.W, lv.segs, 2 * C, tiles, _lib.EPI_BF16, bias=bi, groups=G, g_w_row=lv.g_w_row, g_bias=2 * C,
+                           dilation=1, dilation_shl_group=1, name=f"wn.lvl{s}.ur")
+            pl.lvl.append(fwd)
+            pl.lvl_T.append(pack_wavenet_level_dgrad(convs, ress, C, name=f"wn.lvl{s}^T"))
+        last = [f"wavenet.stacks.{c.wn_stacks - 1}.blocks.{i}." for i in range(G)]
+        skips = [w(b + "skip_conv.weight") for b in last]
+        pl.skip = pack_skip_sum(skips, [w(b + "skip_conv.bias") for b in last], C, name="wn.skip")
+        pl.skip_T = pack_linear(torch.cat([sk.reshape(C, C).t() for sk in skips], 0), None, k_pad=C, n_pad=G * C, name="wn.skip^T")
+        pl.wn_final = pack_linear(w("wavenet.final_conv.weight"), w("wavenet.final_conv.bias"), epi=_lib.EPI_F32, k_pad=C,
+                                  n_pad=C, name="wn.final")
+        pl.wn_final_T = pack_linear(w("wavenet.final_conv.weight").reshape(C, C).t(), None, k_pad=C, n_pad=C, name="wn.final^T")
+        pl.layers = []
+        for l in range(c.depth):
+            p = f"transformer.layers.{l}."
+            L = _Plans()
+            wqkv = torch.cat([w(p + "1.to_q.weight"), w(p + "1.to_kv.weight")], 0)
+            L.qkv = pack_linear(wqkv, None, name=p + "qkv")
+            L.qkv_T = pack_linear(wqkv.t(), None, name=p + "qkv^T")
+            L.out = pack_linear(w(p + "1.to_out.weight"), None, epi=_lib.EPI_RESID, name=p + "to_out")
+            L.out_T = pack_linear(w(p + "1.to_out.weight").t(), None, name=p + "to_out^T")
+            g = pack_geglu(w(p + "5.0.weight"), w(p + "5.0.bias"), name=p + "ff.geglu")
+            L.ff1 = GemmPlan(g.W, g.segs, 2 * ip, g.n_tiles, _lib.EPI_BF16, bias=g.bias, name=p + "ff.h")
+            L.ff1_T = GemmPlan(g.W.t().contiguous(), [(0, 0, 2 * ip // BK, 0, 0)], C, (C + WT - 1) // WT, _lib.EPI_BF16,
+                               name=p + "ff.h^T")
+            wc = w(p + "5.2.1.weight")
+            L.ffc = pack_conv3(wc, w(p + "5.2.1.bias"), cin_pad=ip, n_pad=ip, name=p + "ff.conv")
+            L.ffc_T = pack_conv3(wc.permute(1, 0, 2), None, cin_pad=ip, n_pad=ip, shift_sign=-1, name=p + "ff.conv^T")
+            L.ff3 = pack_linear(w(p + "5.3.weight"), w(p + "5.3.bias"), epi=_lib.EPI_RESID, k_pad=ip, name=p + "ff.out")
+            L.ff3_T = pack_linear(w(p + "5.3.weight").t(), None, k_pad=C, n_pad=ip, name=p + "ff.out^T")
+            pl.layers.append(L)
+        pl.pred = pack_linear(w("transformer.to_pred.1.weight"), None, name="to_pred")
+        pl.pred_T = pack_linear(w("transformer.to_pred.1.weight").t(), None, name="to_pred^T")
+        pl.proj = pack_linear(w("final_proj.weight"), w("final_proj.bias"), epi=_lib.EPI_F32, n_pad=self.zn, name="final_proj")
+        pl.proj_T = pack_linear(w("final_proj.weight").t(), None, k_pad=self.zp, n_pad=C, name="final_proj^T")
+        pl.Wcat = torch.cat([w(n + ".weight") for n in self.cond_names], 0).contiguous()       # [56 * 1024, 2048]
+        pl.bcat = torch.cat([w(n + ".bias") for n in self.cond_names], 0).contiguous()
+        return pl
+
+    def pe_table(self, T: int) -> torch.Tensor:
+        t = self._pe.get(T)
+        if t is None:
+            half = self.cfg.hid // 2
+            e = np.log(10000.0) / (half - 1)
+            freq = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+            ang = torch.arange(T + 1, dtype=torch.float)[:, None] * freq[None, :]
+            tab = torch.cat([ang.sin(), ang.cos()], dim=1)
+            tab[0] = 0
+            t = tab.to(self.dev).contiguous()
+            self._pe[T] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def step(self, audio: torch.Tensor, units: Optional[torch.Tensor], lengths: torch.Tensor,
+             times: Optional[torch.Tensor] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
+             keep_bits: Optional[Sequence[torch.Tensor]] = None, backward: bool = True, decode_losses: bool = True,
+             grad_scale: float = 1.0):
+        """audio fp32 [B,T,768] cuda; units int64 [B,T] (0 = pad, unit k -> k+4) or None; lengths int32 [B].
+        times int [B] in [1, timesteps) (drawn if None, LM:1528); noise = {"vae": [B,z,T], "eps0": [B,T,z], "eps": [B,T,z]}
+        replays the draws; keep_bits = per layer int32 [B,H,T,ceil(T/32)] (drawn with Philox if None and drop_p > 0).
+        Returns (loss dict of 0-d tensors, grads dict name -> fp32 tensor) ; grads = {} when backward=False."""
+        c, dev = self.cfg, self.dev
+        B, T, _ = audio.shape
+        M, z, C, G, S = B * T, c.latent_dim, c.hid, c.wn_layers, c.wn_stacks
+        H, dh, ip, zp, zn = c.heads, c.dim_head, self.ip, self.zp, self.zn
+        noise = noise or {}
+        lens = lengths.to(device=dev, dtype=i32).contiguous()
+        t_idx = (torch.randint(1, c.timesteps, (B,), device=dev) if times is None else times.to(dev)).to(i32).contiguous()
+        eps_vae = noise.get("vae")
+        eps_vae = torch.randn(B, z, T, device=dev) if eps_vae is None else eps_vae.to(dev).float().contiguous()
+        eps0 = noise.get("eps0")
+        eps0 = torch.randn(B, T, z, device=dev) if eps0 is None else eps0.to(dev).float().contiguous()
+        eps = noise.get("eps")
+        eps = torch.randn(B, T, z, device=dev) if eps is None else eps.to(dev).float().contiguous()
+        drop = self.drop_p > 0 or keep_bits is not None
+        keep_scale = 1.0 / (1.0 - self.drop_p) if drop else 1.0
+        Tw = (T + 31) // 32
+        if drop and keep_bits is None:
+            keep_bits = []
+            for l in range(c.depth):
+                kb = torch.empty(B, H, T, Tw, dtype=i32, device=dev)
+                ops.dropout_bits(kb, self.drop_p, self.seed, self.step_no * c.depth + l)
+                keep_bits.append(kb)
+        self.step_no += 1
+        pl = self._pack()
+        rows = torch.arange(B, dtype=i32, device=dev)
+        gstride = self.n_cond * self.gbw
+
+        # ---- frozen VAE encode + noising (LM:1521-1535)
+        zlat = self.vae.encode(audio.float().contiguous(), eps_vae)
+        x_t = self.buf("x_t", M, z, f32)
+        xb = self.buf("xb", M, zp)
+        ops.train_noise(zlat.contiguous(), eps0, eps, self.beta0, self.coef, t_idx, x_t, xb)
+
+        # ---- time conditioning (LM:104-116, :741-745, :507, :624)
+        P = self.P
+        tw = P["to_time_cond.0.weights"].detach().float().contiguous()
+        W1, b1 = P["to_time_cond.1.weight"].detach().contiguous(), P["to_time_cond.1.bias"].detach().contiguous()
+        feats = ops.time_features(t_idx, tw)
+        pre = ops.linear_f32(feats, W1, b1, act=0)
+        temb = ops.silu(pre, torch.empty_like(pre))
+        gball = ops.linear_f32(temb, pl.Wcat, pl.bcat)                 # [B, 56 * 1024]
+        gflat = gball.view(-1)
+        gbk = dict(gb_t_stride=gstride, t_idx=rows, t_idx_stride=1)
+
+        # ---- denoiser forward (LM:828-876), keeping what backward needs
+        sv = {}
+        h0 = self._run(pl.init, xb, self.buf("h0", M, C), B, T)
+        hw = self._run(pl.wn_init, h0, self.buf("hw", M, C), B, T)
+        src, g_a_col = hw, 0
+        for s in range(S):
+            ur = self._run(pl.lvl[s], src, self.buf(f"ur{s}", M, G * 2 * C), B, T, g_a_col=g_a_col, g_out_col=2 * C)
+            y = ops.wn_gate_fwd(ur, self.buf(f"y{s}", M, G * C), B, T, C, G, gb=gflat[s * G * self.gbw:], g_gb=self.gbw, **gbk)
+            sv[f"ur{s}"], sv[f"y{s}"] = ur, y
+            src, g_a_col = y, C
+        sk = self._run(pl.skip, src, self.buf("sk", M, C), B, T)
+        x = self._run(pl.wn_final, sk, self.buf("x", M, C, f32), B, T, pe=self.pe_table(T), lengths=lens)
+        n0 = S * G
+        for l, L in enumerate(pl.layers):
+            xs1 = self.buf(f"xs1.{l}", M, C, f32)
+            xs1.copy_(x)
+            hb1 = ops.adarmsnorm(x, self.buf(f"hb1.{l}", M, C), B, T, None, gflat[(n0 + 2 * l) * self.gbw:], gstride, rows, 1)
+            qkv = self._run(L.qkv, hb1, self.buf(f"qkv.{l}", M, 3 * H * dh), B, T)
+            lse = self.buf(f"lse.{l}", B * H, T, f32)
+            ao = ops.attention_train(qkv, self.buf(f"ao.{l}", M, H * dh), lse, lens, keep_bits[l] if drop else None, keep_scale,
+                                     B, T, H, dh)
+            self._run(L.out, ao, x, B, T)
+            xs2 = self.buf(f"xs2.{l}", M, C, f32)
+            xs2.copy_(x)
+            hb2 = ops.adarmsnorm(x, self.buf(f"hb2.{l}", M, C), B, T, None, gflat[(n0 + 2 * l + 1) * self.gbw:], gstride, rows, 1)
+            hh = self._run(L.ff1, hb2, self.buf(f"h.{l}", M, 2 * ip), B, T)
+            m1 = ops.geglu_fwd(hh, self.buf(f"m1.{l}", M, ip))
+            m2 = self._run(L.ffc, m1, self.buf(f"m2.{l}", M, ip), B, T)
+            self._run(L.ff3, m2, x, B, T)
+            sv[l] = (xs1, hb1, qkv, lse, ao, xs2, hb2, hh, m1, m2)
+        gpred = P["transformer.to_pred.0.gamma"].detach().float().contiguous()
+        hbf = ops.adarmsnorm(x, self.buf("hbf", M, C), B, T, gpred)
+        pb = self._run(pl.pred, hbf, self.buf("pb", M, C), B, T)
+        eh = self._run(pl.proj, pb, self.buf("eh", M, zn, f32), B, T)
+
+        # ---- losses (LM:1563-1611)
+        loss = torch.zeros(1, dtype=f32, device=dev)
+        dpred = self.buf("dpred", M, zp) if backward else None
+        ops.noise_loss(eh, eps, lens, self.coef, t_idx, B, T, z, loss, dpred, grad_scale)
+        out = {"noise_loss": loss[0], "total_loss": loss[0]}
+        if decode_losses and units is not None:
+            xb1 = ops.pred_x1(x_t, eh, self.coef, t_idx, B, T, z, self.buf("xb1", M, zp))
+            recon, logits = self.vae.decode(xb1, lens, B, T)
+            st = ops.decode_losses(recon.contiguous().view(M, -1), audio.float().contiguous().view(M, -1),
+                                   logits.contiguous().view(M, -1), c.vocab, units.to(dev).to(i64).contiguous().view(-1), lens, B, T)
+            e_i = 0.1 / (c.vocab - 1)
+            ntok = st[4].clamp(min=1)
+            out["recon_mse_loss"] = (st[0] / (st[5].clamp(min=1) * c.feat_dim)).float()
+            out["nll_loss"] = (((1.0 - 0.1 - e_i) * st[1] + e_i * st[2]) / ntok).float()
+            out["acc"] = (st[3] / ntok).float()
+        out["pred_noise"] = eh.view(B, T, zn)[..., :z]
+        if not backward:
+            return out, {}
+
+        # ================================================================================================ backward
+        grads: Dict[str, torch.Tensor] = {}
+        zeros = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
+
+        def wg(dY, X, n_rows, k_cols, dy_col0=0, x_col0=0, shift=0, flat=True):
+            dW = zeros(n_rows, rup(k_cols, 4))
+            if flat and shift == 0:
+                ops.wgrad(dY, X, dW, 1, M, n_rows, k_cols, dy_col0, x_col0, 0)
+            else:
+                ops.wgrad(dY, X, dW, B, T, n_rows, k_cols, dy_col0, x_col0, shift)
+            return dW
+
+        def cs(src, col0, cols):
+            return ops.colsum(src, col0, cols, zeros(cols))
+
+        dgball = zeros(B, gstride)
+        # final_proj (Linear 512 -> z) and to_pred
+        grads["final_proj.weight"] = wg(dpred, pb, z, C)[:, :C]
+        grads["final_proj.bias"] = cs(dpred, 0, zn)[:z]
+        dpb = self._run(pl.proj_T, dpred, self.buf("dpb", M, C), B, T)
+        grads["transformer.to_pred.1.weight"] = wg(dpb, hbf, C, C)
+        dhbf = self._run(pl.pred_T, dpb, self.buf("dhb", M, C), B, T)
+        dx = self.buf("dx", M, C, f32, zero=True)
+        dxb = self.buf("dxb", M, C)
+        dgam = zeros(C)
+        ops.adarmsnorm_bwd(x, dhbf, dx, dxb, B, T, gamma_p=gpred, dgamma_p=dgam)
+        grads["transformer.to_pred.0.gamma"] = dgam
+        for l in reversed(range(c.depth)):
+            L = pl.layers[l]
+            p = f"transformer.layers.{l}."
+            xs1, hb1, qkv, lse, ao, xs2, hb2, hh, m1, m2 = sv[l]
+            # feed-forward branch
+            grads[p + "5.3.weight"] = wg(dxb, m2, C, ip)[:, :self.inner]
+            grads[p + "5.3.bias"] = cs(dxb, 0, C)
+            dm2 = self._run(L.ff3_T, dxb, self.buf("dm2", M, ip), B, T)
+            taps = [wg(dm2, m1, ip, ip, shift=2 - k, flat=False)[:self.inner, :self.inner] for k in range(3)]
+            grads[p + "5.2.1.weight"] = torch.stack(taps, dim=-1)
+            grads[p + "5.2.1.bias"] = cs(dm2, 0, ip)[:self.inner]
+            dm1 = self._run(L.ffc_T, dm2, self.buf("dm1", M, ip), B, T)
+            dh_ = ops.geglu_bwd(hh, dm1, self.buf("dh", M, 2 * ip))
+            dW1p = wg(dh_, hb2, 2 * ip, C)
+            db1p = cs(dh_, 0, 2 * ip)
+            valid = self.row_map >= 0
+            gw = zeros(2 * self.inner, C)
+            gw[self.row_map[valid]] = dW1p[valid]
+            gb_ = zeros(2 * self.inner)
+            gb_[self.row_map[valid]] = db1p[valid]
+            grads[p + "5.0.weight"], grads[p + "5.0.bias"] = gw, gb_
+            dhb = self._run(L.ff1_T, dh_, self.buf("dhb", M, C), B, T)
+            ops.adarmsnorm_bwd(xs2, dhb, dx, dxb, B, T, gb=gflat[(n0 + 2 * l + 1) * self.gbw:], dgb=dgball.view(-1)[(n0 + 2 * l + 1) * self.gbw:],
+                               dgb_b_stride=gstride, **gbk)
+            # attention branch
+            grads[p + "1.to_out.weight"] = wg(dxb, ao, C, H * dh)
+            dao = self._run(L.out_T, dxb, self.buf("dao", M, H * dh), B, T)
+            dqkv = ops.attention_bwd(qkv, ao, dao, lse, lens, keep_bits[l] if drop else None, keep_scale,
+                                     self.buf("dqkv", M, 3 * H * dh), self.buf("delta", B * H, T, f32), B, T, H, dh)
+            dWqkv = wg(dqkv, hb1, 3 * H * dh, C)
+            grads[p + "1.to_q.weight"], grads[p + "1.to_kv.weight"] = dWqkv[:H * dh], dWqkv[H * dh:]
+            dhb = self._run(L.qkv_T, dqkv, self.buf("dhb", M, C), B, T)
+            ops.adarmsnorm_bwd(xs1, dhb, dx, dxb, B, T, gb=gflat[(n0 + 2 * l) * self.gbw:], dgb=dgball.view(-1)[(n0 + 2 * l) * self.gbw:],
+                               dgb_b_stride=gstride, **gbk)
+        # WaveNet: final 1x1 conv (+PE), skip sum, 4 levels x 8 chains, init conv
+        grads["wavenet.final_conv.weight"] = wg(dxb, sk, C, C).view(C, C, 1)
+        grads["wavenet.final_conv.bias"] = cs(dxb, 0, C)
+        dsk = self._run(pl.wn_final_T, dxb, self.buf("dsk", M, C), B, T)
+        dWs = wg(dsk, sv[f"y{S - 1}"], C, G * C)
+        dbs = cs(dsk, 0, C)
+        for g in range(G):
+            b_ = f"wavenet.stacks.{S - 1}.blocks.{g}."
+            grads[b_ + "skip_conv.weight"] = dWs[:, g * C:(g + 1) * C].reshape(C, C, 1)
+            grads[b_ + "skip_conv.bias"] = dbs
+        dy = self._run(pl.skip_T, dsk, self.buf("dyA", M, G * C), B, T)
+        dy_next = "dyB"
+        for s in reversed(range(S)):
+            dur = ops.wn_gate_bwd(sv[f"ur{s}"], dy, self.buf("dur", M, G * 2 * C), B, T, C, G, gb=gflat[s * G * self.gbw:],
+                                  g_gb=self.gbw, dgb=dgball.view(-1)[s * G * self.gbw:], dgb_b_stride=gstride, g_dgb=self.gbw, **gbk)
+            inp = sv[f"y{s - 1}"] if s > 0 else hw
+            for g in range(G):
+                b_ = f"wavenet.stacks.{s}.blocks.{g}."
+                xc = g * C if s > 0 else 0
+                taps = [wg(dur, inp, C, C, dy_col0=g * 2 * C, x_col0=xc, shift=(2 - k) * (1 << g), flat=False) for k in range(3)]
+                grads[b_ + "conv.weight"] = torch.stack(taps, dim=-1)
+                grads[b_ + "conv.bias"] = cs(dur, g * 2 * C, C)
+                grads[b_ + "res_conv.weight"] = wg(dur, inp, C, C, dy_col0=g * 2 * C + C, x_col0=xc).view(C, C, 1)
+                grads[b_ + "res_conv.bias"] = cs(dur, g * 2 * C + C, C)
+            if s > 0:
+                dy = self._run(pl.lvl_T[s], dur, self.buf(dy_next, M, G * C), B, T, g_a_col=2 * C, g_out_col=C)
+                dy_next = "dyA" if dy_next == "dyB" else "dyB"
+            else:
+                dhw32 = self.buf("dhw32", M, C, f32, zero=True)
+                self._run(pl.lvl_T[0], dur, dhw32, B, T, g_a_col=2 * C, g_out_col=0, epi=_lib.EPI_RESID)
+                dhw = ops.cast_pad_bf16(dhw32, C, out=self.buf("dhw", M, C))
+        taps = [wg(dhw, h0, C, C, shift=2 - k, flat=False) for k in range(3)]
+        grads["wavenet.init_conv.weight"] = torch.stack(taps, dim=-1)
+        grads["wavenet.init_conv.bias"] = cs(dhw, 0, C)
+        dh0 = self._run(pl.wn_init_T, dhw, self.buf("dh0", M, C), B, T)
+        grads["init_conv.weight"] = wg(dh0, xb, C, z)[:, :z].reshape(C, z, 1)
+        grads["init_conv.bias"] = cs(dh0, 0, C)
+        # time conditioning: 56 Linear(2048 -> 1024), SiLU, Linear(513 -> 2048), learned sinusoid weights
+        dWcat, dbcat = zeros(*pl.Wcat.shape), zeros(*pl.bcat.shape)
+        dtemb = zeros(B, temb.shape[1])
+        ops.linear_f32_bwd(dgball, temb, pl.Wcat, dW=dWcat, db=dbcat, dX=dtemb)
+        for i, n in enumerate(self.cond_names):
+            grads[n + ".weight"] = dWcat[i * self.gbw:(i + 1) * self.gbw]
+            grads[n + ".bias"] = dbcat[i * self.gbw:(i + 1) * self.gbw]
+        dpre = ops.silu_bwd(pre, dtemb, torch.empty_like(pre))
+        dW1, db1_, dfeat = zeros(*W1.shape), zeros(*b1.shape), zeros(B, feats.shape[1])
+        ops.linear_f32_bwd(dpre, feats, W1, dW=dW1, db=db1_, dX=dfeat)
+        grads["to_time_cond.1.weight"], grads["to_time_cond.1.bias"] = dW1, db1_
+        grads["to_time_cond.0.weights"] = ops.time_features_bwd(t_idx, tw, dfeat, zeros(tw.shape[0]))
+        return out, grads

@@ -182,6 +182,93 @@ int dn_gemm(const dn_gemm_desc* d, int32_t impl, void* stream);
 int dn_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H, int32_t dh,
                  void* stream);
 
+/* ---- denoiser training step (LatentDiscreteModel.forward, LM:1514-1613, and its backward) ----------------- */
+/* Forward runs the same GEMM / conv / norm kernels as the normalization pass with per-utterance timesteps
+ * (t_idx_stride = 1) and the un-fused epilogues below, which keep the pre-activations backward needs.
+ * Backward = dn_gemm over transposed weight packings (dgrad) + dn_wgrad + the elementwise kernels below.
+ * Accumulating outputs ("+=") must be zeroed by the caller at the start of a step. */
+
+/* Weight-gradient GEMM:  dW[n, c] += sum_{b,t} dY[b, t, dy_col0 + n] * X[b, t - x_shift, x_col0 + c]
+ * (bf16 operands in their row-major [B, T, C] layout, fp32 accumulation, split-K with TMA reduce-add).
+ * Rows with t - x_shift outside [0, T) read as zero: a conv tap k of dilation d uses x_shift = (2-k) d. */
+typedef struct {
+    int32_t B, T;
+    const void* dY; int32_t ldy; int64_t dy_batch_stride; int32_t dy_col0;
+    const void* X;  int32_t ldx; int64_t x_batch_stride;  int32_t x_col0; int32_t x_shift;
+    int32_t n_rows, k_cols;     /* extent of dW */
+    float* dW; int32_t ldw;
+    int32_t splits;             /* <= 0: chosen by the library */
+} dn_wgrad_desc;
+int dn_wgrad(const dn_wgrad_desc* d, void* stream);
+
+/* out[c] += sum_r src[r, col0 + c]  (bias gradients); src bf16 [rows, ld]. */
+int dn_colsum_bf16(const void* src, int64_t rows, int32_t ld, int32_t col0, int32_t cols, float* out, void* stream);
+
+/* GEGLU (LM:881-885) on the packed pre-activation h [rows, 2*ip] (tile j: 128 "x" columns, then 128 gate columns):
+ * m = gelu_erf(gate) * x, bf16 [rows, ip];  backward writes dh in h's layout. */
+int dn_geglu_fwd(const void* h, int64_t rows, int32_t ip, void* m, void* stream);
+int dn_geglu_bwd(const void* h, const void* dm, int64_t rows, int32_t ip, void* dh, void* stream);
+
+/* WaveNet FiLM + gate (LM:513-536) for G chains at once.  ur bf16 [B*T, G*2*C]: per chain, tile j = 128 conv columns
+ * then 128 res columns (what dn_gemm writes with DN_EPI_BF16 over a wavenet-level packing); y bf16 [B*T, G*C].
+ * gamma/beta of (b, g): gb + t_idx[b*t_idx_stride]*gb_t_stride + g*g_gb (gamma[C], beta[C]); gb may be null.
+ * Backward writes dur bf16 [B*T, G*2*C] per chain as [du (C) | dres (C)] and dgb[b*dgb_b_stride + g*g_dgb + ...] =
+ * (dgamma[C], dbeta[C]) summed over the utterance's frames (overwritten, not accumulated; dgb may be null). */
+int dn_wn_gate_fwd(const void* ur, void* y, int32_t B, int32_t T, int32_t C, int32_t G, const float* gb,
+                   int64_t gb_t_stride, int32_t g_gb, const int32_t* t_idx, int32_t t_idx_stride, void* stream);
+int dn_wn_gate_bwd(const void* ur, const void* dy, void* dur, int32_t B, int32_t T, int32_t C, int32_t G, const float* gb,
+                   int64_t gb_t_stride, int32_t g_gb, const int32_t* t_idx, int32_t t_idx_stride, float* dgb,
+                   int64_t dgb_b_stride, int32_t g_dgb, void* stream);
+
+/* Backward of dn_adarmsnorm: dx (fp32 residual-stream gradient) += d(norm)/dx . dy; optional bf16 copy of the updated
+ * dx; dgamma_p[C] += (unconditioned norms); dgb[b*dgb_b_stride + (gamma | beta)] += (conditioned norms).  C = 512 | 768. */
+int dn_adarmsnorm_bwd(const float* x, const void* dy, float* dx, void* dx_bf16, int32_t B, int32_t T, int32_t C,
+                      const float* gamma_p, float* dgamma_p, const float* gb, int64_t gb_t_stride, const int32_t* t_idx,
+                      int32_t t_idx_stride, float* dgb, int64_t dgb_b_stride, void* stream);
+
+/* Per-timestep training coefficients, float32 x 4 per step: [sqrt_ab, sqrt(1-ab), min(snr,5)/snr, 0] (LM:1530-1566).
+ * x_t = sa[t_b] (z + beta0 eps0) + s1[t_b] eps  (+ bf16 staging copy, zero padded to ldx). */
+int dn_train_noise(const float* z_lat, const float* eps0, const float* eps, float beta0, const float* coef,
+                   const int32_t* t_idx, int32_t B, int32_t T, int32_t z, float* x_t, void* x_bf16, int32_t ldx,
+                   void* stream);
+/* loss[0] += mean_b( w_b mean_{T,z}( mask (pred - eps)^2 ) ) (LM:1563-1569); dpred bf16 [B*T, ldd] = grad_scale *
+ * d loss / d pred (zero on padded frames and pad columns; may be null). */
+int dn_noise_loss(const float* pred, int32_t lde, const float* eps, const int32_t* lengths, const float* coef,
+                  const int32_t* t_idx, int32_t B, int32_t T, int32_t z, float* loss, void* dpred, int32_t ldd,
+                  float grad_scale, void* stream);
+/* x1_hat = (x_t - s1 pred) / max(sa, 1e-10) as the bf16 staging input of decode_feature (LM:1572). */
+int dn_pred_x1(const float* x_t, const float* pred, int32_t lde, const float* coef, const int32_t* t_idx, int32_t B,
+               int32_t T, int32_t z, void* x_bf16, int32_t ldx, void* stream);
+/* Logging losses of the decode branch (LM:1573-1597), forward only.  out6 (double, overwritten) = [sum over valid
+ * frames of (recon-audio)^2, nll sum, smoothing sum (-sum_c lprob), correct argmax, target tokens, valid frames];
+ * units int64 [B*T] with 0 = padding (ignored), logits fp32 [B*T, ld] over V classes. */
+int dn_decode_losses(const float* recon, const float* audio, int32_t C, const float* logits, int32_t ld, int32_t V,
+                     const int64_t* units, const int32_t* lengths, int32_t B, int32_t T, double* out6, void* stream);
+
+/* Attention-dropout keep bits (LM:338): n_words uint32, each bit kept with probability 1-p (Philox4x32-10). */
+int dn_dropout_bits(uint32_t* bits, int64_t n_words, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* dn_attention with dropout and the saved row statistic L2 = m + log2(l) (fp32 [B, H, T]); dh = 64.
+ * keep_bits [B, H, T, ceil(T/32)] (bit k%32 of word k/32 = key k kept) or null; keep_scale = 1/(1-p). */
+int dn_attention_train(const void* qkv, void* out, float* lse2, const int32_t* lengths, const uint32_t* keep_bits,
+                       float keep_scale, int32_t B, int32_t T, int32_t H, int32_t dh, void* stream);
+/* Backward of dn_attention_train: dqkv bf16 [B, T, 3*H*dh] (fully written); delta_ws fp32 [B, H, T] workspace. */
+int dn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, const int32_t* lengths,
+                     const uint32_t* keep_bits, float keep_scale, void* dqkv, float* delta_ws, int32_t B, int32_t T,
+                     int32_t H, int32_t dh, void* stream);
+
+/* Time-conditioning MLP pieces (LM:104-116, :741-745, :507, :624), fp32, M = utterances. */
+int dn_silu(const float* pre, float* out, int64_t n, void* stream);
+int dn_silu_bwd(const float* pre, const float* dout, float* dpre, int64_t n, void* stream);
+/* dW[N,K] += dY^T X, db[N] += colsum(dY) (when dW != null); dX[M,K] += dY W (when dX != null).  dY [M, ldy]. */
+int dn_linear_f32_bwd(const float* dY, int64_t ldy, const float* X, const float* W, int32_t M, int64_t N, int32_t K,
+                      float* dW, float* db, float* dX, void* stream);
+int dn_time_features_bwd(const int32_t* steps, const float* w, const float* dfeat, int32_t M, int32_t half, float* dw,
+                         void* stream);
+/* dst fp32 [rows, ldd] (= or +=) src bf16 [rows, ld] columns [col0, col0 + C). */
+int dn_add_bf16_to_f32(const void* src, int64_t rows, int32_t ld, int32_t col0, int32_t C, float* dst, int32_t ldd,
+                       int32_t accumulate, void* stream);
+
 /* ---- host-side helper (no CUDA) --------------------------------------------------------------------------- */
 
 /* Length-bucketed batching under a padded-token budget; same contract and results as the reference's Cython

@@ -1,0 +1,205 @@
+"""Training step of the denoiser (BASELINE config 5) on the GPU: every new kernel against a plain
+PyTorch fp32 reference of the same op, then the whole forward + backward step against the oracle's autograd
+(oracle.train_loss, itself pinned to the live reference's losses and gradients in tests/test_oracle_golden.py)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from diffnorm_b200 import ops  # noqa: E402
+from diffnorm_b200.train import DenoiserTrainer, pack_keep_bits  # noqa: E402
+from oracle import diffnorm_oracle as O  # noqa: E402
+
+DEV = "cuda"
+bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("B,T,N,K,shift,dy0,x0", [(1, 640, 128, 256, 0, 0, 0), (3, 200, 512, 512, 0, 0, 0),
+                                                  (2, 333, 96, 1408, 2, 0, 0), (2, 150, 512, 512, 8, 1024, 512),
+                                                  (2, 77, 16, 64, 0, 0, 0), (4, 1000, 1408, 1408, 1, 0, 0)])
+def test_wgrad_kernel(B, T, N, K, shift, dy0, x0):
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
+    ldy, ldx = dy0 + rup8(N) + 64, x0 + rup8(K) + 64
+    dY = (torch.randn(B * T, ldy, generator=g) * 0.5).to(bf16).to(DEV)
+    X = (torch.randn(B * T, ldx, generator=g) * 0.5).to(bf16).to(DEV)
+    dW = torch.zeros(N, (K + 3) // 4 * 4, device=DEV)
+    ops.wgrad(dY, X, dW, B, T, N, K, dy0, x0, shift)
+    ops.wgrad(dY, X, dW, B, T, N, K, dy0, x0, shift, splits=3)        # accumulates: expect 2x
+    y = dY.float().view(B, T, ldy)[:, :, dy0:dy0 + N]
+    x = X.float().view(B, T, ldx)[:, :, x0:x0 + K]
+    xs = torch.zeros_like(x)
+    if shift < T:
+        xs[:, shift:] = x[:, :T - shift]
+    want = 2 * torch.einsum("btn,btk->nk", y, xs)
+    err = rel(dW[:, :K], want)
+    print(f"[parity] wgrad B{B} T{T} N{N} K{K} shift{shift}: rel err {err:.2e}")
+    assert err < 2e-3
+
+
+def rup8(v):
+    return (v + 7) // 8 * 8
+
+
+def test_geglu_gate_norm_colsum_backward():
+    g = torch.Generator().manual_seed(5)
+    B, T, C, ip = 2, 70, 512, 256
+    M = B * T
+    # GEGLU
+    h = (torch.randn(M, 2 * ip, generator=g)).to(bf16).to(DEV)
+    dm = (torch.randn(M, ip, generator=g)).to(bf16).to(DEV)
+    m = ops.geglu_fwd(h, torch.empty(M, ip, dtype=bf16, device=DEV))
+    dh = ops.geglu_bwd(h, dm, torch.empty(M, 2 * ip, dtype=bf16, device=DEV))
+    hv = h.float().view(M, ip // 128, 2, 128).requires_grad_(True)
+    ref = torch.nn.functional.gelu(hv[:, :, 1]) * hv[:, :, 0]
+    assert rel(m.float(), ref.reshape(M, ip)) < 6e-3
+    ref.backward(dm.float().view(M, ip // 128, 128))
+    assert rel(dh.float(), hv.grad.reshape(M, 2 * ip)) < 6e-3
+    # WaveNet gate, G chains, per-utterance gamma/beta rows
+    G = 3
+    ur = (torch.randn(M, G * 2 * C, generator=g)).to(bf16).to(DEV)
+    dy = (torch.randn(M, G * C, generator=g)).to(bf16).to(DEV)
+    gb = torch.randn(B, G * 2 * C, generator=g).to(DEV)
+    rows = torch.arange(B, dtype=i32, device=DEV)
+    y = ops.wn_gate_fwd(ur, torch.empty(M, G * C, dtype=bf16, device=DEV), B, T, C, G, gb.view(-1), G * 2 * C, 2 * C, rows, 1)
+    dgb = torch.zeros(B, G * 2 * C, device=DEV)
+    dur = ops.wn_gate_bwd(ur, dy, torch.empty(M, G * 2 * C, dtype=bf16, device=DEV), B, T, C, G, gb.view(-1), G * 2 * C, 2 * C,
+                          rows, 1, dgb.view(-1), G * 2 * C, 2 * C)
+    urv = ur.float().view(B, T, G, C // 128, 2, 128)
+    u = urv[..., 0, :].reshape(B, T, G, C).clone().requires_grad_(True)
+    r = urv[..., 1, :].reshape(B, T, G, C).clone().requires_grad_(True)
+    gbv = gb.view(B, 1, G, 2, C).clone().requires_grad_(True)
+    up = u * gbv[:, :, :, 0] + gbv[:, :, :, 1]
+    yr = up.tanh() * up.sigmoid() + r
+    assert rel(y.float(), yr.reshape(M, G * C)) < 6e-3
+    yr.backward(dy.float().view(B, T, G, C))
+    durv = dur.float().view(B, T, G, 2, C)
+    assert rel(durv[:, :, :, 0], u.grad) < 6e-3 and rel(durv[:, :, :, 1], r.grad) < 1e-6
+    assert rel(dgb.view(B, G, 2, C), gbv.grad.view(B, G, 2, C)) < 2e-3
+    # adaptive RMSNorm backward (conditioned) and gamma-parameter form
+    x = torch.randn(M, C, generator=g).to(DEV)
+    dyn = torch.randn(M, C, generator=g).to(bf16).to(DEV)
+    gbn = torch.randn(B, 2 * C, generator=g).to(DEV)
+    dx0 = torch.randn(M, C, generator=g).to(DEV)
+    dx = dx0.clone()
+    dxb = torch.empty(M, C, dtype=bf16, device=DEV)
+    dgbn = torch.zeros(B, 2 * C, device=DEV)
+    ops.adarmsnorm_bwd(x, dyn, dx, dxb, B, T, gb=gbn.view(-1), gb_t_stride=2 * C, t_idx=rows, t_idx_stride=1, dgb=dgbn.view(-1),
+                       dgb_b_stride=2 * C)
+    xr = x.clone().requires_grad_(True)
+    gr = gbn.clone().requires_grad_(True)
+    out = torch.nn.functional.normalize(xr.view(B, T, C), dim=-1) * C ** 0.5 * gr[:, None, :C] + gr[:, None, C:]
+    out.backward(dyn.float().view(B, T, C))
+    assert rel(dx - dx0, xr.grad) < 1e-4 and rel(dxb.float(), dx) < 5e-3 and rel(dgbn, gr.grad) < 1e-4
+    gp = torch.randn(C, generator=g).to(DEV)
+    dgp = torch.zeros(C, device=DEV)
+    dx = torch.zeros(M, C, device=DEV)
+    ops.adarmsnorm_bwd(x, dyn, dx, None, B, T, gamma_p=gp, dgamma_p=dgp)
+    xr = x.clone().requires_grad_(True)
+    gpr = gp.clone().requires_grad_(True)
+    (torch.nn.functional.normalize(xr, dim=-1) * C ** 0.5 * gpr).backward(dyn.float())
+    assert rel(dx, xr.grad) < 1e-4 and rel(dgp, gpr.grad) < 1e-4
+    # column sums
+    src = torch.randn(M, 1408, generator=g).to(bf16).to(DEV)
+    cs = ops.colsum(src, 128, 1280, torch.zeros(1280, device=DEV))
+    assert rel(cs, src.float()[:, 128:].sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("T,lens,drop", [(200, [200, 131], True), (128, [128, 1], False), (300, [300, 257], True)])
+def test_attention_train_forward_backward(T, lens, drop):
+    g = torch.Generator().manual_seed(T)
+    B, H, dh = len(lens), 8, 64
+    M = B * T
+    qkv = (torch.randn(M, 3 * H * dh, generator=g) * 1.5).to(bf16).to(DEV)
+    dout = torch.randn(M, H * dh, generator=g).to(bf16)
+    ln = torch.tensor(lens, dtype=i32, device=DEV)
+    p = 0.1
+    keep = (torch.rand(B, H, T, T, generator=g) >= p) if drop else None
+    bits = pack_keep_bits(keep).to(DEV) if drop else None
+    ks = 1 / (1 - p) if drop else 1.0
+    out = torch.empty(M, H * dh, dtype=bf16, device=DEV)
+    lse = torch.empty(B * H, T, device=DEV)
+    ops.attention_train(qkv, out, lse, ln, bits, ks, B, T, H, dh)
+    # fp32 reference on the same bf16 inputs
+    leaf = qkv.float().cpu().requires_grad_(True)
+    q, k, v = (t.view(B, T, H, dh).transpose(1, 2) for t in leaf.chunk(3, dim=-1))
+    mask = torch.arange(T)[None, :] < torch.tensor(lens)[:, None]
+    sim = torch.einsum("bhid,bhjd->bhij", q, k) * dh ** -0.5
+    sim = sim.masked_fill(~mask[:, None, None, :], -torch.finfo(torch.float32).max)
+    attn = sim.softmax(-1)
+    if drop:
+        attn = attn * keep.float() * ks
+    ref = torch.einsum("bhij,bhjd->bhid", attn, v).transpose(1, 2).reshape(B, T, H * dh)
+    valid_q = torch.ones(B, T, dtype=torch.bool)   # padded queries are computed too (LM:333 masks keys only)
+    e_out = rel(out.float().cpu().view(B, T, -1)[valid_q], ref.detach()[valid_q])
+    lse_ref = torch.logsumexp(sim, dim=-1) / np.log(2.0)
+    e_lse = float((lse.cpu().view(B, H, T) - lse_ref.detach()).abs().max())
+    # backward: zero the upstream gradient on padded frames (as the training loss does)
+    dmask = dout.float().view(B, T, -1) * mask[:, :, None]
+    ref.backward(dmask)
+    dqkv = torch.empty(M, 3 * H * dh, dtype=bf16, device=DEV)
+    ops.attention_bwd(qkv, out, dmask.view(M, -1).to(bf16).to(DEV).contiguous(), lse, ln, bits, ks, dqkv,
+                      torch.empty(B * H, T, device=DEV), B, T, H, dh)
+    got = dqkv.float().cpu().view(B, T, 3, H * dh)
+    want = leaf.grad.view(B, T, 3, H * dh)
+    errs = [rel(got[:, :, i], want[:, :, i]) for i in range(3)]
+    print(f"[parity] attention train T{T} drop={drop}: out {e_out:.2e} lse {e_lse:.2e} dq/dk/dv {errs}")
+    assert e_out < 1.5e-2 and e_lse < 2e-2 and max(errs) < 2.5e-2
+
+
+def _build(z, wseed):
+    from diffnorm_b200.plugin.latent_module import LatentDiscreteModel, SpeechVAEEncoderDecoder
+    arch = O.Arch(latent_dim=z)
+    sd = O.init_state_dict(arch, seed=wseed, gains=O.PARITY_GAINS)
+    vae = types.SimpleNamespace(encoder=SpeechVAEEncoderDecoder(768, z))
+    ldm = LatentDiscreteModel(vae, 512, z, timesteps=200, multitask=False)
+    ldm.load_state_dict(sd, strict=True)
+    return arch, sd, ldm.to(DEV)
+
+
+@pytest.mark.parametrize("drop_p", [0.1, 0.0])
+def test_train_step_against_oracle_autograd(drop_p):
+    """Whole step (forward losses + every parameter gradient) vs the oracle's autograd on the same replayed draws."""
+    z, wseed, B, T, lengths, times, dseed = 16, 3, 2, 24, [24, 17], [37, 142], 21
+    arch, sd, ldm = _build(z, wseed)
+    audio, units, mask, eps_vae, eps0, eps, keeps = O.train_case_inputs(z, B, T, lengths, dseed, drop_p)
+    train_keys = [k for k in sd if k.startswith("model.") and sd[k].is_floating_point() and "pos_embed" not in k]
+    for k in train_keys:
+        sd[k].requires_grad_(True)
+    ref = O.train_loss(sd, arch, audio, units, mask, torch.tensor(times), eps_vae, eps0, eps, keeps, drop_p, False)
+    ref["total_loss"].backward()
+    tr = DenoiserTrainer(ldm, drop_p=drop_p)
+    bits = [pack_keep_bits(k).to(DEV) for k in keeps] if keeps is not None else None
+    out, grads = tr.step(audio.to(DEV), units.to(DEV), torch.tensor(lengths, dtype=i32, device=DEV),
+                         times=torch.tensor(times), noise={"vae": eps_vae, "eps0": eps0, "eps": eps}, keep_bits=bits)
+    torch.cuda.synchronize()
+    for k in ("noise_loss", "recon_mse_loss", "nll_loss"):
+        a, b = float(out[k]), float(ref[k])
+        print(f"[parity] train {k}: cuda {a:.6f} oracle {b:.6f}")
+        assert abs(a - b) <= 2e-2 * abs(b) + 1e-4
+    assert abs(float(out["acc"]) - float(ref["acc"])) <= 0.1
+    e_pred = rel(out["pred_noise"].cpu()[mask], ref["pred_noise"].detach()[mask])
+    assert e_pred < 3e-2, e_pred
+    assert sorted("model." + k for k in grads) == sorted(train_keys)
+    worst, tot_num, tot_den = ("", 0.0), 0.0, 0.0
+    for k in train_keys:
+        gg, gr = grads[k[6:]].cpu().reshape(sd[k].shape), sd[k].grad
+        e = rel(gg, gr)
+        tot_num += float((gg.double() - gr.double()).pow(2).sum())
+        tot_den += float(gr.double().pow(2).sum())
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < 0.12, (k, e, float(gr.norm()))
+    print(f"[parity] train grads (drop_p={drop_p}): global rel err {np.sqrt(tot_num / tot_den):.3e}, worst {worst}, "
+          f"pred_noise rel err {e_pred:.2e}")
+    assert np.sqrt(tot_num / tot_den) < 4e-2
