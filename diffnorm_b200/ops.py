@@ -291,7 +291,7 @@ def train_noise(z_lat, eps0, eps, beta0: float, coef, t_idx, x_t, xb):
 def noise_loss(pred, eps, lengths, coef, t_idx, B, T, z, loss, dpred=None, grad_scale: float = 1.0):
     _chk(pred, f32, "pred"), _chk(eps, f32, "eps"), _chk(loss, f32, "loss")
     check(lib.dn_noise_loss(_p(pred), pred.shape[-1], _p(eps), _p(lengths), _p(coef), _p(t_idx), B, T, z, _p(loss),
-                            _p(dpred), 0 if dpred is None else dpred.shape[-1], grad_scale, _stream()), "dn_noise_loss")
+                            _p(dpred), z if dpred is None else dpred.shape[-1], grad_scale, _stream()), "dn_noise_loss")
     return loss
 
 

@@ -32,9 +32,13 @@ class DDPMDiscreteLoss(FairseqCriterion):
 
     @staticmethod
     def reduce_metrics(logging_outputs):
-        """:77-105 — per-worker means (logging outputs cannot be summed)."""
-        n = max(len(logging_outputs), 1)
-        return {k: sum(lo.get(k, 0) for lo in logging_outputs) / n for k in ("loss", "noise_loss", "nll_loss", "mse_loss", "acc")}
+        """:77-95 — sample-size-weighted means over the workers (logging outputs cannot be summed)."""
+        ns = [lo.get("sample_size", 0) for lo in logging_outputs]
+        ntot = sum(ns)
+        ws = [n / (ntot + 1e-8) for n in ns]
+        red = {k: sum(lo.get(k, 0) * w for lo, w in zip(logging_outputs, ws)) for k in ("loss", "noise_loss", "mse_loss", "nll_loss", "acc")}
+        red["sample_size"] = ntot
+        return red
 
     @staticmethod
     def logging_outputs_can_be_summed():

@@ -193,6 +193,7 @@ class LatentDiscreteModel(FairseqEncoder):
         self.dim, self.timesteps = dim, timesteps
         self._eng = None
         self._eng_version = None
+        self._trainer_obj = None
         import weakref
         self.speech_decoder._owner = weakref.ref(self)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -200,6 +201,7 @@ class LatentDiscreteModel(FairseqEncoder):
     # ---- engine management -------------------------------------------------------------------------------
     def _invalidate(self):
         self._eng = None
+        self._trainer_obj = None   # holds the packed frozen VAE
 
     def _param_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -254,6 +256,52 @@ class LatentDiscreteModel(FairseqEncoder):
                             noise.get("vae"), noise.get("q"))
         return out
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("denoiser training forward/backward (LM:1514-1613) is not built yet: round 1 "
-                                  "covers the normalization (inference) path; see DESIGN.md roadmap")
+    # ---- training entry (LM:1514-1613) ------------------------------------------------------------------------
+    def _trainer(self):
+        if self._trainer_obj is None:
+            from ..train import DenoiserTrainer
+            self._trainer_obj = DenoiserTrainer(self, drop_p=0.1)
+        return self._trainer_obj
+
+    def forward(self, audio, audio_units, src_feature=None, src_mask=None, tgt_mask=None, prompt=None, pitch=None,
+                *args, _replay: Optional[Dict[str, object]] = None, **kwargs):
+        """LatentDiscreteModel.forward: the denoiser training loss dict {total_loss, nll_loss, recon_mse_loss,
+        noise_loss, acc}.  The whole step (forward AND backward) runs in the sm_100a kernels (diffnorm_b200/train.py);
+        ``total_loss`` is tied to the denoiser parameters through an autograd Function whose backward hands the
+        already-computed gradients to torch, so ``optimizer.backward(loss)`` (fairseq) / ``loss.backward()`` work
+        unchanged.  In eval mode (valid_step) there is no dropout and no backward.
+        ``_replay`` (extension) = {"times", "noise", "keep_bits"} replays the random draws for parity runs."""
+        _require_cuda(audio, "LatentDiscreteModel.forward")
+        if tgt_mask is None:
+            raise ValueError("tgt_mask is required (diff_discrete.py:46-54 always passes it)")
+        tr = self._trainer()
+        tr.drop_p = 0.1 if self.training else 0.0
+        lens = _mask_to_lengths(tgt_mask)
+        names = list(tr.P.keys())
+        params = [tr.P[n] for n in names]
+        need_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params)
+        rp = _replay or {}
+        outs = _TrainStepFn.apply(tr, audio, audio_units, lens, rp, need_grad, names, *params)
+        total, nll, mse, acc = outs
+        return {"total_loss": total, "nll_loss": nll, "recon_mse_loss": mse, "noise_loss": total.detach(), "acc": acc}
+
+
+class _TrainStepFn(torch.autograd.Function):
+    """Forward = the whole CUDA training step (losses + parameter gradients); backward = scale and return them."""
+
+    @staticmethod
+    def forward(ctx, trainer, audio, units, lens, replay, need_grad, names, *params):
+        out, grads = trainer.step(audio, units, lens, times=replay.get("times"), noise=replay.get("noise"),
+                                  keep_bits=replay.get("keep_bits"), backward=need_grad)
+        ctx.grads = [grads[n].reshape(p.shape) for n, p in zip(names, params)] if need_grad else None
+        zero = torch.zeros((), device=audio.device)
+        res = (out["total_loss"].clone(), out.get("nll_loss", zero).clone(), out.get("recon_mse_loss", zero).clone(),
+               out.get("acc", zero).clone())
+        ctx.mark_non_differentiable(*res[1:])
+        return res
+
+    @staticmethod
+    def backward(ctx, g_total, *unused):
+        if ctx.grads is None:
+            raise RuntimeError("backward through a step that ran without gradients (eval mode / no_grad)")
+        return (None,) * 7 + tuple(g * g_total for g in ctx.grads)

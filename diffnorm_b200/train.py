@@ -43,6 +43,19 @@ class _Plans:
     pass
 
 
+class _GradDict(dict):
+    """name -> gradient; tells the data-parallel reducer about every gradient the moment it is final."""
+
+    def __init__(self, hook=None):
+        super().__init__()
+        self._hook = hook
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, v)
+        if self._hook is not None:
+            self._hook(k, v)
+
+
 class DenoiserTrainer:
     def __init__(self, ldm, drop_p: float = 0.1, seed: int = 0):
         if not torch.cuda.is_available():
@@ -170,10 +183,11 @@ class DenoiserTrainer:
     def step(self, audio: torch.Tensor, units: Optional[torch.Tensor], lengths: torch.Tensor,
              times: Optional[torch.Tensor] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
              keep_bits: Optional[Sequence[torch.Tensor]] = None, backward: bool = True, decode_losses: bool = True,
-             grad_scale: float = 1.0):
+             grad_scale: float = 1.0, grad_hook=None):
         """audio fp32 [B,T,768] cuda; units int64 [B,T] (0 = pad, unit k -> k+4) or None; lengths int32 [B].
         times int [B] in [1, timesteps) (drawn if None, LM:1528); noise = {"vae": [B,z,T], "eps0": [B,T,z], "eps": [B,T,z]}
         replays the draws; keep_bits = per layer int32 [B,H,T,ceil(T/32)] (drawn with Philox if None and drop_p > 0).
+        grad_hook(name, tensor) is called as each gradient becomes final (diffnorm_b200.dist.GradAllReducer.hook).
         Returns (loss dict of 0-d tensors, grads dict name -> fp32 tensor) ; grads = {} when backward=False."""
         c, dev = self.cfg, self.dev
         B, T, _ = audio.shape
@@ -274,7 +288,7 @@ class DenoiserTrainer:
             return out, {}
 
         # ================================================================================================ backward
-        grads: Dict[str, torch.Tensor] = {}
+        grads: Dict[str, torch.Tensor] = _GradDict(grad_hook)
         zeros = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
 
         def wg(dY, X, n_rows, k_cols, dy_col0=0, x_col0=0, shift=0, flat=True):

@@ -203,3 +203,33 @@ def test_train_step_against_oracle_autograd(drop_p):
     print(f"[parity] train grads (drop_p={drop_p}): global rel err {np.sqrt(tot_num / tot_den):.3e}, worst {worst}, "
           f"pred_noise rel err {e_pred:.2e}")
     assert np.sqrt(tot_num / tot_den) < 4e-2
+
+
+def test_plugin_forward_backward_through_autograd():
+    """The fairseq-facing entry: model(...) -> loss dict; loss.backward() fills .grad of every denoiser parameter with
+    the CUDA step's gradients; eval mode runs without dropout and without backward (valid_step)."""
+    z, B, T, lengths = 16, 2, 24, [24, 17]
+    arch, sd, ldm = _build(z, 3)
+    audio, units, mask, eps_vae, eps0, eps, keeps = O.train_case_inputs(z, B, T, lengths, 21, 0.1)
+    for n_, p_ in ldm.named_parameters():
+        p_.requires_grad_(not n_.startswith("speech_decoder."))
+    ldm.train()
+    rp = {"times": torch.tensor([37, 142]), "noise": {"vae": eps_vae, "eps0": eps0, "eps": eps},
+          "keep_bits": [pack_keep_bits(k).to(DEV) for k in keeps]}
+    out = ldm(audio.to(DEV), units.to(DEV), tgt_mask=mask.to(DEV), _replay=rp)
+    assert set(out) == {"total_loss", "nll_loss", "recon_mse_loss", "noise_loss", "acc"}
+    (out["total_loss"] * 2.0).backward()
+    tr = ldm._trainer()
+    _, grads = tr.step(audio.to(DEV), units.to(DEV), torch.tensor(lengths, dtype=i32, device=DEV), times=rp["times"],
+                       noise=rp["noise"], keep_bits=rp["keep_bits"])
+    n = 0
+    for name, p_ in ldm.model.named_parameters():
+        assert p_.grad is not None, name
+        assert rel(p_.grad, 2.0 * grads[name].reshape(p_.shape)) < 1e-3, name   # atomics: not bit-reproducible
+        n += 1
+    assert n == 377
+    assert all(p_.grad is None for n_, p_ in ldm.named_parameters() if n_.startswith("speech_decoder."))
+    ldm.eval()
+    with torch.no_grad():
+        ev = ldm(audio.to(DEV), units.to(DEV), tgt_mask=mask.to(DEV), _replay={"times": rp["times"], "noise": rp["noise"]})
+    assert abs(float(ev["total_loss"]) - 0.904014) < 2e-2 * 0.904014   # the oracle's no-dropout loss for this case
