@@ -62,8 +62,11 @@ def test_compute_requires_cuda_and_training_not_silently_faked():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="CUDA"):
             model.encoder.ddim_sample(torch.zeros(1, 8, 768), input_mask=torch.ones(1, 8, dtype=torch.bool), start_step=5)
-    with pytest.raises(NotImplementedError):
-        model.encoder(torch.zeros(1, 8, 768), torch.zeros(1, 8, dtype=torch.long))
+    if not torch.cuda.is_available():   # the training step has no CPU path either: it raises, it does not fake a loss
+        with pytest.raises(RuntimeError, match="CUDA"):
+            model.encoder(torch.zeros(1, 8, 768), torch.zeros(1, 8, dtype=torch.long), tgt_mask=torch.ones(1, 8, dtype=torch.bool))
+    red = type(task.build_criterion(_args())).reduce_metrics([{"loss": 1.0, "sample_size": 1}, {"loss": 3.0, "sample_size": 3}])
+    assert abs(red["loss"] - 2.5) < 1e-6 and red["sample_size"] == 4   # ddpm_discrete_loss.py:77-95 weighting
     crit = task.build_criterion(_args())
     assert type(crit).__name__ == "DDPMDiscreteLoss" and crit.logging_outputs_can_be_summed() is False
 
