@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--latent-dim", type=int, default=16)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--phases", action="store_true", help="print host/device time of packing, forward, backward (1 GPU)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -71,6 +72,24 @@ def main():
     for _ in range(a.warmup):
         out, grads = step()
     barrier()
+    if a.phases and rank == 0:
+        import time
+
+        def timed(fn, n=3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            return (t1 - t0) / n * 1e3, (t2 - t0) / n * 1e3
+
+        print("phase: host-enqueue ms / wall ms (3 runs each)")
+        print("  pack weights      %.1f / %.1f" % timed(tr._pack))
+        print("  forward only      %.1f / %.1f" % timed(lambda: tr.step(audio, units, lens, backward=False)))
+        print("  forward+backward  %.1f / %.1f" % timed(lambda: tr.step(audio, units, lens)))
+        print("  + grad allreduce  %.1f / %.1f" % timed(step))
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
