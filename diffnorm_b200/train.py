@@ -88,9 +88,14 @@ class DenoiserTrainer:
         self.n_cond, self.gbw = len(self.cond_names), 2 * c.hid
         self.inner = DiffNormConfig.ff_inner(c.hid)
         self.ip = rup(self.inner, 128)
-        self.row_map = geglu_row_map(self.inner).to(self.dev)
+        rm = geglu_row_map(self.inner)
+        self.geglu_src = torch.nonzero(rm >= 0).squeeze(1).to(self.dev)   # packed GEGLU rows that hold a real weight row
+        self.geglu_dst = rm[rm >= 0].to(self.dev)                         # ... and the reference row each one maps to
         self.zp, self.zn = rup(c.latent_dim, 64), rup(c.latent_dim, 16)
         self._pe: Dict[int, torch.Tensor] = {}
+        self._pack_graph = None
+        self._pack_plans = None
+        self._pack_ptrs = None
 
     # ------------------------------------------------------------------------------------------------ helpers
     def buf(self, name: str, rows: int, width: int, dtype=bf16, zero: bool = False) -> torch.Tensor:
@@ -165,6 +170,21 @@ class DenoiserTrainer:
         pl.bcat = torch.cat([w(n + ".bias") for n in self.cond_names], 0).contiguous()
         return pl
 
+    def _packed(self) -> _Plans:
+        """The per-step re-packing is ~500 small indexing kernels over fixed addresses (the fp32 masters are updated in
+        place by the optimizer): it is captured once in a CUDA graph and replayed (one launch) every step.  A change of
+        any parameter's storage (e.g. `.to()`, a new tensor assigned) re-captures."""
+        ptrs = tuple(p.data_ptr() for p in self.P.values())
+        if self._pack_graph is None or ptrs != self._pack_ptrs:
+            self._pack()                      # warm-up outside capture (allocator, lazy init)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._pack_plans = self._pack()
+            self._pack_graph, self._pack_ptrs = g, ptrs
+        self._pack_graph.replay()
+        return self._pack_plans
+
     def pe_table(self, T: int) -> torch.Tensor:
         t = self._pe.get(T)
         if t is None:
@@ -212,7 +232,7 @@ class DenoiserTrainer:
                 ops.dropout_bits(kb, self.drop_p, self.seed, self.step_no * c.depth + l)
                 keep_bits.append(kb)
         self.step_no += 1
-        pl = self._pack()
+        pl = self._packed()
         rows = torch.arange(B, dtype=i32, device=dev)
         gstride = self.n_cond * self.gbw
 
@@ -329,11 +349,8 @@ class DenoiserTrainer:
             dh_ = ops.geglu_bwd(hh, dm1, self.buf("dh", M, 2 * ip))
             dW1p = wg(dh_, hb2, 2 * ip, C)
             db1p = cs(dh_, 0, 2 * ip)
-            valid = self.row_map >= 0
-            gw = zeros(2 * self.inner, C)
-            gw[self.row_map[valid]] = dW1p[valid]
-            gb_ = zeros(2 * self.inner)
-            gb_[self.row_map[valid]] = db1p[valid]
+            gw = zeros(2 * self.inner, C).index_copy_(0, self.geglu_dst, dW1p.index_select(0, self.geglu_src))
+            gb_ = zeros(2 * self.inner).index_copy_(0, self.geglu_dst, db1p.index_select(0, self.geglu_src))
             grads[p + "5.0.weight"], grads[p + "5.0.bias"] = gw, gb_
             dhb = self._run(L.ff1_T, dh_, self.buf("dhb", M, C), B, T)
             ops.adarmsnorm_bwd(xs2, dhb, dx, dxb, B, T, gb=gflat[(n0 + 2 * l + 1) * self.gbw:], dgb=dgball.view(-1)[(n0 + 2 * l + 1) * self.gbw:],
