@@ -55,6 +55,7 @@ class WgradDesc(C.Structure):
         ("X", vp), ("ldx", i32), ("x_batch_stride", i64), ("x_col0", i32), ("x_shift", i32),
         ("n_rows", i32), ("k_cols", i32),
         ("dW", vp), ("ldw", i32), ("splits", i32),
+        ("groups", i32), ("g_dy_col", i32), ("g_x_col", i32), ("shift_shl_group", i32), ("g_dw_stride", i64),
     ]
 
 

@@ -8,6 +8,9 @@
 // between 8-frame groups); the next 64 channels are the next box, LBO = 8192 B further on.  A conv tap's gradient is
 // the same contraction with X read `shift` frames earlier; the per-utterance 3-D tensor map zero-fills t - shift < 0
 // and t >= T, which is exactly the causal padding and keeps utterances apart.
+// Groups: `groups` independent problems in one launch (the 8 chains of a WaveNet level): group g reads dY / X at
+// column offsets g * g_dy_col / g * g_x_col, optionally with shift << g (chain g has dilation 2^g), and owns dW + g *
+// g_dw_stride.
 // Split-K: a work item = (128 x 256 output tile, range of 64-frame blocks); partial tiles are added into the fp32
 // gradient with TMA reduce-add (the same epilogue as the residual GEMM), so dW must be zeroed (or hold the running
 // accumulation) before the launch.
@@ -51,7 +54,7 @@ __device__ __forceinline__ uint32_t wg_idesc(uint32_t n) {
 }
 
 struct WgItem {
-    int m0, n0, blk0, blk1;
+    int m0, n0, blk0, blk1, g;
 };
 
 struct WgParams {
@@ -59,10 +62,14 @@ struct WgParams {
     int dy_col0, x_col0;
     int n_rows, k_cols;
     int m_tiles, n_tiles, splits, blocks_per_utt, total_blocks;
+    int groups, g_dy_col, g_x_col, shift_shl_group;
 };
 
 __device__ __forceinline__ WgItem wg_decode(const WgParams& p, int item) {
     WgItem w;
+    const int per_group = p.m_tiles * p.n_tiles * p.splits;
+    w.g = item / per_group;
+    item -= w.g * per_group;
     const int tile = item / p.splits, s = item % p.splits;
     w.m0 = (tile / p.n_tiles) * WG_BM;
     w.n0 = (tile % p.n_tiles) * WG_BN;
@@ -85,7 +92,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = p.m_tiles * p.n_tiles * p.splits;
+    const int total = p.m_tiles * p.n_tiles * p.splits * p.groups;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY);
@@ -116,6 +123,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < total; item += gridDim.x) {
                 const WgItem w = wg_decode(p, item);
+                const int shift = p.shift << (p.shift_shl_group ? w.g : 0);
+                const int ycol = p.dy_col0 + w.g * p.g_dy_col + w.m0, xcol = p.x_col0 + w.g * p.g_x_col + w.n0;
                 for (int blk = w.blk0; blk < w.blk1; ++blk) {
                     const int b = blk / p.blocks_per_utt;
                     const int t0 = (blk % p.blocks_per_utt) * WG_BK;
@@ -125,10 +134,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
                     mbar_expect_tx(&full[stage], WG_STAGE_BYTES);
 #pragma unroll
                     for (int i = 0; i < WG_BM / 64; ++i)
-                        tma_load_3d(&tmY, &full[stage], sa + i * WG_BOX, p.dy_col0 + w.m0 + i * 64, t0, b);
+                        tma_load_3d(&tmY, &full[stage], sa + i * WG_BOX, ycol + i * 64, t0, b);
 #pragma unroll
                     for (int i = 0; i < WG_BN / 64; ++i)
-                        tma_load_3d(&tmX, &full[stage], sb + i * WG_BOX, p.x_col0 + w.n0 + i * 64, t0 - p.shift, b);
+                        tma_load_3d(&tmX, &full[stage], sb + i * WG_BOX, xcol + i * 64, t0 - shift, b);
                     if (++stage == WG_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -207,7 +216,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
                     fence_proxy_async_smem();
                     named_bar_sync(bar_id, 128);
                     if (issuer) {
-                        tma_reduce_add_3d(&tmOut, stage_buf, col, w.m0, 0);
+                        tma_reduce_add_3d(&tmOut, stage_buf, col, w.m0, w.g);
                         bulk_commit();
                     }
                 }
@@ -234,6 +243,9 @@ extern "C" int dn_wgrad(const dn_wgrad_desc* dp, void* stream) {
     const dn_wgrad_desc& d = *dp;
     if (d.B <= 0 || d.T <= 0 || d.n_rows <= 0 || d.k_cols <= 0) return DN_EINVAL;
     if (d.ldy % 8 || d.ldx % 8 || d.ldw % 4 || d.dy_col0 % 8 || d.x_col0 % 8) return DN_EINVAL;
+    const int groups = d.groups > 0 ? d.groups : 1;
+    if (groups > 1 && (d.g_dy_col % 8 || d.g_x_col % 8 || d.g_dw_stride % 4 || d.g_dw_stride < (int64_t)d.n_rows * d.ldw))
+        return DN_EINVAL;
     if ((reinterpret_cast<uintptr_t>(d.dY) | reinterpret_cast<uintptr_t>(d.X) | reinterpret_cast<uintptr_t>(d.dW)) & 15)
         return DN_EINVAL;
     CUtensorMap my, mx, mo;
@@ -252,8 +264,9 @@ extern "C" int dn_wgrad(const dn_wgrad_desc* dp, void* stream) {
         if (r) return r;
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)d.k_cols, (cuuint64_t)d.n_rows, 1};
-        cuuint64_t str[2] = {(cuuint64_t)d.ldw * 4, (cuuint64_t)d.ldw * 4 * (cuuint64_t)d.n_rows};
+        cuuint64_t dims[3] = {(cuuint64_t)d.k_cols, (cuuint64_t)d.n_rows, (cuuint64_t)groups};
+        cuuint64_t str[2] = {(cuuint64_t)d.ldw * 4,
+                             groups > 1 ? (cuuint64_t)d.g_dw_stride * 4 : (cuuint64_t)d.ldw * 4 * (cuuint64_t)d.n_rows};
         cuuint32_t box[3] = {32, 128, 1};
         int r = encode_f32_map(&mo, d.dW, 3, dims, str, box);
         if (r) return r;
@@ -270,7 +283,11 @@ extern "C" int dn_wgrad(const dn_wgrad_desc* dp, void* stream) {
     p.n_tiles = (d.k_cols + WG_BN - 1) / WG_BN;
     p.blocks_per_utt = (d.T + WG_BK - 1) / WG_BK;
     p.total_blocks = d.B * p.blocks_per_utt;
-    const int tiles = p.m_tiles * p.n_tiles;
+    p.groups = groups;
+    p.g_dy_col = d.g_dy_col;
+    p.g_x_col = d.g_x_col;
+    p.shift_shl_group = d.shift_shl_group;
+    const int tiles = p.m_tiles * p.n_tiles * groups;
     int splits = d.splits;
     if (splits <= 0) {  // fill the machine, but keep at least 8 frame blocks per work item
         splits = (2 * num_sms() + tiles - 1) / tiles;
@@ -285,7 +302,7 @@ extern "C" int dn_wgrad(const dn_wgrad_desc* dp, void* stream) {
         DN_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
         attr_set = true;
     }
-    const long long total = (long long)tiles * splits;
+    const long long total = (long long)tiles * splits;  // tiles already counts the groups
     const int grid = (int)(total < num_sms() ? total : num_sms());
     wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(my, mx, mo, p);
     DN_LAUNCH_CHECK();

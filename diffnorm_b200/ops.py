@@ -227,14 +227,17 @@ class GemmPlan:
 
 # ------------------------------------------------------------------------------------------------ training step
 def wgrad(dY, X, dW, B: int, T: int, n_rows: int, k_cols: int, dy_col0: int = 0, x_col0: int = 0, shift: int = 0,
-          splits: int = 0):
-    """dW[n, c] += sum_{b,t} dY[b,t,dy_col0+n] * X[b,t-shift,x_col0+c].  dY, X bf16 [B*T, ld]; dW fp32 [>=n_rows, ldw]."""
+          splits: int = 0, groups: int = 1, g_dy_col: int = 0, g_x_col: int = 0, shift_shl_group: bool = False):
+    """dW[n, c] += sum_{b,t} dY[b,t,dy_col0+n] * X[b,t-shift,x_col0+c].  dY, X bf16 [B*T, ld]; dW fp32 [>=n_rows, ldw]
+    (groups > 1: dW [groups, n_rows, ldw], group g at column offsets g*g_dy_col / g*g_x_col, shift << g if asked)."""
     _chk(dY, bf16, "dY"), _chk(X, bf16, "X"), _chk(dW, f32, "dW")
     d = _lib.WgradDesc()
     d.B, d.T = B, T
     d.dY, d.ldy, d.dy_batch_stride, d.dy_col0 = _p(dY), dY.shape[-1], T * dY.shape[-1], dy_col0
     d.X, d.ldx, d.x_batch_stride, d.x_col0, d.x_shift = _p(X), X.shape[-1], T * X.shape[-1], x_col0, shift
     d.n_rows, d.k_cols, d.dW, d.ldw, d.splits = n_rows, k_cols, _p(dW), dW.shape[-1], splits
+    d.groups, d.g_dy_col, d.g_x_col, d.shift_shl_group = groups, g_dy_col, g_x_col, int(shift_shl_group)
+    d.g_dw_stride = dW.stride(0) if groups > 1 else 0
     check(lib.dn_wgrad(C.byref(d), _stream()), "dn_wgrad")
     return dW
 

@@ -381,14 +381,21 @@ class DenoiserTrainer:
             dur = ops.wn_gate_bwd(sv[f"ur{s}"], dy, self.buf("dur", M, G * 2 * C), B, T, C, G, gb=gflat[s * G * self.gbw:],
                                   g_gb=self.gbw, dgb=dgball.view(-1)[s * G * self.gbw:], dgb_b_stride=gstride, g_dgb=self.gbw, **gbk)
             inp = sv[f"y{s - 1}"] if s > 0 else hw
+            gx = C if s > 0 else 0
+            # all 8 chains per launch: 3 conv taps (shift (2-k) 2^g) + the 1x1 res conv; biases from one column sum
+            tapsG = []
+            for k in range(3):
+                dWg = zeros(G, C, C)
+                ops.wgrad(dur, inp, dWg, B, T, C, C, 0, 0, 2 - k, groups=G, g_dy_col=2 * C, g_x_col=gx, shift_shl_group=True)
+                tapsG.append(dWg)
+            dWc = torch.stack(tapsG, dim=-1)                                     # [G, C, C, 3]
+            dWr = zeros(G, C, C)
+            ops.wgrad(dur, inp, dWr, B, T, C, C, C, 0, 0, groups=G, g_dy_col=2 * C, g_x_col=gx)
+            dbg = cs(dur, 0, G * 2 * C).view(G, 2, C)
             for g in range(G):
                 b_ = f"wavenet.stacks.{s}.blocks.{g}."
-                xc = g * C if s > 0 else 0
-                taps = [wg(dur, inp, C, C, dy_col0=g * 2 * C, x_col0=xc, shift=(2 - k) * (1 << g), flat=False) for k in range(3)]
-                grads[b_ + "conv.weight"] = torch.stack(taps, dim=-1)
-                grads[b_ + "conv.bias"] = cs(dur, g * 2 * C, C)
-                grads[b_ + "res_conv.weight"] = wg(dur, inp, C, C, dy_col0=g * 2 * C + C, x_col0=xc).view(C, C, 1)
-                grads[b_ + "res_conv.bias"] = cs(dur, g * 2 * C + C, C)
+                grads[b_ + "conv.weight"], grads[b_ + "conv.bias"] = dWc[g], dbg[g, 0]
+                grads[b_ + "res_conv.weight"], grads[b_ + "res_conv.bias"] = dWr[g].view(C, C, 1), dbg[g, 1]
             if s > 0:
                 dy = self._run(pl.lvl_T[s], dur, self.buf(dy_next, M, G * C), B, T, g_a_col=2 * C, g_out_col=C)
                 dy_next = "dyA" if dy_next == "dyB" else "dyB"

@@ -198,6 +198,11 @@ typedef struct {
     int32_t n_rows, k_cols;     /* extent of dW */
     float* dW; int32_t ldw;
     int32_t splits;             /* <= 0: chosen by the library */
+    /* groups > 1: independent problems in one launch (the chains of a WaveNet level): group g reads columns
+     * + g * g_dy_col / + g * g_x_col, writes dW + g * g_dw_stride (elements), and uses x_shift << g when
+     * shift_shl_group is set (chain g has dilation 2^g, LM:553). */
+    int32_t groups, g_dy_col, g_x_col, shift_shl_group;
+    int64_t g_dw_stride;
 } dn_wgrad_desc;
 int dn_wgrad(const dn_wgrad_desc* d, void* stream);
 

@@ -51,6 +51,24 @@ def rup8(v):
     return (v + 7) // 8 * 8
 
 
+def test_wgrad_grouped_dilated():
+    """8 chains in one launch: group g reads its own column blocks and shift << g (WaveNet level weight gradients)."""
+    g_ = torch.Generator().manual_seed(3)
+    B, T, G, C = 2, 300, 8, 512
+    dY = (torch.randn(B * T, G * 2 * C, generator=g_) * 0.5).to(bf16).to(DEV)
+    X = (torch.randn(B * T, G * C, generator=g_) * 0.5).to(bf16).to(DEV)
+    dW = torch.zeros(G, C, C, device=DEV)
+    ops.wgrad(dY, X, dW, B, T, C, C, 0, 0, 1, groups=G, g_dy_col=2 * C, g_x_col=C, shift_shl_group=True)
+    y = dY.float().view(B, T, G, 2 * C)[..., :C]
+    x = X.float().view(B, T, G, C)
+    for g in range(G):
+        sh = 1 << g
+        xs = torch.zeros(B, T, C, device=DEV)
+        xs[:, sh:] = x[:, : T - sh, g]
+        want = torch.einsum("btn,btk->nk", y[:, :, g], xs)
+        assert rel(dW[g], want) < 2e-3, g
+
+
 def test_geglu_gate_norm_colsum_backward():
     g = torch.Generator().manual_seed(5)
     B, T, C, ip = 2, 70, 512, 256
