@@ -20,7 +20,8 @@ constexpr int AB_T = 128;             // tile edge (queries or keys)
 constexpr int AB_DH = 64;
 constexpr int AB_THREADS = 320;
 constexpr int AB_TILE = AB_T * AB_DH * 2;   // 16 KB
-constexpr int AB_SMEM = 6 * AB_TILE + 1024 + 256 + 2 * 2 * AB_T * 4;  // resident pair + 2 stages x pair + barriers + column scalars
+constexpr int AB_SMEM = 6 * AB_TILE + 1024 + 256 + 2 * 2 * AB_T * 4 + 2 * AB_T * 4 * 4;  // resident pair + 2 stages x pair + barriers
+                                                                                        // + per-query scalars + keep words
 
 int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                     const cuuint32_t* box);
@@ -256,6 +257,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     AbBars bb{bars + 0, bars + 1, bars + 3, bars + 5, bars + 6, bars + 7, bars + 8};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     float* colv = reinterpret_cast<float*>(bars + 32);   // [2 stages][L2 (128) | D (128)]
+    uint32_t* kws = reinterpret_cast<uint32_t*>(colv + 2 * 2 * AB_T);   // [2 stages][128 queries][4 keep words of this key tile]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
@@ -353,20 +355,34 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const bool key_ok = key < len;
         const long long bh = (long long)b * H + h;
         const int Tw = (T + 31) >> 5;
-        const int kword = (k0 + qd * 32) >> 5;          // the 32 keys of this warp share one keep word per query
         const int st_tid = threadIdx.x - 64;            // 0..255 among the softmax threads
-        for (int i = 0; i < nqb; ++i) {
+        // per-query scalars (L2, D) and keep words of a query block: fetched one block ahead into registers so their
+        // global-memory latency hides under the previous block's math, then published through smem
+        float pf_v = 0.f;
+        uint32_t pf_k[2] = {0u, 0u};
+        auto prefetch = [&](int i) {
             const int qb0 = i * AB_T;
-            // per-query scalars of this block -> smem (L2 = +inf for queries past T: P = 0)
-            float* cv = colv + (i & 1) * 2 * AB_T;
-            {
-                const int qq = qb0 + (st_tid & 127);
-                float v;
-                if (st_tid < 128) v = qq < T ? lse2[bh * T + qq] : INFINITY;
-                else v = qq < T ? delta[bh * T + qq] : 0.f;
-                cv[st_tid] = v;
+            const int qq = qb0 + (st_tid & 127);
+            if (st_tid < 128) pf_v = qq < T ? lse2[bh * T + qq] : INFINITY;   // L2 = +inf for queries past T: P = 0
+            else pf_v = qq < T ? delta[bh * T + qq] : 0.f;
+            if (keep) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int idx = st_tid * 2 + e, qi = idx >> 2, w = idx & 3;
+                    const int q2 = qb0 + qi, wi = (k0 >> 5) + w;
+                    pf_k[e] = wi < Tw ? keep[(bh * T + (q2 < T ? q2 : T - 1)) * Tw + wi] : 0u;
+                }
             }
+        };
+        if (nqb > 0) prefetch(0);
+        for (int i = 0; i < nqb; ++i) {
+            float* cv = colv + (i & 1) * 2 * AB_T;
+            uint32_t* kw = kws + (i & 1) * AB_T * 4;
+            cv[st_tid] = pf_v;
+            kw[st_tid * 2] = pf_k[0];
+            kw[st_tid * 2 + 1] = pf_k[1];
             named_bar_sync(1, 256);
+            if (i + 1 < nqb) prefetch(i + 1);
             float s0[32], s1[32], p0[32], p1[32];
             mbar_wait(bb.sdp_full, i & 1);
             tc_fence_after();
@@ -388,11 +404,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                         const float L2 = cv[qi], Dq = cv[AB_T + qi];
                         const float pr = key_ok ? ab_ex2(fmaf(s[c + e], scale_log2, -L2)) : 0.f;
                         float kf = keep_scale;
-                        if (keep) {
-                            const int qq = qb0 + qi;
-                            const uint32_t word = keep[(bh * T + (qq < T ? qq : T - 1)) * Tw + kword];
-                            kf = ((word >> lane) & 1u) ? keep_scale : 0.f;
-                        }
+                        if (keep) kf = ((kw[qi * 4 + qd] >> lane) & 1u) ? keep_scale : 0.f;
                         pd[e] = pr * kf;
                         ds[e] = scale * pr * (dp[c + e] * kf - Dq);
                     }

@@ -25,3 +25,21 @@ torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / n * 1e3
 fl = 4.0 * B * H * T * T * dh
 print(f"attention B={B} T={T} H={H} dh={dh} stagger={os.environ.get('DN_ATTN_STAGGER')}: {us:.1f} us  {fl / us / 1e6:.0f} TFLOP/s")
+
+if os.environ.get("BWD"):
+    lse = torch.empty(B * H, T, device="cuda")
+    bits = torch.randint(-2**31, 2**31 - 1, (B, H, T, (T + 31) // 32), dtype=torch.int32, device="cuda")
+    ops.attention_train(qkvs[0], out, lse, lens, bits, 1 / 0.9, B, T, H, dh)
+    dout = torch.randn(B * T, H * dh, device="cuda").to(torch.bfloat16)
+    dqkv = torch.empty_like(qkvs[0])
+    dws = torch.empty(B * H, T, device="cuda")
+    for keep in (bits, None):
+        ops.attention_bwd(qkvs[0], out, dout, lse, lens, keep, 1 / 0.9, dqkv, dws, B, T, H, dh)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            ops.attention_bwd(qkvs[0], out, dout, lse, lens, keep, 1 / 0.9, dqkv, dws, B, T, H, dh)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / n * 1e3
+        print(f"attention bwd (delta + dQ + dKdV) dropout={'on' if keep is not None else 'off'}: {us:.1f} us  {2.5 * fl / us / 1e6:.0f} TFLOP/s")
