@@ -40,7 +40,7 @@ constexpr int ATT_BM = 64, ATT_BN = 64, ATT_THREADS = 128;
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                 const int* __restrict__ lengths, int T, int H, float scale_log2) {
+                 const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2) {
     constexpr int LDS = DH + 8;       // padded smem row (elements): conflict-free ldmatrix
     constexpr int CH = DH / 8;        // 16-byte chunks per row
     constexpr int KS = DH / 16;       // k-steps over the head dim
@@ -184,6 +184,11 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+    if (lse2 && (lane & 3) == 0) {   // training form: row statistic L2 = m + log2(l) for the backward kernels
+        float* lp = lse2 + ((long long)b * H + h) * T;
+        if (r0 < T) lp[r0] = m0 + log2f(l0);
+        if (r1 < T) lp[r1] = m1 + log2f(l1);
+    }
     __nv_bfloat16* ob = out + (long long)b * T * (H * DH) + h * DH + (lane & 3) * 2;
 #pragma unroll
     for (int i = 0; i < DH / 8; ++i) {
@@ -193,7 +198,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 }
 
 template <int DH>
-static int launch_attention(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st) {
+static int launch_attention(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
+                            float* lse2 = nullptr) {
     constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * (DH + 8) * 2;
     static bool attr_set = false;
     if (!attr_set) {
@@ -203,7 +209,8 @@ static int launch_attention(const void* qkv, void* out, const int32_t* lengths, 
     dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
     const float scale_log2 = (1.0f / sqrtf((float)DH)) * 1.4426950408889634f;
     attention_kernel<DH><<<grid, ATT_THREADS, SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                         reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H, scale_log2);
+                                                         reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H, scale_log2,
+                                                         lse2);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -233,8 +240,13 @@ extern "C" int dn_attention(const void* qkv, void* out, const int32_t* lengths, 
 
 extern "C" int dn_attention_train(const void* qkv, void* out, float* lse2, const int32_t* lengths, const uint32_t* keep_bits,
                                   float keep_scale, int32_t B, int32_t T, int32_t H, int32_t dh, void* stream) {
-    if (!qkv || !out || !lse2 || B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535 || dh != 64) return DN_EINVAL;
+    if (!qkv || !out || !lse2 || B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535) return DN_EINVAL;
     if (reinterpret_cast<uintptr_t>(qkv) & 15) return DN_EINVAL;
+    if (dh == 96) {   // frozen VAE decoder (eval mode inside the training step: no dropout, LM:1520)
+        if (keep_bits) return DN_EINVAL;
+        return dn::launch_attention<96>(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2);
+    }
+    if (dh != 64) return DN_EINVAL;
     return dn::launch_attention_tc(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
                                    keep_scale, true);
 }

@@ -1,4 +1,5 @@
-// dn_attention_bwd (dh = 64): backward of the denoiser's self-attention (LM:299-343, :908-950) on tcgen05 tensor
+// dn_attention_bwd (dh = 64 | 96): backward of the self-attention of the denoiser (dh 64) and of the frozen VAE decoder
+// (dh 96, data gradients only, multitask training) (LM:299-343, :908-950) on tcgen05 tensor
 // cores, flash style (nothing of size N x N touches HBM).  Forward (attention_tc.cu, TRAIN form) saved, per query
 // row, L2 = m + log2(l) (log-sum-exp of the scaled scores in the log2 domain); with D[q] = sum_d dO[q,d] O[q,d]:
 //     P  = exp2(S * scale_log2 - L2[q])            (keys >= length: 0)
@@ -17,11 +18,25 @@
 namespace dn {
 
 constexpr int AB_T = 128;             // tile edge (queries or keys)
-constexpr int AB_DH = 64;
 constexpr int AB_THREADS = 320;
-constexpr int AB_TILE = AB_T * AB_DH * 2;   // 16 KB
-constexpr int AB_SMEM = 6 * AB_TILE + 1024 + 256 + 2 * 2 * AB_T * 4 + 2 * AB_T * 4 * 4;  // resident pair + 2 stages x pair + barriers
-                                                                                        // + per-query scalars + keep words
+constexpr int AB_TILE = AB_T * 64 * 2;      // 16 KB: one {64 columns, 128 rows} TMA box
+// an operand of head dim DH = ceil(DH/64) boxes (dh 96: the second box's upper 32 columns are never consumed)
+template <int DH> struct AbCfg {
+    static constexpr int NT = (DH + 63) / 64;
+    static constexpr int OP = NT * AB_TILE;
+    // resident pair + 2 stages x pair + align slack + barriers + per-query scalars + keep words
+    static constexpr int SMEM = 6 * OP + 1024 + 256 + 2 * 2 * AB_T * 4 + 2 * AB_T * 4 * 4;
+};
+// MN-major SW128 operand whose 64-column atoms are AB_TILE bytes apart (LBO); 8-row groups 1 KB apart (SBO)
+__device__ __forceinline__ uint64_t ab_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((AB_TILE >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
 int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                     const cuuint32_t* box);
@@ -37,6 +52,7 @@ __device__ __forceinline__ uint32_t ab_idesc(uint32_t n, uint32_t b_mn_major) {
 }
 
 // D[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]   (one warp per (frame, head); 2 bf16 per lane)
+template <int DH>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int B, int T,
                                   int H, float* __restrict__ delta) {
     const int lane = threadIdx.x & 31;
@@ -46,10 +62,17 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
     for (long long w = warp0; w < total; w += nwarps) {
         const int h = (int)(w % H);
         const long long bt = w / H;
-        const long long off = (bt * H + h) * AB_DH + lane * 2;
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
-        const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_o + off));
-        const float s = warp_sum(a.x * g.x + a.y * g.y);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; c += 64) {
+            if (c + lane * 2 < DH) {
+                const long long off = (bt * H + h) * DH + c + lane * 2;
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
+                const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_o + off));
+                acc += a.x * g.x + a.y * g.y;
+            }
+        }
+        const float s = warp_sum(acc);
         if (lane == 0) {
             const int b = (int)(bt / T), t = (int)(bt % T);
             delta[((long long)b * H + h) * T + t] = s;
@@ -67,18 +90,73 @@ struct AbBars {
     uint64_t* ds_empty;    // second GEMMs of block j complete
 };
 
+// loads one operand (NT boxes) of head dim DH: columns [col, col + 64 NT), rows [row0, row0 + 128) of utterance b
+template <int DH>
+__device__ __forceinline__ void ab_load(const CUtensorMap* m, uint64_t* bar, uint8_t* dst, int col, int row0, int b) {
+#pragma unroll
+    for (int i = 0; i < AbCfg<DH>::NT; ++i) tma_load_3d(m, bar, dst + i * AB_TILE, col + i * 64, row0, b);
+}
+// D[128 x 128] = A[128 x DH] B[128 x DH]^T, both K-major over DH (k-step k lives in box k/4)
+template <int DH>
+__device__ __forceinline__ void ab_mma_kk(uint32_t d_tmem, uint32_t sa, uint32_t sb, uint32_t idesc) {
+#pragma unroll
+    for (int k = 0; k < DH / 16; ++k) {
+        const uint32_t off = (k >> 2) * AB_TILE + (k & 3) * 32;
+        umma_bf16(d_tmem, umma_desc_sw128(sa + off), umma_desc_sw128(sb + off), idesc, k > 0);
+    }
+}
+// D[128 x DH] (+)= A[128 x 128 from TMEM] B[128 x DH], B MN-major (rows = contraction index, 16 per k-step)
+template <int DH>
+__device__ __forceinline__ void ab_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t sb, uint32_t idesc, bool accumulate) {
+#pragma unroll
+    for (int k = 0; k < AB_T / 16; ++k)
+        umma_bf16_ts(d_tmem, a_tmem + 8 * k, ab_desc_mn(sb + k * 16 * 128), idesc, accumulate || (k > 0));
+}
+// this thread's half (DH/2 columns) of an fp32 accumulator row -> bf16 global
+template <int DH>
+__device__ __forceinline__ void ab_store_half(uint32_t taddr, __nv_bfloat16* dst, bool valid_acc, bool write) {
+    constexpr int HC = DH / 2;   // 32 or 48
+    float o[48];
+    if (valid_acc) {
+        float a[32];
+        tmem_ld32(taddr, a);
+        if (HC == 48) {
+            float c[16];
+            tmem_ld16(taddr + 32, c);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[32 + i] = c[i];
+        } else {
+            tmem_ld_wait();
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = a[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) o[i] = 0.f;
+    }
+    if (write) {
+#pragma unroll
+        for (int i = 0; i < HC; i += 8)
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_bf16(o[i], o[i + 1]), pack_bf16(o[i + 2], o[i + 3]),
+                                                            pack_bf16(o[i + 4], o[i + 5]), pack_bf16(o[i + 6], o[i + 7]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- dQ
+template <int DH>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ lengths,
                    const uint32_t* __restrict__ keep, float keep_scale, __nv_bfloat16* __restrict__ dqkv, int T, int H,
                    float scale, float scale_log2) {
+    constexpr int OP = AbCfg<DH>::OP;
     extern __shared__ uint8_t ab_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                     // resident: Q tile, dO tile
-    uint8_t* sDO = smem + AB_TILE;
-    uint8_t* sStage = smem + 2 * AB_TILE;   // 2 stages x (K, V)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AB_TILE);
+    uint8_t* sDO = smem + OP;
+    uint8_t* sStage = smem + 2 * OP;        // 2 stages x (K, V)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * OP);
     AbBars bb{bars + 0, bars + 1, bars + 3, bars + 5, bars + 6, bars + 7, bars + 8};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
@@ -87,7 +165,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     int len = lengths ? lengths[b] : T;
     len = len > T ? T : len;
     const int nkb = (len + AB_T - 1) / AB_T;
-    const int qcol = h * AB_DH, kcol = (H + h) * AB_DH, vcol = (2 * H + h) * AB_DH;
+    const int qcol = h * DH, kcol = (H + h) * DH, vcol = (2 * H + h) * DH;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -111,37 +189,31 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM: S fp32 [0,128) | dP fp32 [128,256) | dS bf16x2 [256,320) | dQ fp32 [320,384)
+    // TMEM: S fp32 [0,128) | dP fp32 [128,256) | dS bf16x2 [256,320) | dQ fp32 [320,320+DH)
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDS = tmem_base + 256, tDQ = tmem_base + 320;
 
     if (warp == 0) {
         if (lane == 0 && nkb > 0) {
-            mbar_expect_tx(bb.r_full, 2 * AB_TILE);
-            tma_load_3d(&tmQKV, bb.r_full, sQ, qcol, q0, b);
-            tma_load_3d(&tmDO, bb.r_full, sDO, h * AB_DH, q0, b);
+            mbar_expect_tx(bb.r_full, 2 * OP);
+            ab_load<DH>(&tmQKV, bb.r_full, sQ, qcol, q0, b);
+            ab_load<DH>(&tmDO, bb.r_full, sDO, h * DH, q0, b);
             for (int j = 0; j < nkb; ++j) {
                 const int st = j & 1;
                 mbar_wait(bb.st_empty + st, ((j >> 1) & 1) ^ 1);
-                mbar_expect_tx(bb.st_full + st, 2 * AB_TILE);
-                tma_load_3d(&tmQKV, bb.st_full + st, sStage + st * 2 * AB_TILE, kcol, j * AB_T, b);
-                tma_load_3d(&tmQKV, bb.st_full + st, sStage + st * 2 * AB_TILE + AB_TILE, vcol, j * AB_T, b);
+                mbar_expect_tx(bb.st_full + st, 2 * OP);
+                ab_load<DH>(&tmQKV, bb.st_full + st, sStage + st * 2 * OP, kcol, j * AB_T, b);
+                ab_load<DH>(&tmQKV, bb.st_full + st, sStage + st * 2 * OP + OP, vcol, j * AB_T, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
-            const uint32_t id_s = ab_idesc(AB_T, 0), id_q = ab_idesc(AB_DH, 1);
-            const uint64_t dq_ = umma_desc_sw128(smem_u32(sQ));
-            const uint64_t ddo = umma_desc_sw128(smem_u32(sDO));
+            const uint32_t id_s = ab_idesc(AB_T, 0), id_q = ab_idesc(DH, 1);
             auto issue_first = [&](int j) {
                 const int st = j & 1;
                 mbar_wait(bb.st_full + st, (j >> 1) & 1);
                 tc_fence_after();
-                const uint64_t dk = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));
-                const uint64_t dv = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE + AB_TILE));
-#pragma unroll
-                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tS, dq_ + 2 * k, dk + 2 * k, id_s, k > 0);
-#pragma unroll
-                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tDP, ddo + 2 * k, dv + 2 * k, id_s, k > 0);
+                ab_mma_kk<DH>(tS, smem_u32(sQ), smem_u32(sStage + st * 2 * OP), id_s);          // S  = Q  K^T
+                ab_mma_kk<DH>(tDP, smem_u32(sDO), smem_u32(sStage + st * 2 * OP + OP), id_s);   // dP = dO V^T
                 umma_commit(bb.sdp_full);
             };
             mbar_wait(bb.r_full, 0);
@@ -154,10 +226,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 const int st = j & 1;
                 mbar_wait(bb.ds_full, j & 1);
                 tc_fence_after();
-                const uint64_t dk = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));   // K as MN-major B operand
-#pragma unroll
-                for (int k = 0; k < AB_T / 16; ++k)
-                    umma_bf16_ts(tDQ, tDS + 8 * k, dk + (uint64_t)((k * 16 * 128) >> 4), id_q, (j > 0) || (k > 0));
+                ab_mma_ts<DH>(tDQ, tDS, smem_u32(sStage + st * 2 * OP), id_q, j > 0);            // dQ += dS K
                 umma_commit(bb.st_empty + st);
                 umma_commit(bb.ds_empty);
             }
@@ -221,21 +290,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             mbar_wait(bb.ds_empty, (nkb - 1) & 1);
             tc_fence_after();
         }
-        float o[32];
-        if (nkb > 0) {
-            tmem_ld32(tDQ + lane_off + half * 32, o);
-            tmem_ld_wait();
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0.f;
-        }
-        if (t < T) {
-            __nv_bfloat16* op = dqkv + ((long long)b * T + t) * (3 * H * AB_DH) + qcol + half * 32;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8)
-                *reinterpret_cast<uint4*>(op + i) = make_uint4(pack_bf16(o[i], o[i + 1]), pack_bf16(o[i + 2], o[i + 3]),
-                                                               pack_bf16(o[i + 4], o[i + 5]), pack_bf16(o[i + 6], o[i + 7]));
-        }
+        ab_store_half<DH>(tDQ + lane_off + half * (DH / 2),
+                          dqkv + ((long long)b * T + (t < T ? t : 0)) * (3 * H * DH) + qcol + half * (DH / 2), nkb > 0, t < T);
     }
     tc_fence_before();
     __syncthreads();
@@ -243,17 +299,23 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------- dK, dV
+template <int DH>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ lengths,
                     const uint32_t* __restrict__ keep, float keep_scale, __nv_bfloat16* __restrict__ dqkv, int T, int H,
                     float scale, float scale_log2) {
+    constexpr int OP = AbCfg<DH>::OP;
+    // dh 64: P^T / dS^T have their own TMEM columns, so S^T / dP^T of the next query block can be issued while this
+    // block's softmax runs.  dh 96 needs 2 x 96 accumulator columns: P^T / dS^T then alias S^T / dP^T and blocks run
+    // strictly one after the other.
+    constexpr bool EARLY = DH == 64;
     extern __shared__ uint8_t ab_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sK = smem;                     // resident: K tile, V tile
-    uint8_t* sV = smem + AB_TILE;
-    uint8_t* sStage = smem + 2 * AB_TILE;   // 2 stages x (Q, dO)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AB_TILE);
+    uint8_t* sV = smem + OP;
+    uint8_t* sStage = smem + 2 * OP;        // 2 stages x (Q, dO)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * OP);
     AbBars bb{bars + 0, bars + 1, bars + 3, bars + 5, bars + 6, bars + 7, bars + 8};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     float* colv = reinterpret_cast<float*>(bars + 32);   // [2 stages][L2 (128) | D (128)]
@@ -266,7 +328,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     // queries of every frame of the padded utterance attend (padded queries are computed by the reference too, LM:333);
     // keys past the length have P = 0, so key tiles past the length produce exact zeros.
     const int nqb = (k0 < len) ? (T + AB_T - 1) / AB_T : 0;
-    const int qcol = h * AB_DH, kcol = (H + h) * AB_DH, vcol = (2 * H + h) * AB_DH;
+    const int qcol = h * DH, kcol = (H + h) * DH, vcol = (2 * H + h) * DH;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -290,60 +352,54 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM: S^T [0,128) | dP^T [128,256) | P^T bf16x2 [256,320) | dS^T bf16x2 [320,384) | dV [384,448) | dK [448,512)
-    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320;
-    const uint32_t tDV = tmem_base + 384, tDK = tmem_base + 448;
+    // TMEM dh 64: S^T [0,128) | dP^T [128,256) | P^T bf16x2 [256,320) | dS^T bf16x2 [320,384) | dV [384,448) | dK [448,512)
+    //      dh 96: S^T [0,128) | dP^T [128,256) | P^T over [0,64) | dS^T over [128,192) | dV [256,352) | dK [352,448)
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128;
+    const uint32_t tP = EARLY ? tmem_base + 256 : tmem_base, tDS = EARLY ? tmem_base + 320 : tmem_base + 128;
+    const uint32_t tDV = EARLY ? tmem_base + 384 : tmem_base + 256, tDK = tDV + DH;
 
     if (warp == 0) {
         if (lane == 0 && nqb > 0) {
-            mbar_expect_tx(bb.r_full, 2 * AB_TILE);
-            tma_load_3d(&tmQKV, bb.r_full, sK, kcol, k0, b);
-            tma_load_3d(&tmQKV, bb.r_full, sV, vcol, k0, b);
+            mbar_expect_tx(bb.r_full, 2 * OP);
+            ab_load<DH>(&tmQKV, bb.r_full, sK, kcol, k0, b);
+            ab_load<DH>(&tmQKV, bb.r_full, sV, vcol, k0, b);
             for (int i = 0; i < nqb; ++i) {
                 const int st = i & 1;
                 mbar_wait(bb.st_empty + st, ((i >> 1) & 1) ^ 1);
-                mbar_expect_tx(bb.st_full + st, 2 * AB_TILE);
-                tma_load_3d(&tmQKV, bb.st_full + st, sStage + st * 2 * AB_TILE, qcol, i * AB_T, b);
-                tma_load_3d(&tmDO, bb.st_full + st, sStage + st * 2 * AB_TILE + AB_TILE, h * AB_DH, i * AB_T, b);
+                mbar_expect_tx(bb.st_full + st, 2 * OP);
+                ab_load<DH>(&tmQKV, bb.st_full + st, sStage + st * 2 * OP, qcol, i * AB_T, b);
+                ab_load<DH>(&tmDO, bb.st_full + st, sStage + st * 2 * OP + OP, h * DH, i * AB_T, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && nqb > 0) {
-            const uint32_t id_s = ab_idesc(AB_T, 0), id_o = ab_idesc(AB_DH, 1);
-            const uint64_t dk = umma_desc_sw128(smem_u32(sK));
-            const uint64_t dv = umma_desc_sw128(smem_u32(sV));
+            const uint32_t id_s = ab_idesc(AB_T, 0), id_o = ab_idesc(DH, 1);
             auto issue_first = [&](int i) {
                 const int st = i & 1;
                 mbar_wait(bb.st_full + st, (i >> 1) & 1);
                 tc_fence_after();
-                const uint64_t dq_ = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));
-                const uint64_t ddo = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE + AB_TILE));
-#pragma unroll
-                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tS, dk + 2 * k, dq_ + 2 * k, id_s, k > 0);
-#pragma unroll
-                for (int k = 0; k < AB_DH / 16; ++k) umma_bf16(tDP, dv + 2 * k, ddo + 2 * k, id_s, k > 0);
+                ab_mma_kk<DH>(tS, smem_u32(sK), smem_u32(sStage + st * 2 * OP), id_s);         // S^T  = K Q^T
+                ab_mma_kk<DH>(tDP, smem_u32(sV), smem_u32(sStage + st * 2 * OP + OP), id_s);   // dP^T = V dO^T
                 umma_commit(bb.sdp_full);
             };
             mbar_wait(bb.r_full, 0);
             issue_first(0);
             for (int i = 0; i < nqb; ++i) {
-                if (i + 1 < nqb) {
+                if (EARLY && i + 1 < nqb) {
                     mbar_wait(bb.s_free, i & 1);
                     issue_first(i + 1);
                 }
                 const int st = i & 1;
                 mbar_wait(bb.ds_full, i & 1);
                 tc_fence_after();
-                const uint64_t dq_ = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE));            // Q, MN-major B
-                const uint64_t ddo = umma_desc_sw128(smem_u32(sStage + st * 2 * AB_TILE + AB_TILE));  // dO, MN-major B
-#pragma unroll
-                for (int k = 0; k < AB_T / 16; ++k)
-                    umma_bf16_ts(tDV, tP + 8 * k, ddo + (uint64_t)((k * 16 * 128) >> 4), id_o, (i > 0) || (k > 0));
-#pragma unroll
-                for (int k = 0; k < AB_T / 16; ++k)
-                    umma_bf16_ts(tDK, tDS + 8 * k, dq_ + (uint64_t)((k * 16 * 128) >> 4), id_o, (i > 0) || (k > 0));
+                ab_mma_ts<DH>(tDV, tP, smem_u32(sStage + st * 2 * OP + OP), id_o, i > 0);      // dV += P^T dO
+                ab_mma_ts<DH>(tDK, tDS, smem_u32(sStage + st * 2 * OP), id_o, i > 0);          // dK += dS^T Q
                 umma_commit(bb.st_empty + st);
                 umma_commit(bb.ds_empty);
+                if (!EARLY && i + 1 < nqb) {
+                    mbar_wait(bb.ds_empty, i & 1);   // P^T / dS^T alias the next block's S^T / dP^T
+                    issue_first(i + 1);
+                }
             }
         }
     } else {
@@ -414,9 +470,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             };
             half_row(s0, p0, half * 64, wp0, wd0);
             half_row(s1, p1, half * 64 + 32, wp1, wd1);
-            if (i > 0) {
-                mbar_wait(bb.ds_empty, (i - 1) & 1);
-                tc_fence_after();
+            if (EARLY) {
+                if (i > 0) {
+                    mbar_wait(bb.ds_empty, (i - 1) & 1);
+                    tc_fence_after();
+                }
+            } else {
+                named_bar_sync(2, 256);   // the partner thread of this row has read the S^T / dP^T columns P^T / dS^T overwrite
             }
             tmem_st16(tP + lane_off + half * 32, wp0);
             tmem_st16(tP + lane_off + half * 32 + 16, wp1);
@@ -430,29 +490,64 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             mbar_wait(bb.ds_empty, (nqb - 1) & 1);
             tc_fence_after();
         }
-        float ov[32], ok[32];
-        if (nqb > 0) {
-            tmem_ld32(tDV + lane_off + half * 32, ov);
-            tmem_ld32(tDK + lane_off + half * 32, ok);
-            tmem_ld_wait();
-        } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) { ov[c] = 0.f; ok[c] = 0.f; }
-        }
-        if (key < T) {
-            __nv_bfloat16* base = dqkv + ((long long)b * T + key) * (3 * H * AB_DH) + half * 32;
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-                *reinterpret_cast<uint4*>(base + kcol + c) = make_uint4(pack_bf16(ok[c], ok[c + 1]), pack_bf16(ok[c + 2], ok[c + 3]),
-                                                                        pack_bf16(ok[c + 4], ok[c + 5]), pack_bf16(ok[c + 6], ok[c + 7]));
-                *reinterpret_cast<uint4*>(base + vcol + c) = make_uint4(pack_bf16(ov[c], ov[c + 1]), pack_bf16(ov[c + 2], ov[c + 3]),
-                                                                        pack_bf16(ov[c + 4], ov[c + 5]), pack_bf16(ov[c + 6], ov[c + 7]));
-            }
-        }
+        __nv_bfloat16* base = dqkv + ((long long)b * T + (key < T ? key : 0)) * (3 * H * DH) + half * (DH / 2);
+        ab_store_half<DH>(tDK + lane_off + half * (DH / 2), base + kcol, nqb > 0, key < T);
+        ab_store_half<DH>(tDV + lane_off + half * (DH / 2), base + vcol, nqb > 0, key < T);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int DH>
+static int launch_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, const int32_t* lengths,
+                                const uint32_t* keep_bits, float keep_scale, void* dqkv, float* delta_ws, int B, int T, int H,
+                                cudaStream_t st) {
+    constexpr int SMEM = AbCfg<DH>::SMEM;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    {
+        const long long warps = (long long)B * T * H;
+        long long blocks = (warps + 7) / 8;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        attn_delta_kernel<DH><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                           reinterpret_cast<const __nv_bfloat16*>(dout), B, T, H, delta_ws);
+        DN_LAUNCH_CHECK();
+        count_launch();
+    }
+    CUtensorMap mq, mdo;
+    {
+        const int ld = 3 * H * DH;
+        cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+        cuuint32_t box[3] = {64, AB_T, 1};
+        int r = encode_bf16_map(&mq, qkv, 3, dims, str, box);
+        if (r) return r;
+    }
+    {
+        const int ld = H * DH;
+        cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+        cuuint32_t box[3] = {64, AB_T, 1};
+        int r = encode_bf16_map(&mdo, dout, 3, dims, str, box);
+        if (r) return r;
+    }
+    dim3 grid((T + AB_T - 1) / AB_T, H, B);
+    const float scale = 1.0f / sqrtf((float)DH);
+    const float scale_log2 = scale * 1.4426950408889634f;
+    attn_bwd_dq_kernel<DH><<<grid, AB_THREADS, SMEM, st>>>(mq, mdo, lse2, delta_ws, lengths, keep_bits, keep_scale,
+                                                           reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, scale, scale_log2);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    attn_bwd_dkv_kernel<DH><<<grid, AB_THREADS, SMEM, st>>>(mq, mdo, lse2, delta_ws, lengths, keep_bits, keep_scale,
+                                                            reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, scale, scale_log2);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
 }
 
 }  // namespace dn
@@ -462,50 +557,13 @@ using namespace dn;
 extern "C" int dn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, const int32_t* lengths,
                                 const uint32_t* keep_bits, float keep_scale, void* dqkv, float* delta_ws, int32_t B, int32_t T,
                                 int32_t H, int32_t dh, void* stream) {
-    if (!qkv || !out || !dout || !lse2 || !dqkv || !delta_ws || B <= 0 || T <= 0 || H <= 0 || dh != AB_DH) return DN_EINVAL;
+    if (!qkv || !out || !dout || !lse2 || !dqkv || !delta_ws || B <= 0 || T <= 0 || H <= 0) return DN_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dqkv)) & 15)
+        return DN_EINVAL;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-        DN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-        attr_set = true;
-    }
-    {
-        const long long warps = (long long)B * T * H;
-        long long blocks = (warps + 7) / 8;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        attn_delta_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
-                                                       reinterpret_cast<const __nv_bfloat16*>(dout), B, T, H, delta_ws);
-        DN_LAUNCH_CHECK();
-        count_launch();
-    }
-    CUtensorMap mq, mdo;
-    {
-        const int ld = 3 * H * AB_DH;
-        cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
-        cuuint32_t box[3] = {AB_DH, AB_T, 1};
-        int r = encode_bf16_map(&mq, qkv, 3, dims, str, box);
-        if (r) return r;
-    }
-    {
-        const int ld = H * AB_DH;
-        cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
-        cuuint32_t box[3] = {AB_DH, AB_T, 1};
-        int r = encode_bf16_map(&mdo, dout, 3, dims, str, box);
-        if (r) return r;
-    }
-    dim3 grid((T + AB_T - 1) / AB_T, H, B);
-    const float scale = 1.0f / sqrtf((float)AB_DH);
-    const float scale_log2 = scale * 1.4426950408889634f;
-    attn_bwd_dq_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mdo, lse2, delta_ws, lengths, keep_bits, keep_scale,
-                                                          reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, scale, scale_log2);
-    DN_LAUNCH_CHECK();
-    count_launch();
-    attn_bwd_dkv_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mdo, lse2, delta_ws, lengths, keep_bits, keep_scale,
-                                                           reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, scale, scale_log2);
-    DN_LAUNCH_CHECK();
-    count_launch();
-    return 0;
+    if (dh == 64)
+        return launch_attention_bwd<64>(qkv, out, dout, lse2, lengths, keep_bits, keep_scale, dqkv, delta_ws, B, T, H, st);
+    if (dh == 96)
+        return launch_attention_bwd<96>(qkv, out, dout, lse2, lengths, keep_bits, keep_scale, dqkv, delta_ws, B, T, H, st);
+    return DN_EINVAL;
 }

@@ -133,10 +133,11 @@ def test_geglu_gate_norm_colsum_backward():
     assert rel(cs, src.float()[:, 128:].sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("T,lens,drop", [(200, [200, 131], True), (128, [128, 1], False), (300, [300, 257], True)])
-def test_attention_train_forward_backward(T, lens, drop):
+@pytest.mark.parametrize("T,lens,drop,dh", [(200, [200, 131], True, 64), (128, [128, 1], False, 64), (300, [300, 257], True, 64),
+                                            (200, [200, 131], False, 96), (260, [260, 3], False, 96)])
+def test_attention_train_forward_backward(T, lens, drop, dh):
     g = torch.Generator().manual_seed(T)
-    B, H, dh = len(lens), 8, 64
+    B, H = len(lens), 8
     M = B * T
     qkv = (torch.randn(M, 3 * H * dh, generator=g) * 1.5).to(bf16).to(DEV)
     dout = torch.randn(M, H * dh, generator=g).to(bf16)
@@ -171,7 +172,7 @@ def test_attention_train_forward_backward(T, lens, drop):
     got = dqkv.float().cpu().view(B, T, 3, H * dh)
     want = leaf.grad.view(B, T, 3, H * dh)
     errs = [rel(got[:, :, i], want[:, :, i]) for i in range(3)]
-    print(f"[parity] attention train T{T} drop={drop}: out {e_out:.2e} lse {e_lse:.2e} dq/dk/dv {errs}")
+    print(f"[parity] attention train dh{dh} T{T} drop={drop}: out {e_out:.2e} lse {e_lse:.2e} dq/dk/dv {errs}")
     assert e_out < 1.5e-2 and e_lse < 2e-2 and max(errs) < 2.5e-2
 
 
