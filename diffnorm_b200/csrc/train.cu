@@ -330,7 +330,8 @@ train_noise_kernel(const float* __restrict__ zl, const float* __restrict__ eps0,
 __global__ void __launch_bounds__(TR_THREADS)
 noise_loss_kernel(const float* __restrict__ pred, int lde, const float* __restrict__ eps, const int* __restrict__ lengths,
                   const float* __restrict__ coef, const int* __restrict__ t_idx, int B, int T, int z,
-                  float* __restrict__ loss, __nv_bfloat16* __restrict__ dpred, int ldd, float grad_scale) {
+                  float* __restrict__ loss, __nv_bfloat16* __restrict__ dpred, int ldd, float grad_scale,
+                  const __nv_bfloat16* __restrict__ dx1, int ld1) {
     __shared__ float red[TR_THREADS / 32];
     const int groups = ldd / 4;
     const long long total = (long long)B * T * groups;
@@ -349,6 +350,14 @@ noise_loss_kernel(const float* __restrict__ pred, int lde, const float* __restri
             acc += w * (d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
             const float gsc = 2.f * w * grad_scale;
             d.x *= gsc; d.y *= gsc; d.z *= gsc; d.w *= gsc;
+            if (dx1) {   // multitask: x1_hat = (x_t - s1 pred) / max(sa, 1e-10)  =>  d pred += -s1 / max(sa, 1e-10) * d x1_hat
+                const float* cf = coef + (long long)t_idx[b] * 4;
+                const float k = -cf[1] / fmaxf(cf[0], 1e-10f);
+                const uint2 v = *reinterpret_cast<const uint2*>(dx1 + r * ld1 + c);
+                const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+                const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+                d.x += k * a0.x; d.y += k * a0.y; d.z += k * a1.x; d.w += k * a1.y;
+            }
         }
         if (dpred) *reinterpret_cast<uint2*>(dpred + r * ldd + c) = make_uint2(pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
     }
@@ -435,6 +444,72 @@ decode_losses_kernel(const float* __restrict__ recon, const float* __restrict__ 
         atomicAdd(out + 3, a_ok);
         atomicAdd(out + 4, a_tok);
         atomicAdd(out + 5, a_fr);
+    }
+}
+
+// Backward of the decode branch's losses (multitask, LM:1576-1604): stats = dn_decode_losses' out6 (device doubles).
+// d logits = nll_scale / n_tokens * [ (1 - eps - e_i) (p - onehot(u)) + e_i (V p - 1) ],  e_i = eps / (V - 1), rows with u != 0
+__global__ void __launch_bounds__(TR_THREADS)
+lsnll_bwd_kernel(const float* __restrict__ logits, int ld, int V, const long long* __restrict__ units, long long rows,
+                 const double* __restrict__ stats, float eps_ls, float nll_scale, __nv_bfloat16* __restrict__ dlogits, int ldd) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float ntok = fmaxf((float)stats[4], 1.f);
+    const float e_i = eps_ls / (float)(V - 1);
+    const float a = (1.f - eps_ls - e_i), sc = nll_scale / ntok;
+    for (long long r = warp0; r < rows; r += nwarps) {
+        const long long u = units[r];
+        const float* lg = logits + r * ld;
+        __nv_bfloat16* dl = dlogits + r * ldd;
+        if (u == 0) {
+            for (int c = lane * 2; c < ldd; c += 64) *reinterpret_cast<uint32_t*>(dl + c) = 0u;
+            continue;
+        }
+        float mx = -INFINITY;
+        for (int c = lane; c < V; c += 32) mx = fmaxf(mx, lg[c]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int c = lane; c < V; c += 32) se += __expf(lg[c] - mx);
+        se = warp_sum(se);
+        const float inv = 1.f / se;
+        for (int c = lane * 2; c < ldd; c += 64) {
+            float g[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cc = c + e;
+                if (cc < V) {
+                    const float p = __expf(lg[cc] - mx) * inv;
+                    g[e] = sc * (a * (p - (cc == (int)u ? 1.f : 0.f)) + e_i * ((float)V * p - 1.f));
+                } else {
+                    g[e] = 0.f;
+                }
+            }
+            *reinterpret_cast<uint32_t*>(dl + c) = pack_bf16(g[0], g[1]);
+        }
+    }
+}
+
+// d recon = d_lm (lm-head data gradient, fp32) + mse_scale * 2 (recon - audio) / (n_frames C) on valid frames -> bf16
+__global__ void __launch_bounds__(TR_THREADS)
+recon_grad_kernel(const float* __restrict__ recon, const float* __restrict__ audio, const float* __restrict__ d_lm,
+                  const int* __restrict__ lengths, int B, int T, int C, const double* __restrict__ stats, float mse_scale,
+                  __nv_bfloat16* __restrict__ out) {
+    const int groups = C / 4;
+    const long long total = (long long)B * T * groups;
+    const float k = 2.f * mse_scale / (fmaxf((float)stats[5], 1.f) * (float)C);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int c = (int)(i % groups) * 4;
+        float4 g = *reinterpret_cast<const float4*>(d_lm + r * C + c);
+        if ((int)(r % T) < lengths[r / T]) {
+            const float4 a = *reinterpret_cast<const float4*>(recon + r * C + c);
+            const float4 t = *reinterpret_cast<const float4*>(audio + r * C + c);
+            g.x += k * (a.x - t.x); g.y += k * (a.y - t.y); g.z += k * (a.z - t.z); g.w += k * (a.w - t.w);
+        } else {
+            g = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<uint2*>(out + r * C + c) = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
     }
 }
 
@@ -666,12 +741,12 @@ extern "C" int dn_train_noise(const float* z_lat, const float* eps0, const float
 
 extern "C" int dn_noise_loss(const float* pred, int32_t lde, const float* eps, const int32_t* lengths, const float* coef,
                              const int32_t* t_idx, int32_t B, int32_t T, int32_t z, float* loss, void* dpred, int32_t ldd,
-                             float grad_scale, void* stream) {
+                             float grad_scale, const void* dx1, int32_t ld1, void* stream) {
     if (!pred || !eps || !lengths || !coef || !t_idx || !loss || B <= 0 || T <= 0 || z <= 0 || z % 4 || lde % 4 || ldd % 4 ||
-        ldd < z)
+        ldd < z || (dx1 && (ld1 % 4 || ld1 < z)))
         return DN_EINVAL;
     noise_loss_kernel<<<tr_grid((long long)B * T * (ldd / 4), TR_THREADS), TR_THREADS, 0, ST(stream)>>>(
-        pred, lde, eps, lengths, coef, t_idx, B, T, z, loss, (bf*)dpred, ldd, grad_scale);
+        pred, lde, eps, lengths, coef, t_idx, B, T, z, loss, (bf*)dpred, ldd, grad_scale, (const bf*)dx1, ld1);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -695,6 +770,26 @@ extern "C" int dn_decode_losses(const float* recon, const float* audio, int32_t 
     DN_CUDA_OK(cudaMemsetAsync(out6, 0, 6 * sizeof(double), ST(stream)));
     decode_losses_kernel<<<tr_grid((long long)B * T, TR_THREADS / 32), TR_THREADS, 0, ST(stream)>>>(
         recon, audio, C, logits, ld, V, (const long long*)units, lengths, B, T, out6);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_lsnll_bwd(const float* logits, int32_t ld, int32_t V, const int64_t* units, int64_t rows, const double* stats,
+                            float eps_ls, float nll_scale, void* dlogits, int32_t ldd, void* stream) {
+    if (!logits || !units || !stats || !dlogits || rows <= 0 || V <= 1 || ld < V || ldd < V || ldd % 2) return DN_EINVAL;
+    lsnll_bwd_kernel<<<tr_grid(rows, TR_THREADS / 32), TR_THREADS, 0, ST(stream)>>>(logits, ld, V, (const long long*)units, rows,
+                                                                                   stats, eps_ls, nll_scale, (bf*)dlogits, ldd);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_recon_grad(const float* recon, const float* audio, const float* d_lm, const int32_t* lengths, int32_t B,
+                             int32_t T, int32_t C, const double* stats, float mse_scale, void* out, void* stream) {
+    if (!recon || !audio || !d_lm || !lengths || !stats || !out || B <= 0 || T <= 0 || C <= 0 || C % 4) return DN_EINVAL;
+    recon_grad_kernel<<<tr_grid((long long)B * T * (C / 4), TR_THREADS), TR_THREADS, 0, ST(stream)>>>(
+        recon, audio, d_lm, lengths, B, T, C, stats, mse_scale, (bf*)out);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

@@ -291,11 +291,26 @@ def train_noise(z_lat, eps0, eps, beta0: float, coef, t_idx, x_t, xb):
     return x_t
 
 
-def noise_loss(pred, eps, lengths, coef, t_idx, B, T, z, loss, dpred=None, grad_scale: float = 1.0):
+def noise_loss(pred, eps, lengths, coef, t_idx, B, T, z, loss, dpred=None, grad_scale: float = 1.0, dx1=None):
     _chk(pred, f32, "pred"), _chk(eps, f32, "eps"), _chk(loss, f32, "loss")
     check(lib.dn_noise_loss(_p(pred), pred.shape[-1], _p(eps), _p(lengths), _p(coef), _p(t_idx), B, T, z, _p(loss),
-                            _p(dpred), z if dpred is None else dpred.shape[-1], grad_scale, _stream()), "dn_noise_loss")
+                            _p(dpred), z if dpred is None else dpred.shape[-1], grad_scale, _p(dx1),
+                            0 if dx1 is None else dx1.shape[-1], _stream()), "dn_noise_loss")
     return loss
+
+
+def lsnll_bwd(logits, vocab: int, units, stats, eps_ls: float, nll_scale: float, dlogits):
+    _chk(logits, f32, "logits"), _chk(units, i64, "units"), _chk(dlogits, bf16, "dlogits")
+    check(lib.dn_lsnll_bwd(_p(logits), logits.shape[-1], vocab, _p(units), units.numel(), _p(stats), eps_ls, nll_scale,
+                           _p(dlogits), dlogits.shape[-1], _stream()), "dn_lsnll_bwd")
+    return dlogits
+
+
+def recon_grad(recon, audio, d_lm, lengths, B, T, stats, mse_scale: float, out):
+    _chk(recon, f32, "recon"), _chk(audio, f32, "audio"), _chk(d_lm, f32, "d_lm"), _chk(out, bf16, "out")
+    check(lib.dn_recon_grad(_p(recon), _p(audio), _p(d_lm), _p(lengths), B, T, recon.shape[-1], _p(stats), mse_scale,
+                            _p(out), _stream()), "dn_recon_grad")
+    return out
 
 
 def pred_x1(x_t, pred, coef, t_idx, B, T, z, xb):

@@ -283,7 +283,8 @@ class LatentDiscreteModel(FairseqEncoder):
         rp = _replay or {}
         outs = _TrainStepFn.apply(tr, audio, audio_units, lens, rp, need_grad, names, *params)
         total, nll, mse, acc = outs
-        return {"total_loss": total, "nll_loss": nll, "recon_mse_loss": mse, "noise_loss": total.detach(), "acc": acc}
+        noise = total.detach() - (50.0 * mse + nll) / self.timesteps if self.multitask else total.detach()
+        return {"total_loss": total, "nll_loss": nll, "recon_mse_loss": mse, "noise_loss": noise, "acc": acc}
 
 
 class _TrainStepFn(torch.autograd.Function):

@@ -56,13 +56,173 @@ class _GradDict(dict):
             self._hook(k, v)
 
 
+class FrozenDecoderTrain:
+    """decode_feature (LM:1109-1116) of the FROZEN VAE inside a multitask training step: an un-fused forward that keeps
+    the pre-activations, and the data-gradient backward down to x1_hat (no weight gradients: diff_discrete.py:79-81
+    freezes the VAE).  Packed once; same kernels as the denoiser path (unconditioned WaveNets with 3 chains x 2 levels,
+    6-layer transformer with 8 x 96 heads and gamma-parameter RMSNorms, to_pred, decoder_lm)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: DiffNormConfig, dev, buf):
+        self.cfg, self.dev, self.buf = cfg, dev, buf
+        c = cfg
+        pre = "speech_decoder."
+        w = lambda k: sd[pre + k].detach().to(dev).float()
+        self.zp = rup(c.latent_dim, 64)
+        self.D, self.H, self.dh = c.feat_dim, c.vae_heads, c.vae_dim_head
+        self.inner = DiffNormConfig.ff_inner(self.D)
+        self.ip = rup(self.inner, 128)
+        self.vl = rup(c.vocab, 64)                 # dlogits row width (K of the lm-head data gradient)
+        G, S = c.vae_layers, c.vae_stacks
+        self.G, self.S = G, S
+        self.blocks = []
+        cin_pad = self.zp
+        dec_w = c.dec_widths()
+        for i, (cin, cout) in enumerate(dec_w):
+            last = i == len(dec_w) - 1
+            cp = rup(cout, 128)
+            b = _Plans()
+            b.cp, b.cin_pad, b.last = cp, cin_pad, last
+            p = f"decoder_wave.{i}."
+            b.init = pack_conv3(w(p + "init_conv.weight"), w(p + "init_conv.bias"), cin_pad=cin_pad, n_pad=cp, name=p + "init")
+            b.init_T = pack_conv3(w(p + "init_conv.weight").permute(1, 0, 2), None, cin_pad=cp, n_pad=cin_pad, shift_sign=-1,
+                                  name=p + "init^T")
+            b.lvl, b.lvl_T = [], []
+            tiles = cp // 128
+            for s_ in range(S):
+                blk = [f"{p}stacks.{s_}.blocks.{g}." for g in range(G)]
+                convs, ress = [w(k + "conv.weight") for k in blk], [w(k + "res_conv.weight") for k in blk]
+                lv = pack_wavenet_level(convs, [w(k + "conv.bias") for k in blk], ress, [w(k + "res_conv.bias") for k in blk], cp)
+                bi = torch.stack([lv.bias.view(G, tiles, 128), lv.bias2.view(G, tiles, 128)], dim=2).reshape(-1).contiguous()
+                b.lvl.append(GemmPlan(lv.W, lv.segs, 2 * cp, tiles, _lib.EPI_BF16, bias=bi, groups=G, g_w_row=lv.g_w_row,
+                                      g_bias=2 * cp, dilation=1, dilation_shl_group=1, name=f"{p}lvl{s_}.ur"))
+                b.lvl_T.append(pack_wavenet_level_dgrad(convs, ress, cp, name=f"{p}lvl{s_}^T"))
+            lastb = [f"{p}stacks.{S - 1}.blocks.{g}." for g in range(G)]
+            skips = [w(k + "skip_conv.weight") for k in lastb]
+            b.skip = pack_skip_sum(skips, [w(k + "skip_conv.bias") for k in lastb], cp, name=p + "skip")
+            WsT = torch.zeros(G * cp, cp, device=dev)
+            for g in range(G):
+                WsT[g * cp:g * cp + cout, :cout] = skips[g].reshape(cout, cout).t()
+            b.skip_T = pack_linear(WsT, None, k_pad=cp, n_pad=G * cp, name=p + "skip^T")
+            b.final = pack_linear(w(p + "final_conv.weight"), w(p + "final_conv.bias"), epi=_lib.EPI_F32 if last else _lib.EPI_BF16,
+                                  k_pad=cp, n_pad=cout if last else cp, name=p + "final")
+            b.final_T = pack_linear(w(p + "final_conv.weight").reshape(cout, cout).t(), None, k_pad=rup(cout, 64) if last else cp,
+                                    n_pad=cp, name=p + "final^T")
+            self.blocks.append(b)
+            cin_pad = cp
+        D, ip = self.D, self.ip
+        self.layers = []
+        for l in range(c.vae_depth):
+            p = f"decoder_tf.layers.{l}."
+            L = _Plans()
+            wqkv = torch.cat([w(p + "1.to_q.weight"), w(p + "1.to_kv.weight")], 0)
+            L.qkv, L.qkv_T = pack_linear(wqkv, None, name=p + "qkv"), pack_linear(wqkv.t(), None, name=p + "qkv^T")
+            L.out = pack_linear(w(p + "1.to_out.weight"), None, epi=_lib.EPI_RESID, name=p + "to_out")
+            L.out_T = pack_linear(w(p + "1.to_out.weight").t(), None, name=p + "to_out^T")
+            g = pack_geglu(w(p + "5.0.weight"), w(p + "5.0.bias"))
+            L.ff1 = GemmPlan(g.W, g.segs, 2 * ip, g.n_tiles, _lib.EPI_BF16, bias=g.bias, name=p + "ff.h")
+            L.ff1_T = GemmPlan(g.W.t().contiguous(), [(0, 0, 2 * ip // BK, 0, 0)], D, (D + WT - 1) // WT, _lib.EPI_BF16, name=p + "ff.h^T")
+            wc = w(p + "5.2.1.weight")
+            L.ffc = pack_conv3(wc, w(p + "5.2.1.bias"), cin_pad=ip, n_pad=ip, name=p + "ff.conv")
+            L.ffc_T = pack_conv3(wc.permute(1, 0, 2), None, cin_pad=ip, n_pad=ip, shift_sign=-1, name=p + "ff.conv^T")
+            L.ff3 = pack_linear(w(p + "5.3.weight"), w(p + "5.3.bias"), epi=_lib.EPI_RESID, k_pad=ip, name=p + "ff.out")
+            L.ff3_T = pack_linear(w(p + "5.3.weight").t(), None, k_pad=D, n_pad=ip, name=p + "ff.out^T")
+            L.g1, L.g2 = w(p + "0.gamma").contiguous(), w(p + "4.gamma").contiguous()
+            self.layers.append(L)
+        self.pred_gamma = w("decoder_tf.to_pred.0.gamma").contiguous()
+        self.pred = pack_linear(w("decoder_tf.to_pred.1.weight"), None, epi=_lib.EPI_F32, name="vae.to_pred")
+        self.pred_T = pack_linear(w("decoder_tf.to_pred.1.weight").t(), None, name="vae.to_pred^T")
+        self.lm = pack_linear(w("decoder_lm.weight"), w("decoder_lm.bias"), epi=_lib.EPI_F32, n_pad=rup(c.vocab, 16), name="vae.lm")
+        self.lm_T = pack_linear(w("decoder_lm.weight").t(), None, epi=_lib.EPI_F32, k_pad=self.vl, n_pad=D, name="vae.lm^T")
+        self.sv: Dict[object, object] = {}
+
+    def forward(self, xb, lens, B, T):
+        """xb bf16 [B*T, zp] -> (recon fp32 [B*T, 768], logits fp32 [B*T, vp]); keeps activations for backward()."""
+        c, buf, G, S = self.cfg, self.buf, self.G, self.S
+        M, D, H, dh, ip = B * T, self.D, self.H, self.dh, self.ip
+        sv = self.sv = {}
+        a = xb
+        for i, b in enumerate(self.blocks):
+            cp = b.cp
+            h = b.init.run(a, buf(f"v.h{i}", M, cp), B, T)
+            src, g_a_col = h, 0
+            for s_ in range(S):
+                ur = b.lvl[s_].run(src, buf(f"v.ur{i}.{s_}", M, G * 2 * cp), B, T, g_a_col=g_a_col, g_out_col=2 * cp)
+                y = ops.wn_gate_fwd(ur, buf(f"v.y{i}.{s_}", M, G * cp), B, T, cp, G)
+                sv[("ur", i, s_)] = ur
+                src, g_a_col = y, cp
+            sk = b.skip.run(src, buf(f"v.sk{i}", M, cp), B, T)
+            out = buf("v.x", M, D, f32) if b.last else buf(f"v.o{i}", M, cp)
+            a = b.final.run(sk, out, B, T)
+        x = a
+        for l, L in enumerate(self.layers):
+            xs1 = buf(f"v.xs1.{l}", M, D, f32)
+            xs1.copy_(x)
+            hb1 = ops.adarmsnorm(x, buf(f"v.hb1.{l}", M, D), B, T, L.g1)
+            qkv = L.qkv.run(hb1, buf(f"v.qkv.{l}", M, 3 * H * dh), B, T)
+            lse = buf(f"v.lse.{l}", B * H, T, f32)
+            ao = ops.attention_train(qkv, buf(f"v.ao.{l}", M, H * dh), lse, lens, None, 1.0, B, T, H, dh)
+            L.out.run(ao, x, B, T)
+            xs2 = buf(f"v.xs2.{l}", M, D, f32)
+            xs2.copy_(x)
+            hb2 = ops.adarmsnorm(x, buf(f"v.hb2.{l}", M, D), B, T, L.g2)
+            hh = L.ff1.run(hb2, buf(f"v.h.{l}", M, 2 * ip), B, T)
+            m1 = ops.geglu_fwd(hh, buf(f"v.m1.{l}", M, ip))
+            m2 = L.ffc.run(m1, buf(f"v.m2.{l}", M, ip), B, T)
+            L.ff3.run(m2, x, B, T)
+            sv[l] = (xs1, qkv, lse, ao, xs2, hh)
+        hbf = ops.adarmsnorm(x, buf("v.hbf", M, D), B, T, self.pred_gamma)
+        recon = self.pred.run(hbf, buf("v.recon", M, D, f32), B, T)
+        rb = ops.cast_pad_bf16(recon, D, out=buf("v.rb", M, D))
+        logits = self.lm.run(rb, buf("v.logits", M, rup(c.vocab, 16), f32), B, T)
+        sv["x"] = x
+        return recon, logits
+
+    def backward(self, dlogits, recon, audio, lens, stats, mse_scale: float, B, T):
+        """dlogits bf16 [B*T, vl] (+ the masked-MSE term built here) -> d x1_hat bf16 [B*T, zp]."""
+        buf, G, S, sv = self.buf, self.G, self.S, self.sv
+        M, D, H, dh, ip = B * T, self.D, self.H, self.dh, self.ip
+        d_lm = self.lm_T.run(dlogits, buf("v.dlm", M, D, f32), B, T)
+        drec = ops.recon_grad(recon, audio, d_lm, lens, B, T, stats, mse_scale, buf("v.drec", M, D))
+        dhb = self.pred_T.run(drec, buf("v.dhb", M, D), B, T)
+        dx = buf("v.dx", M, D, f32, zero=True)
+        dxb = buf("v.dxb", M, D)
+        ops.adarmsnorm_bwd(sv["x"], dhb, dx, dxb, B, T, gamma_p=self.pred_gamma)
+        for l in reversed(range(len(self.layers))):
+            L = self.layers[l]
+            xs1, qkv, lse, ao, xs2, hh = sv[l]
+            dm2 = L.ff3_T.run(dxb, buf("v.dm2", M, ip), B, T)
+            dm1 = L.ffc_T.run(dm2, buf("v.dm1", M, ip), B, T)
+            dh_ = ops.geglu_bwd(hh, dm1, buf("v.dh", M, 2 * ip))
+            dhb = L.ff1_T.run(dh_, buf("v.dhb", M, D), B, T)
+            ops.adarmsnorm_bwd(xs2, dhb, dx, dxb, B, T, gamma_p=L.g2)
+            dao = L.out_T.run(dxb, buf("v.dao", M, H * dh), B, T)
+            dqkv = ops.attention_bwd(qkv, ao, dao, lse, lens, None, 1.0, buf("v.dqkv", M, 3 * H * dh), buf("v.delta", B * H, T, f32),
+                                     B, T, H, dh)
+            dhb = L.qkv_T.run(dqkv, buf("v.dhb", M, D), B, T)
+            ops.adarmsnorm_bwd(xs1, dhb, dx, dxb, B, T, gamma_p=L.g1)
+        dcur = dxb
+        for i in reversed(range(len(self.blocks))):
+            b = self.blocks[i]
+            cp = b.cp
+            dsk = b.final_T.run(dcur, buf(f"v.dsk{i}", M, cp), B, T)
+            dy = b.skip_T.run(dsk, buf(f"v.dyA{i}", M, G * cp), B, T)
+            for s_ in reversed(range(S)):
+                dur = ops.wn_gate_bwd(sv[("ur", i, s_)], dy, buf(f"v.dur{i}", M, G * 2 * cp), B, T, cp, G)
+                if s_ > 0:
+                    dy = b.lvl_T[s_].run(dur, buf(f"v.dyB{i}", M, G * cp), B, T, g_a_col=2 * cp, g_out_col=cp)
+                else:
+                    d32 = buf(f"v.dh32.{i}", M, cp, f32, zero=True)
+                    b.lvl_T[0].run(dur, d32, B, T, g_a_col=2 * cp, g_out_col=0, epi=_lib.EPI_RESID)
+                    dh0 = ops.cast_pad_bf16(d32, cp, out=buf(f"v.dh0.{i}", M, cp))
+            dcur = b.init_T.run(dh0, buf(f"v.din{i}", M, b.cin_pad), B, T)
+        return dcur
+
+
 class DenoiserTrainer:
     def __init__(self, ldm, drop_p: float = 0.1, seed: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("DenoiserTrainer needs a CUDA device: the product has no CPU path")
-        if getattr(ldm, "multitask", False):
-            raise NotImplementedError("multitask=True back-propagates through decode_feature (LM:1572-1604); only the "
-                                      "latent-noise loss (multitask=False, BASELINE config 5) is built")
+        self.multitask = bool(getattr(ldm, "multitask", False))   # LM:1600-1604: + (50 mse + nll) / T through decode_feature
         self.ldm = ldm
         self.cfg: DiffNormConfig = ldm.cfg
         self.P: Dict[str, torch.nn.Parameter] = dict(ldm.model.named_parameters())
@@ -96,6 +256,7 @@ class DenoiserTrainer:
         self._pack_graph = None
         self._pack_plans = None
         self._pack_ptrs = None
+        self.dec = FrozenDecoderTrain(sd, self.cfg, self.dev, self.buf) if self.multitask else None
 
     # ------------------------------------------------------------------------------------------------ helpers
     def buf(self, name: str, rows: int, width: int, dtype=bf16, zero: bool = False) -> torch.Tensor:
@@ -291,18 +452,34 @@ class DenoiserTrainer:
         # ---- losses (LM:1563-1611)
         loss = torch.zeros(1, dtype=f32, device=dev)
         dpred = self.buf("dpred", M, zp) if backward else None
-        ops.noise_loss(eh, eps, lens, self.coef, t_idx, B, T, z, loss, dpred, grad_scale)
-        out = {"noise_loss": loss[0], "total_loss": loss[0]}
-        if decode_losses and units is not None:
+        out = {}
+        dx1 = None
+        need_decode = (decode_losses or self.multitask) and units is not None
+        if self.multitask and units is None:
+            raise ValueError("multitask training needs the target units (LM:1583-1597)")
+        if need_decode:
             xb1 = ops.pred_x1(x_t, eh, self.coef, t_idx, B, T, z, self.buf("xb1", M, zp))
-            recon, logits = self.vae.decode(xb1, lens, B, T)
-            st = ops.decode_losses(recon.contiguous().view(M, -1), audio.float().contiguous().view(M, -1),
-                                   logits.contiguous().view(M, -1), c.vocab, units.to(dev).to(i64).contiguous().view(-1), lens, B, T)
+            audio_f = audio.float().contiguous().view(M, -1)
+            units_f = units.to(dev).to(i64).contiguous().view(-1)
+            if self.multitask:
+                recon, logits = self.dec.forward(xb1, lens, B, T)
+            else:
+                recon, logits = self.vae.decode(xb1, lens, B, T)
+                recon, logits = recon.contiguous().view(M, -1), logits.contiguous().view(M, -1)
+            st = ops.decode_losses(recon, audio_f, logits, c.vocab, units_f, lens, B, T)
             e_i = 0.1 / (c.vocab - 1)
             ntok = st[4].clamp(min=1)
             out["recon_mse_loss"] = (st[0] / (st[5].clamp(min=1) * c.feat_dim)).float()
             out["nll_loss"] = (((1.0 - 0.1 - e_i) * st[1] + e_i * st[2]) / ntok).float()
             out["acc"] = (st[3] / ntok).float()
+            if self.multitask and backward:
+                dlogits = ops.lsnll_bwd(logits, c.vocab, units_f, st, 0.1, grad_scale / c.timesteps, self.buf("v.dlogits", M, self.dec.vl))
+                dx1 = self.dec.backward(dlogits, recon, audio_f, lens, st, 50.0 * grad_scale / c.timesteps, B, T)
+        ops.noise_loss(eh, eps, lens, self.coef, t_idx, B, T, z, loss, dpred, grad_scale, dx1)
+        out["noise_loss"] = loss[0]
+        out["total_loss"] = loss[0]
+        if self.multitask and need_decode:
+            out["total_loss"] = loss[0] + (50.0 * out["recon_mse_loss"] + out["nll_loss"]) / c.timesteps
         out["pred_noise"] = eh.view(B, T, zn)[..., :z]
         if not backward:
             return out, {}

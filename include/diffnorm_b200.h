@@ -237,10 +237,11 @@ int dn_train_noise(const float* z_lat, const float* eps0, const float* eps, floa
                    const int32_t* t_idx, int32_t B, int32_t T, int32_t z, float* x_t, void* x_bf16, int32_t ldx,
                    void* stream);
 /* loss[0] += mean_b( w_b mean_{T,z}( mask (pred - eps)^2 ) ) (LM:1563-1569); dpred bf16 [B*T, ldd] = grad_scale *
- * d loss / d pred (zero on padded frames and pad columns; may be null). */
+ * d loss / d pred (zero on padded frames and pad columns; may be null).  dx1 (bf16 [B*T, ld1], optional) = gradient
+ * w.r.t. x1_hat from the decode branch (multitask): adds -s1 / max(sa, 1e-10) * dx1 on valid frames (LM:1572). */
 int dn_noise_loss(const float* pred, int32_t lde, const float* eps, const int32_t* lengths, const float* coef,
                   const int32_t* t_idx, int32_t B, int32_t T, int32_t z, float* loss, void* dpred, int32_t ldd,
-                  float grad_scale, void* stream);
+                  float grad_scale, const void* dx1, int32_t ld1, void* stream);
 /* x1_hat = (x_t - s1 pred) / max(sa, 1e-10) as the bf16 staging input of decode_feature (LM:1572). */
 int dn_pred_x1(const float* x_t, const float* pred, int32_t lde, const float* coef, const int32_t* t_idx, int32_t B,
                int32_t T, int32_t z, void* x_bf16, int32_t ldx, void* stream);
@@ -250,14 +251,23 @@ int dn_pred_x1(const float* x_t, const float* pred, int32_t lde, const float* co
 int dn_decode_losses(const float* recon, const float* audio, int32_t C, const float* logits, int32_t ld, int32_t V,
                      const int64_t* units, const int32_t* lengths, int32_t B, int32_t T, double* out6, void* stream);
 
+/* Backward of the decode branch's losses (multitask, LM:1576-1604); stats = out6 of dn_decode_losses (device).
+ * dlogits bf16 [rows, ldd] = nll_scale / n_tokens * d(label-smoothed NLL, eps_ls) / d logits (0 on rows with unit 0 and on
+ * pad columns); dn_recon_grad: out bf16 [B*T, C] = d_lm + mse_scale * d(masked MSE) / d recon. */
+int dn_lsnll_bwd(const float* logits, int32_t ld, int32_t V, const int64_t* units, int64_t rows, const double* stats,
+                 float eps_ls, float nll_scale, void* dlogits, int32_t ldd, void* stream);
+int dn_recon_grad(const float* recon, const float* audio, const float* d_lm, const int32_t* lengths, int32_t B, int32_t T,
+                  int32_t C, const double* stats, float mse_scale, void* out, void* stream);
+
 /* Attention-dropout keep bits (LM:338): n_words uint32, each bit kept with probability 1-p (Philox4x32-10). */
 int dn_dropout_bits(uint32_t* bits, int64_t n_words, float p, uint64_t seed, uint64_t offset, void* stream);
 
-/* dn_attention with dropout and the saved row statistic L2 = m + log2(l) (fp32 [B, H, T]); dh = 64.
+/* dn_attention with dropout and the saved row statistic L2 = m + log2(l) (fp32 [B, H, T]); dh = 64, or dh = 96
+ * without dropout (the frozen VAE decoder inside a multitask training step).
  * keep_bits [B, H, T, ceil(T/32)] (bit k%32 of word k/32 = key k kept) or null; keep_scale = 1/(1-p). */
 int dn_attention_train(const void* qkv, void* out, float* lse2, const int32_t* lengths, const uint32_t* keep_bits,
                        float keep_scale, int32_t B, int32_t T, int32_t H, int32_t dh, void* stream);
-/* Backward of dn_attention_train: dqkv bf16 [B, T, 3*H*dh] (fully written); delta_ws fp32 [B, H, T] workspace. */
+/* Backward of dn_attention_train (dh = 64 | 96): dqkv bf16 [B, T, 3*H*dh] (fully written); delta_ws fp32 [B, H, T]. */
 int dn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, const int32_t* lengths,
                      const uint32_t* keep_bits, float keep_scale, void* dqkv, float* delta_ws, int32_t B, int32_t T,
                      int32_t H, int32_t dh, void* stream);

@@ -176,33 +176,37 @@ def test_attention_train_forward_backward(T, lens, drop, dh):
     assert e_out < 1.5e-2 and e_lse < 2e-2 and max(errs) < 2.5e-2
 
 
-def _build(z, wseed):
+def _build(z, wseed, multitask=False):
     from diffnorm_b200.plugin.latent_module import LatentDiscreteModel, SpeechVAEEncoderDecoder
     arch = O.Arch(latent_dim=z)
     sd = O.init_state_dict(arch, seed=wseed, gains=O.PARITY_GAINS)
     vae = types.SimpleNamespace(encoder=SpeechVAEEncoderDecoder(768, z))
-    ldm = LatentDiscreteModel(vae, 512, z, timesteps=200, multitask=False)
+    ldm = LatentDiscreteModel(vae, 512, z, timesteps=200, multitask=multitask)
     ldm.load_state_dict(sd, strict=True)
     return arch, sd, ldm.to(DEV)
 
 
-@pytest.mark.parametrize("drop_p", [0.1, 0.0])
-def test_train_step_against_oracle_autograd(drop_p):
-    """Whole step (forward losses + every parameter gradient) vs the oracle's autograd on the same replayed draws."""
+@pytest.mark.parametrize("drop_p,multitask,extreme_t", [(0.1, False, False), (0.0, False, False), (0.0, True, True),
+                                                        (0.1, True, True), (0.1, True, False)])
+def test_train_step_against_oracle_autograd(drop_p, multitask, extreme_t):
+    """Whole step (forward losses + every parameter gradient) vs the oracle's autograd on the same replayed draws;
+    multitask adds (50 mse + nll) / T back-propagated through the frozen VAE decoder (LM:1572-1604)."""
     z, wseed, B, T, lengths, times, dseed = 16, 3, 2, 24, [24, 17], [37, 142], 21
-    arch, sd, ldm = _build(z, wseed)
+    if extreme_t:
+        times, dseed = [5, 199], 22          # the case pinned in tests/golden/train_z16_nodrop_multitask.npz
+    arch, sd, ldm = _build(z, wseed, multitask)
     audio, units, mask, eps_vae, eps0, eps, keeps = O.train_case_inputs(z, B, T, lengths, dseed, drop_p)
     train_keys = [k for k in sd if k.startswith("model.") and sd[k].is_floating_point() and "pos_embed" not in k]
     for k in train_keys:
         sd[k].requires_grad_(True)
-    ref = O.train_loss(sd, arch, audio, units, mask, torch.tensor(times), eps_vae, eps0, eps, keeps, drop_p, False)
+    ref = O.train_loss(sd, arch, audio, units, mask, torch.tensor(times), eps_vae, eps0, eps, keeps, drop_p, multitask)
     ref["total_loss"].backward()
     tr = DenoiserTrainer(ldm, drop_p=drop_p)
     bits = [pack_keep_bits(k).to(DEV) for k in keeps] if keeps is not None else None
     out, grads = tr.step(audio.to(DEV), units.to(DEV), torch.tensor(lengths, dtype=i32, device=DEV),
                          times=torch.tensor(times), noise={"vae": eps_vae, "eps0": eps0, "eps": eps}, keep_bits=bits)
     torch.cuda.synchronize()
-    for k in ("noise_loss", "recon_mse_loss", "nll_loss"):
+    for k in ("noise_loss", "recon_mse_loss", "nll_loss", "total_loss"):
         a, b = float(out[k]), float(ref[k])
         print(f"[parity] train {k}: cuda {a:.6f} oracle {b:.6f}")
         assert abs(a - b) <= 2e-2 * abs(b) + 1e-4
@@ -218,10 +222,13 @@ def test_train_step_against_oracle_autograd(drop_p):
         tot_den += float(gr.double().pow(2).sum())
         if e > worst[1]:
             worst = (k, e)
-        assert e < 0.12, (k, e, float(gr.norm()))
-    print(f"[parity] train grads (drop_p={drop_p}): global rel err {np.sqrt(tot_num / tot_den):.3e}, worst {worst}, "
+        # softmax-gradient cancellation (dP - D) makes the to_q / to_kv gradients the noisiest under bf16 operands
+        assert e < (0.25 if (".1.to_" in k or extreme_t) else 0.12), (k, e, float(gr.norm()))
+    print(f"[parity] train grads (drop_p={drop_p}, multitask={multitask}): t={times}: global rel err {np.sqrt(tot_num / tot_den):.3e}, worst {worst}, "
           f"pred_noise rel err {e_pred:.2e}")
-    assert np.sqrt(tot_num / tot_den) < 4e-2
+    # extreme_t case: utterance 1 sits at t = 199 where x1_hat = (x_t - s1 pred) / sqrt(ab) is scaled by 1/2.5e-4, so the
+    # decode branch runs on inputs of magnitude ~1e3 and its gradient (x -s1/sa) dominates: the worst-conditioned step there is
+    assert np.sqrt(tot_num / tot_den) < (8e-2 if extreme_t else 4e-2)
 
 
 def test_plugin_forward_backward_through_autograd():
