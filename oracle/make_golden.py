@@ -233,6 +233,53 @@ def make_train(name):
           "params with grad", len(names))
 
 
+VAE_TRAIN_CASES = {
+    # name -> (latent_dim, weight seed, B, T, lengths, data seed, dropout p)
+    "vae_train_z16": (16, 4, 2, 24, [24, 15], 31, 0.1),
+}
+
+
+def make_vae_train(name):
+    """SpeechVAEEncoderDecoder.forward in train mode (LM:1118-1142) + the loss arithmetic of
+    speech_vae_decoder_loss.py:60-82 (restated here in 6 lines: that file imports fairseq at module top), backward."""
+    z, wseed, B, T, lengths, dseed, drop_p = VAE_TRAIN_CASES[name]
+    arch = O.Arch(latent_dim=z)
+    sd = O.init_state_dict(arch, seed=wseed, gains=O.PARITY_GAINS)
+    ldm = ref_loader.build_reference_model(z)
+    ldm.load_state_dict(sd)
+    vae = ldm.speech_decoder
+    vae.train()
+    audio, units, mask, eps_vae, _, _, keeps = O.train_case_inputs(z, B, T, lengths, dseed, drop_p, depth=arch.vae_depth)
+    rt = ReplayTraining(None, eps_vae, None, None, keeps, drop_p)
+    rt.like_q = []
+    with rt:
+        mse_loss, lm_pred, kl_loss = vae(audio.clone(), units.clone(), mask)
+    assert rt.drop_used == arch.vae_depth and not rt.randn_q
+    lprobs = torch.log_softmax(lm_pred, dim=-1).view(-1, lm_pred.size(-1))
+    target = units.view(-1)
+    tmask = target.ne(0)
+    acc = (lprobs.argmax(1)[tmask] == target[tmask]).sum() / tmask.sum()
+    from fairseq.criterions.label_smoothed_cross_entropy import label_smoothed_nll_loss   # the stub of ref_loader (:34-51)
+    ls, nll = label_smoothed_nll_loss(lprobs, target, 0.1, ignore_index=0, reduce=True)
+    ntokens = int(tmask.sum())
+    loss = 0.1 * (ls / ntokens) + 10 * mse_loss + 0.0001 * kl_loss
+    loss.backward()
+    store = dict(latent_dim=z, weight_seed=wseed, lengths=np.array(lengths), data_seed=dseed, drop_p=drop_p, T=T, ntokens=ntokens)
+    for k, v in (("loss", loss), ("nll_loss", nll / ntokens), ("mse_loss", mse_loss), ("kl_loss", kl_loss), ("acc", acc)):
+        store[k] = np.float64(v.detach().double().item())
+    names, norms, samples = [], [], []
+    for n_, p_ in vae.named_parameters():
+        if p_.grad is None:
+            continue
+        gflat = p_.grad.detach().double().flatten()
+        names.append("speech_decoder." + n_)
+        norms.append(float(gflat.norm()))
+        samples.append(gflat[torch.from_numpy(grad_probe("speech_decoder." + n_, gflat.numel()))].numpy())
+    store["grad_names"], store["grad_norms"], store["grad_samples"] = np.array(names), np.array(norms), np.stack(samples)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **store)
+    print(name, {k: float(store[k]) for k in ("loss", "nll_loss", "mse_loss", "kl_loss", "acc")}, "params with grad", len(names))
+
+
 def make_schedule(ldm):
     s = ldm.scheduler
     np.savez_compressed(
@@ -315,6 +362,10 @@ def main():
         for name in TRAIN_CASES:
             make_train(name)
         return
+    if "--vae-train-only" in sys.argv:
+        for name in VAE_TRAIN_CASES:
+            make_vae_train(name)
+        return
     make_batcher()
     make_reduce()
     for name in PASS_CASES:
@@ -324,6 +375,8 @@ def main():
             make_schedule(ldm)
     for name in TRAIN_CASES:
         make_train(name)
+    for name in VAE_TRAIN_CASES:
+        make_vae_train(name)
 
 
 if __name__ == "__main__":

@@ -164,3 +164,28 @@ def test_oracle_train_loss_and_grads_match_reference(name):
         if key.startswith("full:"):
             np.testing.assert_allclose(sd[key[5:]].grad.numpy(), g[key], rtol=2e-3, atol=1e-6 * float(np.abs(g[key]).max()) + 1e-9)
     print(f"[parity] {name}: oracle autograd vs reference autograd, worst sampled-gradient error {worst:.2e}")
+
+
+def test_oracle_vae_train_loss_and_grads_match_reference():
+    """VAE training: SpeechVAEEncoderDecoder.forward + speech_vae_decoder_loss of the live reference in train
+    mode (posterior draw and the 6 attention-dropout masks replayed) vs the oracle under autograd."""
+    g = np.load(os.path.join(GOLD, "vae_train_z16.npz"), allow_pickle=False)
+    z, T = int(g["latent_dim"]), int(g["T"])
+    lengths, drop_p = g["lengths"].tolist(), float(g["drop_p"])
+    arch = O.Arch(latent_dim=z)
+    sd = O.init_state_dict(arch, seed=int(g["weight_seed"]), gains=O.PARITY_GAINS)
+    keys = [str(n) for n in g["grad_names"]]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    audio, units, mask, eps_vae, _, _, keeps = O.train_case_inputs(z, len(lengths), T, lengths, int(g["data_seed"]), drop_p,
+                                                                   depth=arch.vae_depth)
+    out = O.vae_train_loss(sd, arch, audio, units, mask, eps_vae, keeps, drop_p, int(g["ntokens"]))
+    for k in ("loss", "nll_loss", "mse_loss", "kl_loss", "acc"):
+        assert abs(float(out[k].detach()) - float(g[k])) <= 2e-5 * max(1.0, abs(float(g[k]))), (k, float(out[k].detach()), float(g[k]))
+    out["loss"].backward()
+    assert sorted(keys) == sorted(k for k in sd if k.startswith("speech_decoder.") and sd[k].is_floating_point())
+    for n, norm, samp in zip(keys, g["grad_norms"], g["grad_samples"]):
+        gr = sd[n].grad.double().flatten()
+        assert abs(float(gr.norm()) - norm) <= 1e-3 * norm + 1e-9, (n, float(gr.norm()), norm)
+        got = gr[torch.from_numpy(O.grad_probe(n, gr.numel()))].numpy()
+        assert np.abs(got - samp).max() / (np.abs(samp).max() + norm / np.sqrt(gr.numel()) + 1e-12) <= 5e-3, n
