@@ -90,6 +90,8 @@ _SIGS = {
     "dn_adarmsnorm_bwd": [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, i32, vp, i64, vp],
     "dn_train_noise": [vp, vp, vp, f32, vp, vp, i32, i32, i32, vp, vp, i32, vp],
     "dn_noise_loss": [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, f32, vp, i32, vp],
+    "dn_vae_kl": [vp, i32, vp, i32, i32, i32, vp, vp],
+    "dn_vae_reparam_bwd": [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, f32, vp, i32, vp],
     "dn_lsnll_bwd": [vp, i32, i32, vp, i64, vp, f32, f32, vp, i32, vp],
     "dn_recon_grad": [vp, vp, vp, vp, i32, i32, i32, vp, f32, vp, vp],
     "dn_pred_x1": [vp, vp, i32, vp, vp, i32, i32, i32, vp, i32, vp],

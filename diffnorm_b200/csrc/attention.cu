@@ -40,7 +40,8 @@ constexpr int ATT_BM = 64, ATT_BN = 64, ATT_THREADS = 128;
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                 const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2) {
+                 const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2,
+                 const uint32_t* __restrict__ keep, float keep_scale) {
     constexpr int LDS = DH + 8;       // padded smem row (elements): conflict-free ldmatrix
     constexpr int CH = DH / 8;        // 16-byte chunks per row
     constexpr int KS = DH / 16;       // k-steps over the head dim
@@ -144,12 +145,33 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
         m1 = mn1;
         float rs0 = 0.f, rs1 = 0.f;
         uint32_t pf[4][4];  // P as A fragments for the 4 k16 steps over the 64 keys
+        // attention dropout (training form): keep words of this thread's two query rows for the 64 keys of the block
+        uint32_t kw0[2] = {0xffffffffu, 0xffffffffu}, kw1[2] = {0xffffffffu, 0xffffffffu};
+        if (keep) {
+            const int Tw = (T + 31) >> 5;
+            const int ra = q0 + warp * 16 + (lane >> 2), rb = ra + 8;
+            const uint32_t* k0p = keep + (((long long)b * H + h) * T + (ra < T ? ra : T - 1)) * Tw;
+            const uint32_t* k1p = keep + (((long long)b * H + h) * T + (rb < T ? rb : T - 1)) * Tw;
+            const int wi = (kb * ATT_BN) >> 5;
+            kw0[0] = wi < Tw ? k0p[wi] : 0u;
+            kw0[1] = wi + 1 < Tw ? k0p[wi + 1] : 0u;
+            kw1[0] = wi < Tw ? k1p[wi] : 0u;
+            kw1[1] = wi + 1 < Tw ? k1p[wi + 1] : 0u;
+        }
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-            const float p0 = exp2f(s[nb][0] - mn0), p1 = exp2f(s[nb][1] - mn0);
-            const float p2 = exp2f(s[nb][2] - mn1), p3 = exp2f(s[nb][3] - mn1);
+            float p0 = exp2f(s[nb][0] - mn0), p1 = exp2f(s[nb][1] - mn0);
+            float p2 = exp2f(s[nb][2] - mn1), p3 = exp2f(s[nb][3] - mn1);
             rs0 += p0 + p1;
             rs1 += p2 + p3;
+            if (keep) {   // dropout acts on the normalised probabilities: the row sums above stay un-dropped
+                const int kk = nb * 8 + (lane & 3) * 2;   // key offset inside the block
+                const uint32_t wa = kw0[kk >> 5], wb = kw1[kk >> 5];
+                p0 = ((wa >> (kk & 31)) & 1u) ? p0 * keep_scale : 0.f;
+                p1 = ((wa >> ((kk + 1) & 31)) & 1u) ? p1 * keep_scale : 0.f;
+                p2 = ((wb >> (kk & 31)) & 1u) ? p2 * keep_scale : 0.f;
+                p3 = ((wb >> ((kk + 1) & 31)) & 1u) ? p3 * keep_scale : 0.f;
+            }
             pf[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(p0, p1);
             pf[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(p2, p3);
         }
@@ -199,7 +221,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
 template <int DH>
 static int launch_attention(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
-                            float* lse2 = nullptr) {
+                            float* lse2 = nullptr, const uint32_t* keep = nullptr, float keep_scale = 1.f) {
     constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * (DH + 8) * 2;
     static bool attr_set = false;
     if (!attr_set) {
@@ -210,7 +232,7 @@ static int launch_attention(const void* qkv, void* out, const int32_t* lengths, 
     const float scale_log2 = (1.0f / sqrtf((float)DH)) * 1.4426950408889634f;
     attention_kernel<DH><<<grid, ATT_THREADS, SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                          reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H, scale_log2,
-                                                         lse2);
+                                                         lse2, keep, keep_scale);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -242,10 +264,9 @@ extern "C" int dn_attention_train(const void* qkv, void* out, float* lse2, const
                                   float keep_scale, int32_t B, int32_t T, int32_t H, int32_t dh, void* stream) {
     if (!qkv || !out || !lse2 || B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535) return DN_EINVAL;
     if (reinterpret_cast<uintptr_t>(qkv) & 15) return DN_EINVAL;
-    if (dh == 96) {   // frozen VAE decoder (eval mode inside the training step: no dropout, LM:1520)
-        if (keep_bits) return DN_EINVAL;
-        return dn::launch_attention<96>(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2);
-    }
+    if (dh == 96)   // VAE decoder: frozen / eval inside a diffusion step (no dropout), train mode in VAE training
+        return dn::launch_attention<96>(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
+                                        keep_scale);
     if (dh != 64) return DN_EINVAL;
     return dn::launch_attention_tc(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
                                    keep_scale, true);

@@ -513,6 +513,58 @@ recon_grad_kernel(const float* __restrict__ recon, const float* __restrict__ aud
     }
 }
 
+// ---------------------------------------------------------------------------------------------- VAE posterior (training)
+// kl[0] += mean_b( 0.5 * mean_{z,T}( mask * (mu^2 + exp(lv) - 1 - lv) ) ),  lv = clamp(logvar, -30, 20)
+// (distributions.py:62-74 kl_3d + LM:1127-1128).  params fp32 [B*T, ldp]: mu in [0,z), logvar in [z,2z).
+__global__ void __launch_bounds__(TR_THREADS)
+vae_kl_kernel(const float* __restrict__ params, int ldp, const int* __restrict__ lengths, int B, int T, int z,
+              float* __restrict__ kl) {
+    __shared__ float red[TR_THREADS / 32];
+    const long long total = (long long)B * T * z;
+    float acc = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % z);
+        const long long r = i / z;
+        if ((int)(r % T) < lengths[r / T]) {
+            const float mu = params[r * ldp + c];
+            const float lv = fminf(fmaxf(params[r * ldp + z + c], -30.f), 20.f);
+            acc += mu * mu + expf(lv) - 1.f - lv;
+        }
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(kl, acc * 0.5f / ((float)B * (float)T * (float)z));
+}
+
+// backward of z = mu + exp(0.5 lv) eps and of the KL term: dparams bf16 [B*T, ldd] (pad columns zero).
+// dz bf16 [B*T, ldz] (gradient w.r.t. the latent, channel-last); eps channel-first [B, z, T] or channel-last.
+__global__ void __launch_bounds__(TR_THREADS)
+vae_reparam_bwd_kernel(const float* __restrict__ params, int ldp, const float* __restrict__ eps, int eps_cf,
+                       const __nv_bfloat16* __restrict__ dz, int ldz, const int* __restrict__ lengths, int B, int T, int z,
+                       float kl_scale, __nv_bfloat16* __restrict__ dparams, int ldd) {
+    const long long total = (long long)B * T * ldd;
+    const float ks = kl_scale * 0.5f / ((float)B * (float)T * (float)z);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % ldd);
+        const long long r = i / ldd;
+        float g = 0.f;
+        if (col < 2 * z) {
+            const int c = col < z ? col : col - z;
+            const int b = (int)(r / T), t = (int)(r % T);
+            const float d = __bfloat162float(dz[r * ldz + c]);
+            const float valid = t < lengths[b] ? 1.f : 0.f;
+            const float mu = params[r * ldp + c];
+            const float lvr = params[r * ldp + z + c];
+            if (col < z) {
+                g = d + ks * valid * 2.f * mu;
+            } else if (lvr >= -30.f && lvr <= 20.f) {   // clamp passes the gradient only inside its range
+                const float e = eps_cf ? eps[((long long)b * z + c) * T + t] : eps[r * z + c];
+                g = d * e * 0.5f * expf(0.5f * lvr) + ks * valid * (expf(lvr) - 1.f);
+            }
+        }
+        dparams[i] = __float2bfloat16(g);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- dropout keep bits
 __global__ void dropout_bits_kernel(uint32_t* __restrict__ bits, long long n_words, float p, unsigned long long seed,
                                     unsigned long long offset) {
@@ -770,6 +822,27 @@ extern "C" int dn_decode_losses(const float* recon, const float* audio, int32_t 
     DN_CUDA_OK(cudaMemsetAsync(out6, 0, 6 * sizeof(double), ST(stream)));
     decode_losses_kernel<<<tr_grid((long long)B * T, TR_THREADS / 32), TR_THREADS, 0, ST(stream)>>>(
         recon, audio, C, logits, ld, V, (const long long*)units, lengths, B, T, out6);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_vae_kl(const float* params, int32_t ldp, const int32_t* lengths, int32_t B, int32_t T, int32_t z, float* kl,
+                         void* stream) {
+    if (!params || !lengths || !kl || B <= 0 || T <= 0 || z <= 0 || ldp < 2 * z) return DN_EINVAL;
+    vae_kl_kernel<<<tr_grid((long long)B * T * z, TR_THREADS), TR_THREADS, 0, ST(stream)>>>(params, ldp, lengths, B, T, z, kl);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_vae_reparam_bwd(const float* params, int32_t ldp, const float* eps, int32_t eps_channel_first, const void* dz,
+                                  int32_t ldz, const int32_t* lengths, int32_t B, int32_t T, int32_t z, float kl_scale,
+                                  void* dparams, int32_t ldd, void* stream) {
+    if (!params || !eps || !dz || !lengths || !dparams || B <= 0 || T <= 0 || z <= 0 || ldp < 2 * z || ldz < z || ldd < 2 * z)
+        return DN_EINVAL;
+    vae_reparam_bwd_kernel<<<tr_grid((long long)B * T * ldd, TR_THREADS), TR_THREADS, 0, ST(stream)>>>(
+        params, ldp, eps, eps_channel_first, (const bf*)dz, ldz, lengths, B, T, z, kl_scale, (bf*)dparams, ldd);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

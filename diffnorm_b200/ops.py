@@ -376,3 +376,18 @@ def add_bf16_to_f32(src, col0: int, Cc: int, dst, accumulate: bool):
     check(lib.dn_add_bf16_to_f32(_p(src), src.numel() // ld, ld, col0, Cc, _p(dst), dst.shape[-1], int(accumulate), _stream()),
           "dn_add_bf16_to_f32")
     return dst
+
+
+def vae_kl(params, lengths, z: int, kl):
+    _chk(params, f32, "params"), _chk(kl, f32, "kl")
+    B, T, ldp = params.shape
+    check(lib.dn_vae_kl(_p(params), ldp, _p(lengths), B, T, z, _p(kl), _stream()), "dn_vae_kl")
+    return kl
+
+
+def vae_reparam_bwd(params, eps, eps_channel_first: bool, dz, lengths, z: int, kl_scale: float, dparams):
+    _chk(params, f32, "params"), _chk(eps, f32, "eps"), _chk(dz, bf16, "dz"), _chk(dparams, bf16, "dparams")
+    B, T, ldp = params.shape
+    check(lib.dn_vae_reparam_bwd(_p(params), ldp, _p(eps), int(eps_channel_first), _p(dz), dz.shape[-1], _p(lengths), B, T, z,
+                                 kl_scale, _p(dparams), dparams.shape[-1], _stream()), "dn_vae_reparam_bwd")
+    return dparams

@@ -56,64 +56,171 @@ class _GradDict(dict):
             self._hook(k, v)
 
 
-class FrozenDecoderTrain:
-    """decode_feature (LM:1109-1116) of the FROZEN VAE inside a multitask training step: an un-fused forward that keeps
-    the pre-activations, and the data-gradient backward down to x1_hat (no weight gradients: diff_discrete.py:79-81
-    freezes the VAE).  Packed once; same kernels as the denoiser path (unconditioned WaveNets with 3 chains x 2 levels,
-    6-layer transformer with 8 x 96 heads and gamma-parameter RMSNorms, to_pred, decoder_lm)."""
+def _pack_vae_wavenet(w, p: str, cin: int, cout: int, cin_pad: int, G: int, S: int, last_f32: bool, dev) -> _Plans:
+    """Forward (un-fused) and data-gradient packings of one VAE WavenetEncoder block (LM:1003-1032): init conv k3
+    cin -> cout, S levels x G chains (dilation 2^g, unconditioned), skip sum, final 1x1.  Channel extents are padded to 128."""
+    cp = rup(cout, 128)
+    b = _Plans()
+    b.p, b.cin, b.cout, b.cp, b.cin_pad, b.last = p, cin, cout, cp, cin_pad, last_f32
+    b.init = pack_conv3(w(p + "init_conv.weight"), w(p + "init_conv.bias"), cin_pad=cin_pad, n_pad=cp, name=p + "init")
+    b.init_T = pack_conv3(w(p + "init_conv.weight").permute(1, 0, 2), None, cin_pad=cp, n_pad=cin_pad, shift_sign=-1, name=p + "init^T")
+    b.lvl, b.lvl_T = [], []
+    tiles = cp // 128
+    for s_ in range(S):
+        blk = [f"{p}stacks.{s_}.blocks.{g}." for g in range(G)]
+        convs, ress = [w(k + "conv.weight") for k in blk], [w(k + "res_conv.weight") for k in blk]
+        lv = pack_wavenet_level(convs, [w(k + "conv.bias") for k in blk], ress, [w(k + "res_conv.bias") for k in blk], cp)
+        bi = torch.stack([lv.bias.view(G, tiles, 128), lv.bias2.view(G, tiles, 128)], dim=2).reshape(-1).contiguous()
+        b.lvl.append(GemmPlan(lv.W, lv.segs, 2 * cp, tiles, _lib.EPI_BF16, bias=bi, groups=G, g_w_row=lv.g_w_row,
+                              g_bias=2 * cp, dilation=1, dilation_shl_group=1, name=f"{p}lvl{s_}.ur"))
+        b.lvl_T.append(pack_wavenet_level_dgrad(convs, ress, cp, name=f"{p}lvl{s_}^T"))
+    lastb = [f"{p}stacks.{S - 1}.blocks.{g}." for g in range(G)]
+    skips = [w(k + "skip_conv.weight") for k in lastb]
+    b.skip = pack_skip_sum(skips, [w(k + "skip_conv.bias") for k in lastb], cp, name=p + "skip")
+    WsT = torch.zeros(G * cp, cp, device=dev)
+    for g in range(G):
+        WsT[g * cp:g * cp + cout, :cout] = skips[g].reshape(cout, cout).t()
+    b.skip_T = pack_linear(WsT, None, k_pad=cp, n_pad=G * cp, name=p + "skip^T")
+    b.n_final = rup(cout, 16) if last_f32 else cp
+    b.final = pack_linear(w(p + "final_conv.weight"), w(p + "final_conv.bias"), epi=_lib.EPI_F32 if last_f32 else _lib.EPI_BF16,
+                          k_pad=cp, n_pad=b.n_final, name=p + "final")
+    b.final_T = pack_linear(w(p + "final_conv.weight").reshape(cout, cout).t(), None, k_pad=rup(cout, 64) if last_f32 else cp,
+                            n_pad=cp, name=p + "final^T")
+    return b
 
-    def __init__(self, sd: Dict[str, torch.Tensor], cfg: DiffNormConfig, dev, buf):
+
+class VaeBlocksTrain:
+    """Training-mode execution of VAE WaveNet blocks (encoder or decoder side): un-fused forward keeping the pre-gate
+    pairs, data-gradient backward, and (when `grads` is given) the weight / bias gradients of every conv in the block."""
+
+    def __init__(self, buf, G: int, S: int, tag: str):
+        self.buf, self.G, self.S, self.tag = buf, G, S, tag
+        self.sv: Dict[object, object] = {}
+
+    def forward(self, blocks, a, B, T, x_out=None):
+        buf, G, S, tag = self.buf, self.G, self.S, self.tag
+        M = B * T
+        sv = self.sv = {}
+        for i, b in enumerate(blocks):
+            cp = b.cp
+            sv[("in", i)] = a
+            h = b.init.run(a, buf(f"{tag}.h{i}", M, cp), B, T)
+            sv[("h", i)] = h
+            src, g_a_col = h, 0
+            for s_ in range(S):
+                ur = b.lvl[s_].run(src, buf(f"{tag}.ur{i}.{s_}", M, G * 2 * cp), B, T, g_a_col=g_a_col, g_out_col=2 * cp)
+                y = ops.wn_gate_fwd(ur, buf(f"{tag}.y{i}.{s_}", M, G * cp), B, T, cp, G)
+                sv[("ur", i, s_)], sv[("y", i, s_)] = ur, y
+                src, g_a_col = y, cp
+            sk = b.skip.run(src, buf(f"{tag}.sk{i}", M, cp), B, T)
+            sv[("sk", i)] = sk
+            if b.last:
+                out = x_out if x_out is not None else buf(f"{tag}.out", M, b.n_final, f32)
+            else:
+                out = buf(f"{tag}.o{i}", M, cp)
+            a = b.final.run(sk, out, B, T)
+        return a
+
+    def backward(self, blocks, dcur, B, T, grads=None, first_needs_dx: bool = True):
+        """dcur bf16 [M, >= cout of the last block] = gradient of the last block's output; returns the gradient w.r.t. the
+        first block's input (bf16 [M, cin_pad]) or None when first_needs_dx is False."""
+        buf, G, S, tag, sv = self.buf, self.G, self.S, self.tag, self.sv
+        M = B * T
+        dev = dcur.device
+        zeros = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
+        for i in reversed(range(len(blocks))):
+            b = blocks[i]
+            cp, c, cin, p = b.cp, b.cout, b.cin, b.p
+            if grads is not None:
+                dWf = zeros(c, rup(cp, 4))
+                ops.wgrad(dcur, sv[("sk", i)], dWf, 1, M, c, cp)
+                grads[p + "final_conv.weight"] = dWf[:, :c].reshape(c, c, 1)
+                grads[p + "final_conv.bias"] = ops.colsum(dcur, 0, rup(c, 8), zeros(rup(c, 8)))[:c]
+            dsk = b.final_T.run(dcur, buf(f"{tag}.dsk{i}", M, cp), B, T)
+            if grads is not None:
+                dWs = zeros(cp, G * cp)
+                ops.wgrad(dsk, sv[("y", i, S - 1)], dWs, 1, M, cp, G * cp)
+                dbs = ops.colsum(dsk, 0, cp, zeros(cp))[:c]
+                for g in range(G):
+                    k_ = f"{p}stacks.{S - 1}.blocks.{g}."
+                    grads[k_ + "skip_conv.weight"] = dWs[:c, g * cp:g * cp + c].reshape(c, c, 1)
+                    grads[k_ + "skip_conv.bias"] = dbs
+            dy = b.skip_T.run(dsk, buf(f"{tag}.dyA{i}", M, G * cp), B, T)
+            for s_ in reversed(range(S)):
+                dur = ops.wn_gate_bwd(sv[("ur", i, s_)], dy, buf(f"{tag}.dur{i}", M, G * 2 * cp), B, T, cp, G)
+                if grads is not None:
+                    inp = sv[("y", i, s_ - 1)] if s_ > 0 else sv[("h", i)]
+                    gx = cp if s_ > 0 else 0
+                    tapsG = []
+                    for k in range(3):
+                        dWg = zeros(G, cp, cp)
+                        ops.wgrad(dur, inp, dWg, B, T, cp, cp, 0, 0, 2 - k, groups=G, g_dy_col=2 * cp, g_x_col=gx, shift_shl_group=True)
+                        tapsG.append(dWg[:, :c, :c])
+                    dWc = torch.stack(tapsG, dim=-1)
+                    dWr = zeros(G, cp, cp)
+                    ops.wgrad(dur, inp, dWr, B, T, cp, cp, cp, 0, 0, groups=G, g_dy_col=2 * cp, g_x_col=gx)
+                    dbg = ops.colsum(dur, 0, G * 2 * cp, zeros(G * 2 * cp)).view(G, 2, cp)
+                    for g in range(G):
+                        k_ = f"{p}stacks.{s_}.blocks.{g}."
+                        grads[k_ + "conv.weight"], grads[k_ + "conv.bias"] = dWc[g], dbg[g, 0, :c]
+                        grads[k_ + "res_conv.weight"], grads[k_ + "res_conv.bias"] = dWr[g, :c, :c].reshape(c, c, 1), dbg[g, 1, :c]
+                if s_ > 0:
+                    dy = b.lvl_T[s_].run(dur, buf(f"{tag}.dyB{i}", M, G * cp), B, T, g_a_col=2 * cp, g_out_col=cp)
+                else:
+                    d32 = buf(f"{tag}.dh32.{i}", M, cp, f32, zero=True)
+                    b.lvl_T[0].run(dur, d32, B, T, g_a_col=2 * cp, g_out_col=0, epi=_lib.EPI_RESID)
+                    dh0 = ops.cast_pad_bf16(d32, cp, out=buf(f"{tag}.dh0.{i}", M, cp))
+            if grads is not None:
+                a_in = sv[("in", i)]
+                taps = []
+                for k in range(3):
+                    dWi = zeros(cp, rup(b.cin_pad, 4))
+                    ops.wgrad(dh0, a_in, dWi, B, T, cp, b.cin_pad, 0, 0, 2 - k)
+                    taps.append(dWi[:c, :cin])
+                grads[p + "init_conv.weight"] = torch.stack(taps, dim=-1)
+                grads[p + "init_conv.bias"] = ops.colsum(dh0, 0, cp, zeros(cp))[:c]
+            if i > 0 or first_needs_dx:
+                dcur = b.init_T.run(dh0, buf(f"{tag}.din{i}", M, b.cin_pad), B, T)
+            else:
+                dcur = None
+        return dcur
+
+
+class FrozenDecoderTrain:
+    """decode_feature (LM:1109-1116) in training form: an un-fused forward that keeps the pre-activations, the
+    data-gradient backward down to the latent, and optionally (VAE training) every weight gradient.  Inside a multitask
+    diffusion step the VAE is frozen (diff_discrete.py:79-81): packed once, no dropout, no weight gradients."""
+
+    def __init__(self, sd: Optional[Dict[str, torch.Tensor]], cfg: DiffNormConfig, dev, buf, pre: str = "speech_decoder."):
         self.cfg, self.dev, self.buf = cfg, dev, buf
         c = cfg
-        pre = "speech_decoder."
-        w = lambda k: sd[pre + k].detach().to(dev).float()
         self.zp = rup(c.latent_dim, 64)
         self.D, self.H, self.dh = c.feat_dim, c.vae_heads, c.vae_dim_head
         self.inner = DiffNormConfig.ff_inner(self.D)
         self.ip = rup(self.inner, 128)
         self.vl = rup(c.vocab, 64)                 # dlogits row width (K of the lm-head data gradient)
-        G, S = c.vae_layers, c.vae_stacks
-        self.G, self.S = G, S
+        self.G, self.S = c.vae_layers, c.vae_stacks
+        self.wn = VaeBlocksTrain(buf, self.G, self.S, "v")
+        rm = geglu_row_map(self.inner)
+        self.geglu_src, self.geglu_dst = torch.nonzero(rm >= 0).squeeze(1).to(dev), rm[rm >= 0].to(dev)
+        self.sv: Dict[object, object] = {}
+        if sd is not None:
+            self.pack(lambda k: sd[pre + k].detach().to(dev).float())
+
+    def pack(self, w):
+        c, dev, D, ip = self.cfg, self.dev, self.D, self.ip
         self.blocks = []
         cin_pad = self.zp
         dec_w = c.dec_widths()
         for i, (cin, cout) in enumerate(dec_w):
-            last = i == len(dec_w) - 1
-            cp = rup(cout, 128)
-            b = _Plans()
-            b.cp, b.cin_pad, b.last = cp, cin_pad, last
-            p = f"decoder_wave.{i}."
-            b.init = pack_conv3(w(p + "init_conv.weight"), w(p + "init_conv.bias"), cin_pad=cin_pad, n_pad=cp, name=p + "init")
-            b.init_T = pack_conv3(w(p + "init_conv.weight").permute(1, 0, 2), None, cin_pad=cp, n_pad=cin_pad, shift_sign=-1,
-                                  name=p + "init^T")
-            b.lvl, b.lvl_T = [], []
-            tiles = cp // 128
-            for s_ in range(S):
-                blk = [f"{p}stacks.{s_}.blocks.{g}." for g in range(G)]
-                convs, ress = [w(k + "conv.weight") for k in blk], [w(k + "res_conv.weight") for k in blk]
-                lv = pack_wavenet_level(convs, [w(k + "conv.bias") for k in blk], ress, [w(k + "res_conv.bias") for k in blk], cp)
-                bi = torch.stack([lv.bias.view(G, tiles, 128), lv.bias2.view(G, tiles, 128)], dim=2).reshape(-1).contiguous()
-                b.lvl.append(GemmPlan(lv.W, lv.segs, 2 * cp, tiles, _lib.EPI_BF16, bias=bi, groups=G, g_w_row=lv.g_w_row,
-                                      g_bias=2 * cp, dilation=1, dilation_shl_group=1, name=f"{p}lvl{s_}.ur"))
-                b.lvl_T.append(pack_wavenet_level_dgrad(convs, ress, cp, name=f"{p}lvl{s_}^T"))
-            lastb = [f"{p}stacks.{S - 1}.blocks.{g}." for g in range(G)]
-            skips = [w(k + "skip_conv.weight") for k in lastb]
-            b.skip = pack_skip_sum(skips, [w(k + "skip_conv.bias") for k in lastb], cp, name=p + "skip")
-            WsT = torch.zeros(G * cp, cp, device=dev)
-            for g in range(G):
-                WsT[g * cp:g * cp + cout, :cout] = skips[g].reshape(cout, cout).t()
-            b.skip_T = pack_linear(WsT, None, k_pad=cp, n_pad=G * cp, name=p + "skip^T")
-            b.final = pack_linear(w(p + "final_conv.weight"), w(p + "final_conv.bias"), epi=_lib.EPI_F32 if last else _lib.EPI_BF16,
-                                  k_pad=cp, n_pad=cout if last else cp, name=p + "final")
-            b.final_T = pack_linear(w(p + "final_conv.weight").reshape(cout, cout).t(), None, k_pad=rup(cout, 64) if last else cp,
-                                    n_pad=cp, name=p + "final^T")
+            b = _pack_vae_wavenet(w, f"decoder_wave.{i}.", cin, cout, cin_pad, self.G, self.S, i == len(dec_w) - 1, dev)
             self.blocks.append(b)
-            cin_pad = cp
-        D, ip = self.D, self.ip
+            cin_pad = b.cp
         self.layers = []
         for l in range(c.vae_depth):
             p = f"decoder_tf.layers.{l}."
             L = _Plans()
+            L.p = p
             wqkv = torch.cat([w(p + "1.to_q.weight"), w(p + "1.to_kv.weight")], 0)
             L.qkv, L.qkv_T = pack_linear(wqkv, None, name=p + "qkv"), pack_linear(wqkv.t(), None, name=p + "qkv^T")
             L.out = pack_linear(w(p + "1.to_out.weight"), None, epi=_lib.EPI_RESID, name=p + "to_out")
@@ -126,41 +233,28 @@ class FrozenDecoderTrain:
             L.ffc_T = pack_conv3(wc.permute(1, 0, 2), None, cin_pad=ip, n_pad=ip, shift_sign=-1, name=p + "ff.conv^T")
             L.ff3 = pack_linear(w(p + "5.3.weight"), w(p + "5.3.bias"), epi=_lib.EPI_RESID, k_pad=ip, name=p + "ff.out")
             L.ff3_T = pack_linear(w(p + "5.3.weight").t(), None, k_pad=D, n_pad=ip, name=p + "ff.out^T")
-            L.g1, L.g2 = w(p + "0.gamma").contiguous(), w(p + "4.gamma").contiguous()
+            L.g1, L.g2 = w(p + "0.gamma").float().contiguous().clone(), w(p + "4.gamma").float().contiguous().clone()
             self.layers.append(L)
-        self.pred_gamma = w("decoder_tf.to_pred.0.gamma").contiguous()
+        self.pred_gamma = w("decoder_tf.to_pred.0.gamma").float().contiguous().clone()
         self.pred = pack_linear(w("decoder_tf.to_pred.1.weight"), None, epi=_lib.EPI_F32, name="vae.to_pred")
         self.pred_T = pack_linear(w("decoder_tf.to_pred.1.weight").t(), None, name="vae.to_pred^T")
         self.lm = pack_linear(w("decoder_lm.weight"), w("decoder_lm.bias"), epi=_lib.EPI_F32, n_pad=rup(c.vocab, 16), name="vae.lm")
         self.lm_T = pack_linear(w("decoder_lm.weight").t(), None, epi=_lib.EPI_F32, k_pad=self.vl, n_pad=D, name="vae.lm^T")
-        self.sv: Dict[object, object] = {}
 
-    def forward(self, xb, lens, B, T):
+    def forward(self, xb, lens, B, T, keep_bits=None, keep_scale: float = 1.0):
         """xb bf16 [B*T, zp] -> (recon fp32 [B*T, 768], logits fp32 [B*T, vp]); keeps activations for backward()."""
-        c, buf, G, S = self.cfg, self.buf, self.G, self.S
+        c, buf = self.cfg, self.buf
         M, D, H, dh, ip = B * T, self.D, self.H, self.dh, self.ip
         sv = self.sv = {}
-        a = xb
-        for i, b in enumerate(self.blocks):
-            cp = b.cp
-            h = b.init.run(a, buf(f"v.h{i}", M, cp), B, T)
-            src, g_a_col = h, 0
-            for s_ in range(S):
-                ur = b.lvl[s_].run(src, buf(f"v.ur{i}.{s_}", M, G * 2 * cp), B, T, g_a_col=g_a_col, g_out_col=2 * cp)
-                y = ops.wn_gate_fwd(ur, buf(f"v.y{i}.{s_}", M, G * cp), B, T, cp, G)
-                sv[("ur", i, s_)] = ur
-                src, g_a_col = y, cp
-            sk = b.skip.run(src, buf(f"v.sk{i}", M, cp), B, T)
-            out = buf("v.x", M, D, f32) if b.last else buf(f"v.o{i}", M, cp)
-            a = b.final.run(sk, out, B, T)
-        x = a
+        x = self.wn.forward(self.blocks, xb, B, T, x_out=buf("v.x", M, D, f32))
         for l, L in enumerate(self.layers):
             xs1 = buf(f"v.xs1.{l}", M, D, f32)
             xs1.copy_(x)
             hb1 = ops.adarmsnorm(x, buf(f"v.hb1.{l}", M, D), B, T, L.g1)
             qkv = L.qkv.run(hb1, buf(f"v.qkv.{l}", M, 3 * H * dh), B, T)
             lse = buf(f"v.lse.{l}", B * H, T, f32)
-            ao = ops.attention_train(qkv, buf(f"v.ao.{l}", M, H * dh), lse, lens, None, 1.0, B, T, H, dh)
+            kb = None if keep_bits is None else keep_bits[l]
+            ao = ops.attention_train(qkv, buf(f"v.ao.{l}", M, H * dh), lse, lens, kb, keep_scale, B, T, H, dh)
             L.out.run(ao, x, B, T)
             xs2 = buf(f"v.xs2.{l}", M, D, f32)
             xs2.copy_(x)
@@ -169,53 +263,79 @@ class FrozenDecoderTrain:
             m1 = ops.geglu_fwd(hh, buf(f"v.m1.{l}", M, ip))
             m2 = L.ffc.run(m1, buf(f"v.m2.{l}", M, ip), B, T)
             L.ff3.run(m2, x, B, T)
-            sv[l] = (xs1, qkv, lse, ao, xs2, hh)
+            sv[l] = (xs1, hb1, qkv, lse, ao, xs2, hb2, hh, m1, m2, kb)
         hbf = ops.adarmsnorm(x, buf("v.hbf", M, D), B, T, self.pred_gamma)
         recon = self.pred.run(hbf, buf("v.recon", M, D, f32), B, T)
         rb = ops.cast_pad_bf16(recon, D, out=buf("v.rb", M, D))
         logits = self.lm.run(rb, buf("v.logits", M, rup(c.vocab, 16), f32), B, T)
-        sv["x"] = x
+        sv["x"], sv["hbf"], sv["rb"], sv["keep_scale"] = x, hbf, rb, keep_scale
         return recon, logits
 
-    def backward(self, dlogits, recon, audio, lens, stats, mse_scale: float, B, T):
-        """dlogits bf16 [B*T, vl] (+ the masked-MSE term built here) -> d x1_hat bf16 [B*T, zp]."""
-        buf, G, S, sv = self.buf, self.G, self.S, self.sv
-        M, D, H, dh, ip = B * T, self.D, self.H, self.dh, self.ip
+    def backward(self, dlogits, recon, audio, lens, stats, mse_scale: float, B, T, grads=None):
+        """dlogits bf16 [B*T, vl] (+ the masked-MSE term built here) -> d latent bf16 [B*T, zp].
+        grads (dict) given => also every weight / bias / gamma gradient of the decoder (VAE training)."""
+        buf, sv, c = self.buf, self.sv, self.cfg
+        M, D, H, dh, ip, inner = B * T, self.D, self.H, self.dh, self.ip, self.inner
+        dev = dlogits.device
+        zeros = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
+        wg = None
+        if grads is not None:
+            def wg(dY, X, n_rows, k_cols, shift=0):
+                dW = zeros(n_rows, rup(k_cols, 4))
+                if shift == 0:
+                    ops.wgrad(dY, X, dW, 1, M, n_rows, k_cols)
+                else:
+                    ops.wgrad(dY, X, dW, B, T, n_rows, k_cols, 0, 0, shift)
+                return dW
+            cs = lambda src, cols: ops.colsum(src, 0, cols, zeros(cols))
+            grads["decoder_lm.weight"] = wg(dlogits, sv["rb"], c.vocab, D)[:, :D]
+            grads["decoder_lm.bias"] = cs(dlogits, rup(c.vocab, 8))[:c.vocab]
         d_lm = self.lm_T.run(dlogits, buf("v.dlm", M, D, f32), B, T)
         drec = ops.recon_grad(recon, audio, d_lm, lens, B, T, stats, mse_scale, buf("v.drec", M, D))
+        if grads is not None:
+            grads["decoder_tf.to_pred.1.weight"] = wg(drec, sv["hbf"], D, D)
         dhb = self.pred_T.run(drec, buf("v.dhb", M, D), B, T)
         dx = buf("v.dx", M, D, f32, zero=True)
         dxb = buf("v.dxb", M, D)
-        ops.adarmsnorm_bwd(sv["x"], dhb, dx, dxb, B, T, gamma_p=self.pred_gamma)
+        dg = zeros(D) if grads is not None else None
+        ops.adarmsnorm_bwd(sv["x"], dhb, dx, dxb, B, T, gamma_p=self.pred_gamma, dgamma_p=dg)
+        if grads is not None:
+            grads["decoder_tf.to_pred.0.gamma"] = dg
         for l in reversed(range(len(self.layers))):
             L = self.layers[l]
-            xs1, qkv, lse, ao, xs2, hh = sv[l]
+            p = L.p
+            xs1, hb1, qkv, lse, ao, xs2, hb2, hh, m1, m2, kb = sv[l]
+            if grads is not None:
+                grads[p + "5.3.weight"] = wg(dxb, m2, D, ip)[:, :inner]
+                grads[p + "5.3.bias"] = cs(dxb, D)
             dm2 = L.ff3_T.run(dxb, buf("v.dm2", M, ip), B, T)
+            if grads is not None:
+                grads[p + "5.2.1.weight"] = torch.stack([wg(dm2, m1, ip, ip, shift=2 - k)[:inner, :inner] for k in range(3)], dim=-1)
+                grads[p + "5.2.1.bias"] = cs(dm2, ip)[:inner]
             dm1 = L.ffc_T.run(dm2, buf("v.dm1", M, ip), B, T)
             dh_ = ops.geglu_bwd(hh, dm1, buf("v.dh", M, 2 * ip))
+            if grads is not None:
+                dW1p, db1p = wg(dh_, hb2, 2 * ip, D), cs(dh_, 2 * ip)
+                grads[p + "5.0.weight"] = zeros(2 * inner, D).index_copy_(0, self.geglu_dst, dW1p.index_select(0, self.geglu_src))
+                grads[p + "5.0.bias"] = zeros(2 * inner).index_copy_(0, self.geglu_dst, db1p.index_select(0, self.geglu_src))
             dhb = L.ff1_T.run(dh_, buf("v.dhb", M, D), B, T)
-            ops.adarmsnorm_bwd(xs2, dhb, dx, dxb, B, T, gamma_p=L.g2)
+            dg = zeros(D) if grads is not None else None
+            ops.adarmsnorm_bwd(xs2, dhb, dx, dxb, B, T, gamma_p=L.g2, dgamma_p=dg)
+            if grads is not None:
+                grads[p + "4.gamma"] = dg
+                grads[p + "1.to_out.weight"] = wg(dxb, ao, D, H * dh)
             dao = L.out_T.run(dxb, buf("v.dao", M, H * dh), B, T)
-            dqkv = ops.attention_bwd(qkv, ao, dao, lse, lens, None, 1.0, buf("v.dqkv", M, 3 * H * dh), buf("v.delta", B * H, T, f32),
-                                     B, T, H, dh)
+            dqkv = ops.attention_bwd(qkv, ao, dao, lse, lens, kb, sv["keep_scale"], buf("v.dqkv", M, 3 * H * dh),
+                                     buf("v.delta", B * H, T, f32), B, T, H, dh)
+            if grads is not None:
+                dWqkv = wg(dqkv, hb1, 3 * H * dh, D)
+                grads[p + "1.to_q.weight"], grads[p + "1.to_kv.weight"] = dWqkv[:H * dh], dWqkv[H * dh:]
             dhb = L.qkv_T.run(dqkv, buf("v.dhb", M, D), B, T)
-            ops.adarmsnorm_bwd(xs1, dhb, dx, dxb, B, T, gamma_p=L.g1)
-        dcur = dxb
-        for i in reversed(range(len(self.blocks))):
-            b = self.blocks[i]
-            cp = b.cp
-            dsk = b.final_T.run(dcur, buf(f"v.dsk{i}", M, cp), B, T)
-            dy = b.skip_T.run(dsk, buf(f"v.dyA{i}", M, G * cp), B, T)
-            for s_ in reversed(range(S)):
-                dur = ops.wn_gate_bwd(sv[("ur", i, s_)], dy, buf(f"v.dur{i}", M, G * 2 * cp), B, T, cp, G)
-                if s_ > 0:
-                    dy = b.lvl_T[s_].run(dur, buf(f"v.dyB{i}", M, G * cp), B, T, g_a_col=2 * cp, g_out_col=cp)
-                else:
-                    d32 = buf(f"v.dh32.{i}", M, cp, f32, zero=True)
-                    b.lvl_T[0].run(dur, d32, B, T, g_a_col=2 * cp, g_out_col=0, epi=_lib.EPI_RESID)
-                    dh0 = ops.cast_pad_bf16(d32, cp, out=buf(f"v.dh0.{i}", M, cp))
-            dcur = b.init_T.run(dh0, buf(f"v.din{i}", M, b.cin_pad), B, T)
-        return dcur
+            dg = zeros(D) if grads is not None else None
+            ops.adarmsnorm_bwd(xs1, dhb, dx, dxb, B, T, gamma_p=L.g1, dgamma_p=dg)
+            if grads is not None:
+                grads[p + "0.gamma"] = dg
+        return self.wn.backward(self.blocks, dxb, B, T, grads=grads)
 
 
 class DenoiserTrainer:

@@ -259,11 +259,20 @@ int dn_lsnll_bwd(const float* logits, int32_t ld, int32_t V, const int64_t* unit
 int dn_recon_grad(const float* recon, const float* audio, const float* d_lm, const int32_t* lengths, int32_t B, int32_t T,
                   int32_t C, const double* stats, float mse_scale, void* out, void* stream);
 
+/* VAE training (LM:1118-1142): kl[0] += mean_b(0.5 mean_{z,T}(mask (mu^2 + exp(lv) - 1 - lv))) (distributions.py:62-74),
+ * and the backward of the reparameterisation + KL: dparams bf16 [B*T, ldd] from dz bf16 [B*T, ldz] (channel-last),
+ * kl_scale = d loss / d kl.  params as in dn_vae_reparam. */
+int dn_vae_kl(const float* params, int32_t ldp, const int32_t* lengths, int32_t B, int32_t T, int32_t z, float* kl,
+              void* stream);
+int dn_vae_reparam_bwd(const float* params, int32_t ldp, const float* eps, int32_t eps_channel_first, const void* dz,
+                       int32_t ldz, const int32_t* lengths, int32_t B, int32_t T, int32_t z, float kl_scale, void* dparams,
+                       int32_t ldd, void* stream);
+
 /* Attention-dropout keep bits (LM:338): n_words uint32, each bit kept with probability 1-p (Philox4x32-10). */
 int dn_dropout_bits(uint32_t* bits, int64_t n_words, float p, uint64_t seed, uint64_t offset, void* stream);
 
-/* dn_attention with dropout and the saved row statistic L2 = m + log2(l) (fp32 [B, H, T]); dh = 64, or dh = 96
- * without dropout (the frozen VAE decoder inside a multitask training step).
+/* dn_attention with dropout and the saved row statistic L2 = m + log2(l) (fp32 [B, H, T]); dh = 64 (denoiser) or
+ * dh = 96 (VAE decoder).
  * keep_bits [B, H, T, ceil(T/32)] (bit k%32 of word k/32 = key k kept) or null; keep_scale = 1/(1-p). */
 int dn_attention_train(const void* qkv, void* out, float* lse2, const int32_t* lengths, const uint32_t* keep_bits,
                        float keep_scale, int32_t B, int32_t T, int32_t H, int32_t dh, void* stream);

@@ -259,3 +259,51 @@ def test_plugin_forward_backward_through_autograd():
     with torch.no_grad():
         ev = ldm(audio.to(DEV), units.to(DEV), tgt_mask=mask.to(DEV), _replay={"times": rp["times"], "noise": rp["noise"]})
     assert abs(float(ev["total_loss"]) - 0.904014) < 2e-2 * 0.904014   # the oracle's no-dropout loss for this case
+
+
+def test_vae_train_step_against_oracle_autograd():
+    """VAE training: SpeechVAEEncoderDecoder.forward -> (mse, lm_pred, kl) and the gradients of the criterion's
+    loss 0.1 LS-NLL/ntokens + 10 mse + 1e-4 kl w.r.t. all 274 VAE tensors, vs the oracle's autograd (pinned to the reference)."""
+    import torch.nn.functional as F
+    from diffnorm_b200.plugin.latent_module import SpeechVAEEncoderDecoder
+    from diffnorm_b200.train_vae import VaeTrainer
+    z, wseed, B, T, lengths, dseed, drop_p = 16, 4, 2, 24, [24, 15], 31, 0.1
+    arch = O.Arch(latent_dim=z)
+    sd = O.init_state_dict(arch, seed=wseed, gains=O.PARITY_GAINS)
+    vae = SpeechVAEEncoderDecoder(768, z)
+    vae.load_state_dict({k[len("speech_decoder."):]: v for k, v in sd.items() if k.startswith("speech_decoder.")}, strict=True)
+    vae = vae.to(DEV)
+    audio, units, mask, eps_vae, _, _, keeps = O.train_case_inputs(z, B, T, lengths, dseed, drop_p, depth=arch.vae_depth)
+    keys = [k for k in sd if k.startswith("speech_decoder.") and sd[k].is_floating_point()]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    ref = O.vae_train_loss(sd, arch, audio, units, mask, eps_vae, keeps, drop_p)
+    ref["loss"].backward()
+    tr = VaeTrainer(vae, drop_p=drop_p)
+    mse, logits, kl = tr.forward(audio.to(DEV), torch.tensor(lengths, dtype=i32, device=DEV), eps_vae,
+                                 [pack_keep_bits(k).to(DEV) for k in keeps])
+    # the criterion's arithmetic on the returned logits (speech_vae_decoder_loss.py:60-82), plain torch
+    lg = logits.detach().clone().requires_grad_(True)
+    lprobs = F.log_softmax(lg, dim=-1).view(-1, lg.shape[-1])
+    u = units.to(DEV).view(-1)
+    ls, nll = O.label_smoothed_nll_loss(lprobs, u, 0.1, 0)
+    ntok = int(u.ne(0).sum())
+    (0.1 * ls / ntok).backward()
+    loss = 0.1 * ls.detach() / ntok + 10 * mse + 1e-4 * kl
+    for name, a, b in (("mse", mse, ref["mse_loss"]), ("kl", kl, ref["kl_loss"]), ("nll", nll / ntok, ref["nll_loss"]), ("loss", loss, ref["loss"])):
+        print(f"[parity] vae train {name}: cuda {float(a):.6f} oracle {float(b):.6f}")
+        assert abs(float(a) - float(b)) <= 2e-2 * abs(float(b)) + 1e-4
+    grads = tr.backward(10.0, lg.grad, 1e-4)
+    torch.cuda.synchronize()
+    assert sorted("speech_decoder." + k for k in grads) == sorted(keys)
+    worst, num, den = ("", 0.0), 0.0, 0.0
+    for k in keys:
+        gg, gr = grads[k[len("speech_decoder."):]].cpu().reshape(sd[k].shape), sd[k].grad
+        e = rel(gg, gr)
+        num += float((gg.double() - gr.double()).pow(2).sum())
+        den += float(gr.double().pow(2).sum())
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < 0.25, (k, e, float(gr.norm()))
+    print(f"[parity] vae train grads: global rel err {np.sqrt(num / den):.3e}, worst {worst}")
+    assert np.sqrt(num / den) < 4e-2
