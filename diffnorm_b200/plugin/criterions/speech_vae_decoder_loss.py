@@ -32,17 +32,22 @@ class SpeechVAEDecoderLoss(FairseqCriterion):
         self.padding_idx = 0
 
     def forward(self, model, sample, reduction="mean"):
-        tgt_feature, tgt_unit, tgt_lengths = sample["target"], sample["target_unit"], sample["target_lengths"]
-        mse_loss, lm_pred, kl_loss = model(tgt_feature, tgt_unit, tgt_lengths=tgt_lengths)
-        lprobs = torch.log_softmax(lm_pred, dim=-1)
-        loss_lm, nll = label_smoothed_nll_loss(lprobs.view(-1, lprobs.size(-1)), tgt_unit.view(-1), self.eps,
-                                               ignore_index=self.padding_idx)
+        """:45-95 — trains on the REDUCED targets (:48-50), like the diffusion criterion."""
+        tgt_feature, tgt_unit = sample["reduce_target"], sample["reduce_target_unit"]
+        kwargs = dict(src_feature=sample["net_input"]["src_tokens"], src_lengths=sample["net_input"]["src_lengths"],
+                      tgt_lengths=sample["reduce_target_lengths"], unk_token=self.task.tgt_dict.unk_index)
+        mse_loss, lm_pred, kl_loss = model(tgt_feature, tgt_unit, **kwargs)
+        lprobs = torch.log_softmax(lm_pred, dim=-1).view(-1, lm_pred.size(-1))
+        target = tgt_unit.view(-1)
+        tmask = target.ne(0)
+        acc = torch.sum(lprobs.argmax(1).masked_select(tmask).eq(target.masked_select(tmask))) / torch.sum(tmask)
+        loss_lm, nll = label_smoothed_nll_loss(lprobs, target, self.eps, ignore_index=0)
         ntokens = sample["ntokens"]
-        loss = 0.1 * loss_lm / ntokens + 10.0 * mse_loss + 1e-4 * kl_loss
+        loss = 0.1 * (loss_lm / ntokens) + 10 * mse_loss + 0.0001 * kl_loss
         sample_size = sample["nsentences"]
         logging_output = {"loss": loss.item(), "nll_loss": (nll / ntokens).item(), "mse_loss": mse_loss.item(),
-                          "kl_loss": kl_loss.item(), "ntokens": ntokens, "nsentences": sample["nsentences"],
-                          "sample_size": sample_size}
+                          "kl_loss": kl_loss.item(), "acc": acc.item(), "ntokens": ntokens,
+                          "nsentences": sample["nsentences"], "sample_size": sample_size}
         return loss, sample_size, logging_output
 
     @staticmethod

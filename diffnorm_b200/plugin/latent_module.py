@@ -152,9 +152,41 @@ class SpeechVAEEncoderDecoder(FairseqEncoder):
         recon, logits = eng.decode(xb, lens, B, T)
         return recon.clone(), logits[..., : eng.cfg.vocab].clone()
 
-    def forward(self, input_feature, input_token, mask):
-        raise NotImplementedError("VAE training forward (LM:1118-1142) is not part of the round-1 hot path; "
-                                  "see DESIGN.md roadmap (SURVEY §8f rank 2)")
+    # ---- training entry (LM:1118-1142) ------------------------------------------------------------------------
+    def _vae_trainer(self):
+        if getattr(self, "_vae_trainer_obj", None) is None:
+            from ..train_vae import VaeTrainer
+            self._vae_trainer_obj = VaeTrainer(self, drop_p=0.1)
+        return self._vae_trainer_obj
+
+    def forward(self, input_feature, input_token, mask, _replay: Optional[Dict[str, object]] = None):
+        """(mse_loss, lm_result [B,T,1004], kl_loss) like the reference; forward and backward run in the sm_100a kernels
+        (diffnorm_b200/train_vae.py).  The three outputs carry an autograd node: whatever the criterion builds from them
+        (speech_vae_decoder_loss.py:60-82) back-propagates into the CUDA backward, which fills the parameter gradients.
+        ``_replay`` (extension) = {"eps_vae", "keep_bits"} replays the random draws for parity runs."""
+        _require_cuda(input_feature, "SpeechVAEEncoderDecoder.forward")
+        tr = self._vae_trainer()
+        lens = _mask_to_lengths(mask)
+        names = list(tr.P.keys())
+        params = [tr.P[n] for n in names]
+        need_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params)
+        return _VaeStepFn.apply(tr, input_feature, lens, _replay or {}, self.training, need_grad, names, *params)
+
+
+class _VaeStepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, trainer, feat, lens, replay, training, need_grad, names, *params):
+        mse, logits, kl = trainer.forward(feat, lens, eps_vae=replay.get("eps_vae"), keep_bits=replay.get("keep_bits"),
+                                          train=training)
+        ctx.trainer, ctx.names, ctx.shapes, ctx.need_grad = trainer, names, [p.shape for p in params], need_grad
+        return mse.clone(), logits.clone(), kl.clone()
+
+    @staticmethod
+    def backward(ctx, g_mse, g_logits, g_kl):
+        if not ctx.need_grad:
+            raise RuntimeError("backward through a VAE step that ran without gradients (eval mode / no_grad)")
+        grads = ctx.trainer.backward(0.0 if g_mse is None else float(g_mse), g_logits, 0.0 if g_kl is None else float(g_kl))
+        return (None,) * 7 + tuple(grads[n].reshape(sh) for n, sh in zip(ctx.names, ctx.shapes))
 
 
 def _mask_to_lengths(mask: torch.Tensor) -> torch.Tensor:
