@@ -30,6 +30,32 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------- bf16 split staging
+// fp32 [rows, C] -> bf16 [rows, 3C] = [hi | hi | lo] with hi = bf16(x), lo = bf16(x - hi): against weights packed as
+// [hi | lo | hi] one bf16 GEMM over K = 3C computes x.w to ~2^-16 relative (the lo.lo term is dropped) — the fp32-grade
+// contraction the k-means assignment needs (near-ties between centroids).
+__global__ void split_bf16x3_kernel(const float* __restrict__ src, long long rows, int C, __nv_bfloat16* __restrict__ dst) {
+    const int groups = C / 4;
+    const long long total = rows * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int c = (int)(i % groups) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * C + c);
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hi[k] = __bfloat162float(__float2bfloat16(x[k]));
+            lo[k] = x[k] - hi[k];
+        }
+        const uint2 h = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
+        __nv_bfloat16* d = dst + r * 3 * C + c;
+        *reinterpret_cast<uint2*>(d) = h;
+        *reinterpret_cast<uint2*>(d + C) = h;
+        *reinterpret_cast<uint2*>(d + 2 * C) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- VAE reparam
 // Generic form (any z, either eps layout): one element per thread.
 __global__ void vae_reparam_kernel(const float* __restrict__ params, int ldp, const float* __restrict__ eps,
@@ -356,6 +382,15 @@ extern "C" int dn_cast_pad_bf16(const float* src, int64_t rows, int32_t C, int32
     if (!src || !dst || rows <= 0 || ldo % 8 || C > ldo) return DN_EINVAL;
     cast_pad_kernel<<<ew_grid(rows * (ldo / 8), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
         src, rows, C, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldo);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_split_bf16x3(const float* src, int64_t rows, int32_t C, void* dst, void* stream) {
+    if (!src || !dst || rows <= 0 || C <= 0 || C % 4 || (reinterpret_cast<uintptr_t>(src) & 15)) return DN_EINVAL;
+    split_bf16x3_kernel<<<ew_grid(rows * (C / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(src, rows, C,
+                                                                                          reinterpret_cast<__nv_bfloat16*>(dst));
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

@@ -391,3 +391,13 @@ def vae_reparam_bwd(params, eps, eps_channel_first: bool, dz, lengths, z: int, k
     check(lib.dn_vae_reparam_bwd(_p(params), ldp, _p(eps), int(eps_channel_first), _p(dz), dz.shape[-1], _p(lengths), B, T, z,
                                  kl_scale, _p(dparams), dparams.shape[-1], _stream()), "dn_vae_reparam_bwd")
     return dparams
+
+
+def split_bf16x3(src, out=None):
+    """fp32 [rows, C] -> bf16 [rows, 3C] = [hi | hi | lo]."""
+    _chk(src, f32, "src")
+    rows, Cc = src.shape
+    if out is None:
+        out = torch.empty(rows, 3 * Cc, dtype=bf16, device=src.device)
+    check(lib.dn_split_bf16x3(_p(src), rows, Cc, _p(out), _stream()), "dn_split_bf16x3")
+    return out

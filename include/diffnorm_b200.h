@@ -60,6 +60,11 @@ int dn_gather_pack(const float* src, const int64_t* src_row0, const int64_t* ind
 /* fp32 [rows, C] -> bf16 [rows, ldo] with zero fill of the pad columns (operand staging for the GEMMs). */
 int dn_cast_pad_bf16(const float* src, int64_t rows, int32_t C, int32_t lds, void* dst, int32_t ldo, void* stream);
 
+/* fp32 [rows, C] -> bf16 [rows, 3C] = [hi | hi | lo] (hi = bf16(x), lo = bf16(x - hi)).  Against weights packed as
+ * [hi | lo | hi] a single dn_gemm over K = 3C gives the contraction to ~2^-16 relative: used by the k-means unit
+ * quantiser (examples/textless_nlp/gslm/speech2unit/clustering/quantize_with_kmeans.py:109-121). */
+int dn_split_bf16x3(const float* src, int64_t rows, int32_t C, void* dst, void* stream);
+
 /* VAE posterior reparameterisation.  Replaces distributions.py:24-41 + the caller's transpose LM:1397.
  * params [B, T, ldp] fp32 row-major with mean in columns [0,z) and logvar in [z,2z) (channel-last);
  * eps: eps_channel_first = 1 -> [B, z, T] (the reference's draw order), 0 -> [B, T, z].

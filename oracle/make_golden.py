@@ -280,6 +280,29 @@ def make_vae_train(name):
     print(name, {k: float(store[k]) for k in ("loss", "nll_loss", "mse_loss", "kl_loss", "acc")}, "params with grad", len(names))
 
 
+def kmeans_case(seed=11, K=1000, D=768, N=4000):
+    """Seeded centroids / features of the k-means fixture (features = planted centroid + noise, plus 500 pure-noise rows)."""
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((K, D)).astype(np.float32) * 0.6
+    lab = rng.integers(0, K, size=N)
+    feats = (centers[lab] + rng.standard_normal((N, D)).astype(np.float32) * 0.9).astype(np.float32)
+    feats[-500:] = rng.standard_normal((500, D)).astype(np.float32)
+    return centers, feats
+
+
+def make_kmeans():
+    """Labels from scikit-learn's own KMeans.predict (what quantize_with_kmeans.py:115 calls on the joblib-loaded model)."""
+    from sklearn.cluster import KMeans
+    centers, feats = kmeans_case()
+    km = KMeans(n_clusters=len(centers), n_init=1)
+    km.fit(feats[: len(centers)])          # creates the fitted attributes; the centroids are then replaced
+    km.cluster_centers_ = centers.copy()
+    pred = km.predict(feats)
+    np.savez_compressed(os.path.join(GOLD, "kmeans_predict.npz"), seed=11, K=len(centers), D=centers.shape[1], N=len(feats),
+                        labels=pred.astype(np.int16))
+    print("kmeans labels", len(pred), "agreement with oracle", float((pred == O.kmeans_predict(centers, feats)).mean()))
+
+
 def make_schedule(ldm):
     s = ldm.scheduler
     np.savez_compressed(
@@ -362,6 +385,8 @@ def main():
         for name in TRAIN_CASES:
             make_train(name)
         return
+    if "--kmeans-only" in sys.argv:
+        return make_kmeans()
     if "--vae-train-only" in sys.argv:
         for name in VAE_TRAIN_CASES:
             make_vae_train(name)
@@ -377,6 +402,7 @@ def main():
         make_train(name)
     for name in VAE_TRAIN_CASES:
         make_vae_train(name)
+    make_kmeans()
 
 
 if __name__ == "__main__":

@@ -350,3 +350,25 @@ def test_gemm_persistent_many_tiles():
     plan.run(A, out, B, T)
     want = A.float() @ W.bfloat16().float().T
     torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
+
+
+def test_kmeans_quantizer_matches_sklearn_and_oracle():
+    """dn_split_bf16x3 + dn_gemm (K = 3 x 768) + dn_argmax_units vs scikit-learn's labels (golden) and the float64 oracle.
+    Bar: identical labels wherever the float64 top-2 squared-distance gap exceeds 1e-3 (near-ties below that are within
+    fp32 rounding of scikit-learn's own float32 arithmetic); >= 99.9 % overall."""
+    import os
+    from diffnorm_b200.kmeans import KMeansQuantizer
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmeans_predict.npz"))
+    centers, feats = O.kmeans_case(int(g["seed"]), int(g["K"]), int(g["D"]), int(g["N"]))
+    q = KMeansQuantizer(centers)
+    got = q.predict(torch.from_numpy(feats).cuda()).cpu().numpy()
+    want = g["labels"].astype(np.int64)
+    c, x = centers.astype(np.float64), feats.astype(np.float64)
+    d = (c * c).sum(1)[None, :] - 2.0 * x @ c.T
+    part = np.partition(d, 1, axis=1)
+    confident = (part[:, 1] - part[:, 0]) > 1e-3
+    print(f"[parity] kmeans: agreement {np.mean(got == want):.5f} overall, {np.mean(got[confident] == want[confident]):.5f} on "
+          f"{confident.mean():.4f} confident frames")
+    assert (got[confident] == want[confident]).all() and np.mean(got == want) >= 0.999
+    parts = q.predict_many([feats[:700], feats[700:701], feats[701:]], max_rows=1024)
+    assert np.array_equal(np.concatenate(parts), got)

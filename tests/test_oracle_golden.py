@@ -189,3 +189,12 @@ def test_oracle_vae_train_loss_and_grads_match_reference():
         assert abs(float(gr.norm()) - norm) <= 1e-3 * norm + 1e-9, (n, float(gr.norm()), norm)
         got = gr[torch.from_numpy(O.grad_probe(n, gr.numel()))].numpy()
         assert np.abs(got - samp).max() / (np.abs(samp).max() + norm / np.sqrt(gr.numel()) + 1e-12) <= 5e-3, n
+
+
+def test_oracle_kmeans_predict_matches_sklearn_golden():
+    """k-means unit quantisation: the algorithm lives in scikit-learn (not vendored by the reference; 1.9.0
+    here); the fixture holds KMeans.predict's own labels (oracle/make_golden.py make_kmeans)."""
+    g = np.load(os.path.join(GOLD, "kmeans_predict.npz"))
+    centers, feats = O.kmeans_case(int(g["seed"]), int(g["K"]), int(g["D"]), int(g["N"]))
+    got = O.kmeans_predict(centers, feats)
+    assert (got == g["labels"].astype(np.int64)).mean() == 1.0
