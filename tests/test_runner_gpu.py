@@ -88,3 +88,32 @@ def test_runner_end_to_end_against_oracle(tmp_path):
     # length mismatch is an error, like the reference's assert (:152)
     with pytest.raises(AssertionError):
         runner.normalize_batch([feats["utt0"]], [units_full["utt0"]], expect_reduced=[999])
+
+
+def test_quantize_cli_end_to_end(tmp_path):
+    """quantize_with_kmeans.py drop-in: centroids + feature manifest -> '{name}|{units}' lines, labels equal
+    to the float64 oracle's nearest centroid."""
+    from diffnorm_b200 import quantize_cli
+    rng = np.random.default_rng(2)
+    centers = rng.standard_normal((1000, 768)).astype(np.float32)
+    np.save(tmp_path / "centers.npy", centers)
+    fdir = tmp_path / "feat"
+    fdir.mkdir()
+    feats = {}
+    rows = [str(fdir)]
+    for k, n in enumerate([17, 1, 230]):
+        lab = rng.integers(0, 1000, size=n)
+        f = (centers[lab] + 0.5 * rng.standard_normal((n, 768))).astype(np.float32)
+        np.save(fdir / f"u{k}.feat.npy", f)
+        feats[f"u{k}.feat.npy"] = f
+        rows.append(f"u{k}.feat.npy\t{n}")
+    (tmp_path / "split.manifest.tsv").write_text("\n".join(rows) + "\n")
+    out = tmp_path / "out" / "split.quant.tsv"
+    quantize_cli.cli_main(["--kmeans_model_path", str(tmp_path / "centers.npy"), "--manifest_path", str(tmp_path / "split.manifest.tsv"),
+                           "--out_quantized_file_path", str(out)])
+    lines = out.read_text().strip().splitlines()
+    assert len(lines) == 3
+    for ln in lines:
+        name, units = ln.split("|")
+        want = O.kmeans_predict(centers, feats[name])
+        assert [int(u) for u in units.split(" ")] == want.tolist()
