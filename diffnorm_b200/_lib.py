@@ -60,7 +60,7 @@ class WgradDesc(C.Structure):
 
 
 EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_WN_GATE = range(5)
-GEMM_TCGEN05, GEMM_SIMT_CHECK = 0, 1
+GEMM_TCGEN05, GEMM_SIMT_CHECK, GEMM_TCGEN05_2CTA = 0, 1, 2
 
 # name -> argtypes ; every function returns int status except the two info calls
 _SIGS = {

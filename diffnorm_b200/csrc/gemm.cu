@@ -20,20 +20,24 @@ unsigned long long g_launch_count = 0;
 constexpr int BM = 128;         // frames per tile (UMMA M)
 constexpr int BK = 64;          // bf16 per K block = one 128-byte swizzle atom
 constexpr int WT = 256;         // packed weight rows per N tile (max UMMA N)
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = WT * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// smem ring: single CTA = 4 stages of (A 16 KB + W 32 KB); CTA pair = 6 stages of (A 16 KB + half of W 16 KB)
+template <int CTAS> struct Ring {
+    static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES / CTAS;
+};
 constexpr int ACC_COLS = 256;   // TMEM columns per accumulator stage
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
 constexpr int UNIT_BYTES = 128 * 128;  // epilogue staging unit: 128 rows x 128 B (one TMA store box)
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 2 * UNIT_BYTES + 1024 /*align slack*/;
+constexpr int GEMM_SMEM = 4 * (A_BYTES + B_BYTES) + 1024 /*barriers*/ + 2 * UNIT_BYTES + 1024 /*align slack*/;  // both ring forms = 192 KB
 
 struct TileCoord {
     int g, b, t0, n;
 };
-__device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile, int tiles_t) {
+// bm = rows per tile (128, or 256 for a CTA pair); row_off = this CTA's offset inside the tile
+__device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile, int tiles_t, int bm = BM, int row_off = 0) {
     TileCoord c;
     c.n = tile % p.n_tiles;
     int r = tile / p.n_tiles;
@@ -41,7 +45,7 @@ __device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile
     int m = r % m_tiles;
     c.g = r / m_tiles;
     c.b = m / tiles_t;
-    c.t0 = (m % tiles_t) * BM;
+    c.t0 = (m % tiles_t) * bm + row_off;
     return c;
 }
 
@@ -51,11 +55,18 @@ __device__ __forceinline__ const float* gb_row(const dn_gemm_desc& p, int b, int
     return p.gb + (long long)t * p.gb_t_stride + (long long)g * p.g_gb;
 }
 
-template <int EPI>
+// CTAS = 2: the kernel runs as a cluster of two CTAs (one TPC) on M = 256 tiles with tcgen05.mma.cta_group::2: each CTA
+// loads its own 128 A rows and HALF of the W tile's rows, the leader CTA issues the MMAs for both, completion is
+// multicast to both CTAs' barriers, and each CTA runs the unchanged epilogue on its own 128 accumulator rows.  Per flop
+// the pair reads a third less shared memory and fetches each W tile once instead of twice.
+template <int EPI, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmW128, const __grid_constant__ CUtensorMap tmOut,
-               const dn_gemm_desc p) {
+               const __grid_constant__ CUtensorMap tmW128, const __grid_constant__ CUtensorMap tmW64,
+               const __grid_constant__ CUtensorMap tmOut, const dn_gemm_desc p) {
+    constexpr int STAGES = Ring<CTAS>::STAGES;
+    constexpr int STAGE_BYTES = Ring<CTAS>::STAGE_BYTES;
+    static_assert(STAGES * STAGE_BYTES == 4 * (A_BYTES + B_BYTES), "both ring forms use the same 192 KB");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -67,14 +78,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_t = (p.T + BM - 1) / BM;
+    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    constexpr int TBM = BM * CTAS;                 // rows per tile
+    const int row_off = (int)rank * BM;
+    const int tiles_t = (p.T + TBM - 1) / TBM;
     const int total = p.groups * p.B * tiles_t * p.n_tiles;
     const int rows_pg = p.groups > 1 ? p.g_w_row : p.w_rows;
+    const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmW128);
+        tma_prefetch_desc(&tmW64);
         tma_prefetch_desc(&tmOut);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
@@ -82,16 +99,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], EPI_WARPS);
+            mbar_init(&tempty[i], EPI_WARPS * CTAS);   // pair: the leader's MMA waits for both CTAs' epilogues
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if (CTAS == 2) {
+            tmem_alloc2(tmem_slot, 512);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(tmem_slot, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -100,21 +122,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // ---------------------------------------------------------------- TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                TileCoord c = decode_tile(p, tile, tiles_t);
+            for (int tile = tile0; tile < total; tile += tile_step) {
+                TileCoord c = decode_tile(p, tile, tiles_t, TBM, row_off);
                 const int d = p.dilation << (p.dilation_shl_group ? c.g : 0);
+                int n_full = rows_pg - c.n * WT;
+                n_full = n_full > WT ? WT : n_full;
                 for (int s = 0; s < p.num_segs; ++s) {
                     const dn_gemm_seg sg = p.seg[s];
                     const bool half_w = sg.n_mma == 128;
+                    const int nrows = sg.n_mma ? sg.n_mma : n_full;   // W rows this segment multiplies
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * STAGE_BYTES;
                         uint8_t* sb = sa + A_BYTES;
-                        mbar_expect_tx(&full[stage], A_BYTES + (half_w ? B_BYTES / 2 : B_BYTES));
-                        tma_load_3d(&tmA, &full[stage], sa, sg.a_col0 + c.g * p.g_a_col + kb * BK,
-                                    c.t0 - sg.shift_mul * d, c.b);
-                        tma_load_2d(half_w ? &tmW128 : &tmW, &full[stage], sb, sg.w_k0 + kb * BK,
-                                    c.g * p.g_w_row + c.n * WT);
+                        if (CTAS == 1) {
+                            mbar_expect_tx(&full[stage], A_BYTES + (half_w ? B_BYTES / 2 : B_BYTES));
+                            tma_load_3d(&tmA, &full[stage], sa, sg.a_col0 + c.g * p.g_a_col + kb * BK,
+                                        c.t0 - sg.shift_mul * d, c.b);
+                            tma_load_2d(half_w ? &tmW128 : &tmW, &full[stage], sb, sg.w_k0 + kb * BK,
+                                        c.g * p.g_w_row + c.n * WT);
+                        } else {
+                            // each CTA brings nrows / 2 W rows (box of 128 or 64 rows; rows past the half are not read)
+                            const int half = nrows >> 1;
+                            const bool box128 = half > 64;
+                            const uint32_t bytes = A_BYTES + (box128 ? 128 : 64) * BK * 2;
+                            if (leader) mbar_expect_tx(&full[stage], 2 * bytes);
+                            tma2_load_3d(&tmA, &full[stage], sa, sg.a_col0 + c.g * p.g_a_col + kb * BK,
+                                         c.t0 - sg.shift_mul * d, c.b);
+                            tma2_load_2d(box128 ? &tmW128 : &tmW64, &full[stage], sb, sg.w_k0 + kb * BK,
+                                         c.g * p.g_w_row + c.n * WT + (int)rank * half);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -124,14 +161,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer (one thread)
+        if (lane == 0 && leader) {
+            // ---------------------------------------------------------------- MMA issuer (one thread; pair: leader CTA)
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                TileCoord c = decode_tile(p, tile, tiles_t);
+            for (int tile = tile0; tile < total; tile += tile_step) {
+                TileCoord c = decode_tile(p, tile, tiles_t, TBM, row_off);
                 int n_full = rows_pg - c.n * WT;
                 n_full = n_full > WT ? WT : n_full;
                 mbar_wait(&tempty[as], aphase ^ 1);
@@ -140,7 +177,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t acc = 0;
                 for (int s = 0; s < p.num_segs; ++s) {
                     const dn_gemm_seg sg = p.seg[s];
-                    const uint32_t idesc = umma_idesc_bf16_m128(sg.n_mma ? sg.n_mma : n_full);
+                    const uint32_t nrows = sg.n_mma ? sg.n_mma : n_full;
+                    const uint32_t idesc = CTAS == 2 ? umma_idesc_bf16_m256(nrows) : umma_idesc_bf16_m128(nrows);
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
@@ -150,17 +188,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+                            if (CTAS == 2) umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+                            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
                             acc = 1;
                         }
-                        umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+                        // smem slot reusable (in both CTAs of a pair) once these MMAs have read it
+                        if (CTAS == 2) umma2_commit_mc(&empty[stage]); else umma_commit(&empty[stage]);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
                 }
-                umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+                if (CTAS == 2) umma2_commit_mc(&tfull[as]); else umma_commit(&tfull[as]);  // accumulator complete -> epilogue(s)
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }
@@ -181,8 +221,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int bar_id = 1 + half;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            TileCoord c = decode_tile(p, tile, tiles_t);
+        for (int tile = tile0; tile < total; tile += tile_step) {
+            TileCoord c = decode_tile(p, tile, tiles_t, TBM, row_off);
             const int t = c.t0 + row;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
@@ -314,7 +354,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                if (CTAS == 2 && !leader) mbar_arrive_remote(&tempty[as], 0);
+                else mbar_arrive(&tempty[as]);
+            }
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
@@ -322,8 +365,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (CTAS == 2) {
+        cluster_sync_all();   // the peer's barriers / smem must outlive the leader's last multicast and MMA reads
+        if (warp == 2) tmem_dealloc2(tmem_base, 512);
+    } else {
+        __syncthreads();
+        if (warp == 2) tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -442,15 +490,35 @@ int num_sms() {
     return n;
 }
 
-template <int EPI>
-static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& w128, const CUtensorMap& o,
-                     const dn_gemm_desc& d, int grid, cudaStream_t st) {
+template <int EPI, int CTAS>
+static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& w128, const CUtensorMap& w64,
+                     const CUtensorMap& o, const dn_gemm_desc& d, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        DN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_set = true;
     }
-    gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, w, w128, o, d);
+    const int tiles_t = (d.T + BM * CTAS - 1) / (BM * CTAS);
+    const long long total = (long long)d.groups * d.B * tiles_t * d.n_tiles;
+    const int units = num_sms() / CTAS;   // CTAs (or CTA pairs) resident at once
+    const int grid = (int)(total < units ? total : units) * CTAS;
+    if (CTAS == 1) {
+        gemm_tc_kernel<EPI, 1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, w, w128, w64, o, d);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = GEMM_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        DN_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, 2>, a, w, w128, w64, o, d));
+    }
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -484,7 +552,7 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
         return 0;
     }
 
-    CUtensorMap ma, mw, mw128;
+    CUtensorMap ma, mw, mw128, mw64;
     {
         cuuint64_t dims[3] = {(cuuint64_t)d.a_cols, (cuuint64_t)d.T, (cuuint64_t)d.B};
         cuuint64_t str[2] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.a_batch_stride * 2};
@@ -501,6 +569,9 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
         cuuint32_t box2[2] = {BK, 128};
         r = encode_bf16_map(&mw128, d.W, 2, dims, str, box2);
         if (r) return r;
+        cuuint32_t box3[2] = {BK, 64};
+        r = encode_bf16_map(&mw64, d.W, 2, dims, str, box3);
+        if (r) return r;
     }
     CUtensorMap mo;
     {
@@ -514,15 +585,22 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
                            dims, str, box);
         if (r) return r;
     }
-    const int tiles_t = (d.T + BM - 1) / BM;
-    const long long total = (long long)d.groups * d.B * tiles_t * d.n_tiles;
-    const int grid = (int)(total < num_sms() ? total : num_sms());
+    if (impl == DN_GEMM_TCGEN05_2CTA) {
+        switch (d.epi) {
+            case DN_EPI_BF16: return launch_tc<DN_EPI_BF16, 2>(ma, mw, mw128, mw64, mo, d, st);
+            case DN_EPI_F32: return launch_tc<DN_EPI_F32, 2>(ma, mw, mw128, mw64, mo, d, st);
+            case DN_EPI_RESID: return launch_tc<DN_EPI_RESID, 2>(ma, mw, mw128, mw64, mo, d, st);
+            case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU, 2>(ma, mw, mw128, mw64, mo, d, st);
+            case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE, 2>(ma, mw, mw128, mw64, mo, d, st);
+            default: return DN_EINVAL;
+        }
+    }
     switch (d.epi) {
-        case DN_EPI_BF16: return launch_tc<DN_EPI_BF16>(ma, mw, mw128, mo, d, grid, st);
-        case DN_EPI_F32: return launch_tc<DN_EPI_F32>(ma, mw, mw128, mo, d, grid, st);
-        case DN_EPI_RESID: return launch_tc<DN_EPI_RESID>(ma, mw, mw128, mo, d, grid, st);
-        case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU>(ma, mw, mw128, mo, d, grid, st);
-        case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE>(ma, mw, mw128, mo, d, grid, st);
+        case DN_EPI_BF16: return launch_tc<DN_EPI_BF16, 1>(ma, mw, mw128, mw64, mo, d, st);
+        case DN_EPI_F32: return launch_tc<DN_EPI_F32, 1>(ma, mw, mw128, mw64, mo, d, st);
+        case DN_EPI_RESID: return launch_tc<DN_EPI_RESID, 1>(ma, mw, mw128, mw64, mo, d, st);
+        case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU, 1>(ma, mw, mw128, mw64, mo, d, st);
+        case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE, 1>(ma, mw, mw128, mw64, mo, d, st);
         default: return DN_EINVAL;
     }
 }

@@ -177,6 +177,11 @@ def attention(qkv, out, lengths, B: int, T: int, H: int, dh: int):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
+import os as _os
+
+_USE_2CTA = _os.environ.get("DN_GEMM_2CTA", "1") != "0"   # A/B switch for measurements; results are bit-identical
+
+
 class GemmPlan:
     """A packed weight (bf16 [w_rows, ldw], 256 rows per N tile) + its K-segment program + epilogue vectors.
     Built once per layer by diffnorm_b200.packing; `run` fills a dn_gemm_desc and calls dn_gemm."""
@@ -197,12 +202,16 @@ class GemmPlan:
 
     def run(self, A, out, B: int, T: int, *, g_a_col: int = 0, g_out_col: int = 0, gb=None, gb_t_stride: int = 0,
             g_gb: int = 0, gb_half: int = 0, t_idx=None, t_idx_stride: int = 0, pe=None, lengths=None,
-            epi: Optional[int] = None, impl: int = _lib.GEMM_TCGEN05, a_cols: Optional[int] = None):
+            epi: Optional[int] = None, impl: Optional[int] = None, a_cols: Optional[int] = None):
         epi = self.epi if epi is None else epi
         if self._flat_ok and gb is None and pe is None:
             # no frame shifts and no per-utterance epilogue inputs: treat the batch as one long utterance so M tiles
             # run across utterance boundaries (T = 1000 would otherwise waste 24 of every 1024 tile rows)
             B, T = 1, B * T
+        if impl is None:
+            # CTA-pair form (tcgen05 cta_group::2, M = 256 tiles) whenever it still fills the machine: 74 pairs of SMs
+            pair_tiles = self.groups * B * ((T + 255) // 256) * self.n_tiles
+            impl = _lib.GEMM_TCGEN05_2CTA if (_USE_2CTA and pair_tiles >= 74) else _lib.GEMM_TCGEN05
         _chk(A, bf16, "A")
         _chk(out, f32 if epi in (_lib.EPI_F32, _lib.EPI_RESID) else bf16, "out")
         d = GemmDesc()

@@ -136,7 +136,7 @@ enum {
     DN_EPI_GEGLU = 3,    /* W tile = 128 "x" rows then 128 "gate" rows: out = gelu_erf(gate) * x (LM:881-885) */
     DN_EPI_WN_GATE = 4   /* W tile = 128 conv rows then 128 res rows: y = tanh(u')sigmoid(u') + res (LM:513-536) */
 };
-enum { DN_GEMM_TCGEN05 = 0, DN_GEMM_SIMT_CHECK = 1 };
+enum { DN_GEMM_TCGEN05 = 0, DN_GEMM_SIMT_CHECK = 1, DN_GEMM_TCGEN05_2CTA = 2 };
 
 typedef struct {
     int32_t B, T;               /* utterances, frames per utterance */
@@ -176,7 +176,9 @@ typedef struct {
 /* out = epilogue(A (*) W^T): bf16 operands, fp32 accumulation in TMEM (tcgen05.mma fed by TMA).
  * Replaces the cuBLAS / cuDNN calls behind nn.Linear / CausalConv1d on the path.
  * impl = DN_GEMM_SIMT_CHECK runs a slow one-thread-per-output CUDA kernel with identical semantics
- * (test checker for the tensor-core kernel; never used by the engine). */
+ * (test checker for the tensor-core kernel; never used by the engine).
+ * impl = DN_GEMM_TCGEN05_2CTA runs the same kernel as clusters of two CTAs on M = 256 tiles (tcgen05.mma.cta_group::2:
+ * each CTA stages half of the W tile, the leader issues the MMAs for both SMs); results are bit-identical. */
 int dn_gemm(const dn_gemm_desc* d, int32_t impl, void* stream);
 
 /* ---- attention ------------------------------------------------------------------------------------------ */

@@ -244,6 +244,12 @@ def _gemm_case(plan, A, out_shape, out_dtype, B, T, **kw):
         plan.run(A, out, B, T, impl=impl, **kw)
         outs.append(out.float())
     torch.cuda.synchronize()
+    # the CTA-pair (cta_group::2) form of the same kernel must reproduce the single-CTA result bit for bit
+    torch.manual_seed(0)
+    out2 = torch.randn(out_shape, device=DEV).to(out_dtype).contiguous()
+    plan.run(A, out2, B, T, impl=_lib.GEMM_TCGEN05_2CTA, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(out2.float(), outs[1]), "cta_group::2 kernel differs from the single-CTA kernel"
     return outs
 
 
