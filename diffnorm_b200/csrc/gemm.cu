@@ -31,7 +31,8 @@ constexpr int ACC_COLS = 256;   // TMEM columns per accumulator stage
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
 constexpr int UNIT_BYTES = 128 * 128;  // epilogue staging unit: 128 rows x 128 B (one TMA store box)
-constexpr int GEMM_SMEM = 4 * (A_BYTES + B_BYTES) + 1024 /*barriers*/ + 2 * UNIT_BYTES + 1024 /*align slack*/;  // both ring forms = 192 KB
+constexpr int BAR_BYTES = 2048;      // mbarriers (first 512 B) + per-tile epilogue parameter staging (GEGLU bias, 1 KB)
+constexpr int GEMM_SMEM = 4 * (A_BYTES + B_BYTES) + BAR_BYTES + 2 * UNIT_BYTES + 1024 /*align slack*/;  // both ring forms = 192 KB
 
 struct TileCoord {
     int g, b, t0, n;
@@ -215,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half = (warp - 4) >> 2;  // warpgroup: which units of the tile it handles
         const int row = q * 32 + lane;
         const bool issuer = (warp == 4 + 4 * half) && lane == 0;
-        uint8_t* stage_buf = smem + STAGES * STAGE_BYTES + 1024 + half * UNIT_BYTES;
+        uint8_t* stage_buf = smem + STAGES * STAGE_BYTES + BAR_BYTES + half * UNIT_BYTES;
         uint8_t* srow = stage_buf + row * 128;
         const int sw = row & 7;
         const int bar_id = 1 + half;
@@ -295,6 +296,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int col = c.n * 128 + half * 64;  // logical output column of this warpgroup's unit
                 if (col < p.n_out) {
                     if (issuer) bulk_wait_read0();
+                    if constexpr (EPI == DN_EPI_GEGLU) {
+                        // this warpgroup's 64 x-bias + 64 gate-bias values of the tile: one global load per thread, shared
+                        // through smem (the per-column __ldg chain inside the loop was exposed latency)
+                        float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 512) + half * 128;
+                        const int r = threadIdx.x & 127;
+                        const int wr = c.g * p.g_bias + c.n * WT + half * 64 + (r & 63) + (r >> 6) * 128;
+                        sbias[r] = p.bias ? __ldg(p.bias + wr) : 0.f;
+                    }
                     named_bar_sync(bar_id, 128);
 #pragma unroll 1
                     for (int sub = 0; sub < 2; ++sub) {
@@ -319,12 +328,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             };
                             if constexpr (EPI == DN_EPI_GEGLU) {
-                                const int wr = c.g * p.g_bias + c.n * WT + half * 64 + sub * 32 + j * 8;  // packed W row
-                                ld8(p.bias ? p.bias + wr : nullptr, pa, 0.f);
-                                ld8(p.bias ? p.bias + wr + 128 : nullptr, pb, 0.f);
+                                const float* sbias = reinterpret_cast<const float*>(smem + STAGES * STAGE_BYTES + 512) + half * 128;
+                                const int cc = sub * 32 + j * 8;
+                                const float4 a0 = *reinterpret_cast<const float4*>(sbias + cc), a1 = *reinterpret_cast<const float4*>(sbias + cc + 4);
+                                const float4 b0 = *reinterpret_cast<const float4*>(sbias + 64 + cc), b1 = *reinterpret_cast<const float4*>(sbias + 64 + cc + 4);
+                                pa[0] = a0.x; pa[1] = a0.y; pa[2] = a0.z; pa[3] = a0.w; pa[4] = a1.x; pa[5] = a1.y; pa[6] = a1.z; pa[7] = a1.w;
+                                pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    o[i] = gelu_erf_fast(hi[j * 8 + i] + pb[i]) * (lo[j * 8 + i] + pa[i]);
+                                for (int i = 0; i < 8; i += 2)
+                                    geglu2(hi[j * 8 + i], hi[j * 8 + i + 1], pb[i], pb[i + 1], lo[j * 8 + i], lo[j * 8 + i + 1],
+                                           pa[i], pa[i + 1], o[i], o[i + 1]);
                             } else {
                                 const int oc = c.g * p.g_bias + cj;
                                 float ga[8], be[8];

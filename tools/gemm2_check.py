@@ -75,3 +75,14 @@ if not small:
     compare("wavenet level 8x512", lv, y, (M, G * C), bf16, B, T, iters=10, g_a_col=C, g_out_col=C)
     compare("ff.out 1408->512 resid", packing.pack_linear(rnd(512, 1365, seed=95, scale=0.03).cpu(), rnd(512, seed=96).cpu(), epi=_lib.EPI_RESID, k_pad=ip).to(DEV),
             m1, (M, 512), f32, B, T, resid=True)
+if not small:
+    # is the WaveNet level epilogue-bound?  same MMAs, plain +bias epilogue (the training step's un-fused form)
+    from diffnorm_b200.ops import GemmPlan
+    tiles = C // 128
+    bi = torch.stack([lv.bias.view(G, tiles, 128), lv.bias2.view(G, tiles, 128)], dim=2).reshape(-1).contiguous()
+    plain = GemmPlan(lv.W, lv.segs, 2 * C, tiles, _lib.EPI_BF16, bias=bi, groups=G, g_w_row=lv.g_w_row, g_bias=2 * C, dilation=1,
+                     dilation_shl_group=1, name="wn.plain")
+    compare("wavenet level, +bias only", plain, y, (M, G * 2 * C), bf16, B, T, iters=10, g_a_col=C, g_out_col=2 * C)
+    nob = GemmPlan(lv.W, lv.segs, 2 * C, tiles, _lib.EPI_BF16, bias=None, groups=G, g_w_row=lv.g_w_row, g_bias=2 * C, dilation=1,
+                   dilation_shl_group=1, name="wn.nobias")
+    compare("wavenet level, no bias", nob, y, (M, G * 2 * C), bf16, B, T, iters=10, g_a_col=C, g_out_col=2 * C)
