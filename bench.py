@@ -267,7 +267,9 @@ def run_ours(args):
                     "frac": ach / peaks["sustained"], "traffic": NCU_CONV_DRAM_BYTES if (B, T, z) == (64, 1000, 16) else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one ncu --set "
                                       "full capture (profiles/r01_u1_gemm_layer_ncu_summary.txt); algorithmic A + out = 360 MB",
-                    "peak_source": peaks["source"] + " sustained bf16",
+                    "peak_source": peaks["source"] + " sustained bf16 (the launches are timed back to back inside one denoiser "
+                                   "call right after the timed passes, i.e. under the same power-capped clocks)",
+                    "frac_of_burst_peak": ach / peaks["burst"], "burst_peak": peaks["burst"],
                     "launch_ms": conv_ms, "launches_timed": len(conv),
                     "transformer_gemm_ms_per_call": all_gemm_ms,
                     "whole_pass_tflops": fpf * B * T / (ms * 1e-3) / 1e12,

@@ -1,8 +1,9 @@
 // dn_attention: flash-style non-causal multi-head attention with key-padding mask.
 // Replaces Attend.forward (LM:299-343) + the head split/merge of Attention.forward (LM:945-949): no N x N
 // matrix is ever written to HBM (the reference materialises [B, 8, N, N] fp32 per layer).
-// Round-1 implementation: 64-query x 64-key tiles, bf16 mma.sync.m16n8k16 with fp32 accumulation and online
-// softmax in registers (exp2 domain), cp.async double-buffered K/V.  (tcgen05/TMEM version: see DESIGN.md roadmap.)
+// This file: the mma.sync form (64-query x 64-key tiles, bf16 m16n8k16 with fp32 accumulation, online softmax in
+// registers in the exp2 domain, cp.async double-buffered K/V) used for the VAE decoder's dh = 96 heads (once per pass)
+// and as the A/B reference of the tcgen05/TMEM kernel in attention_tc.cu, which serves the denoiser's dh = 64 heads.
 #include <stdlib.h>
 
 #include "common.cuh"

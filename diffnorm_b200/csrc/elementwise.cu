@@ -333,11 +333,24 @@ linear_f32_kernel(const float* __restrict__ in, const float* __restrict__ W, con
 #pragma unroll
         for (int i = 0; i < LIN_MB; ++i) acc[i] = 0.f;
         const float* wr = W + (long long)n * K;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = __ldg(wr + k);
+        if ((K & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(in)) & 15) == 0) {
+            // 16-byte loads: the weight row streams from HBM once per 8 outputs, the 8 input rows come from L1
+            for (int k = lane * 4; k < K; k += 128) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
 #pragma unroll
-            for (int i = 0; i < LIN_MB; ++i)
-                if (m0 + i < M) acc[i] += wv * in[(long long)(m0 + i) * K + k];
+                for (int i = 0; i < LIN_MB; ++i)
+                    if (m0 + i < M) {
+                        const float4 xv = *reinterpret_cast<const float4*>(in + (long long)(m0 + i) * K + k);
+                        acc[i] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+                    }
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) {
+                const float wv = __ldg(wr + k);
+#pragma unroll
+                for (int i = 0; i < LIN_MB; ++i)
+                    if (m0 + i < M) acc[i] += wv * in[(long long)(m0 + i) * K + k];
+            }
         }
 #pragma unroll
         for (int i = 0; i < LIN_MB; ++i) {
