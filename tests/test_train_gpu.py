@@ -261,13 +261,14 @@ def test_plugin_forward_backward_through_autograd():
     assert abs(float(ev["total_loss"]) - 0.904014) < 2e-2 * 0.904014   # the oracle's no-dropout loss for this case
 
 
-def test_vae_train_step_against_oracle_autograd():
+@pytest.mark.parametrize("z,wseed", [(16, 4), (128, 6)])
+def test_vae_train_step_against_oracle_autograd(z, wseed):
     """VAE training: SpeechVAEEncoderDecoder.forward -> (mse, lm_pred, kl) and the gradients of the criterion's
     loss 0.1 LS-NLL/ntokens + 10 mse + 1e-4 kl w.r.t. all 274 VAE tensors, vs the oracle's autograd (pinned to the reference)."""
     import torch.nn.functional as F
     from diffnorm_b200.plugin.latent_module import SpeechVAEEncoderDecoder
     from diffnorm_b200.train_vae import VaeTrainer
-    z, wseed, B, T, lengths, dseed, drop_p = 16, 4, 2, 24, [24, 15], 31, 0.1
+    B, T, lengths, dseed, drop_p = 2, 24, [24, 15], 31, 0.1
     arch = O.Arch(latent_dim=z)
     sd = O.init_state_dict(arch, seed=wseed, gains=O.PARITY_GAINS)
     vae = SpeechVAEEncoderDecoder(768, z)
@@ -333,3 +334,34 @@ def test_vae_plugin_criterion_backward():
     with torch.no_grad():
         loss_eval, _, _ = crit(model, sample)
     assert torch.isfinite(loss_eval)
+
+
+@pytest.mark.parametrize("z", [32, 128])
+def test_other_latent_dims_inference_and_training(z):
+    """latent_dim 32 / 128 (LM:1044-1051 chan_mults; 128 is the only value the reference's scripts deploy): one denoiser
+    call + decode vs the oracle, and the training step's loss + gradients vs the oracle's autograd."""
+    B, T, lengths, times = 2, 24, [24, 13], [61, 120]
+    arch, sd, ldm = _build(z, 5)
+    audio, units, mask, eps_vae, eps0, eps, keeps = O.train_case_inputs(z, B, T, lengths, 41, 0.1)
+    eng = ldm._engine()
+    lens = torch.tensor(lengths, dtype=i32, device=DEV)
+    x = torch.randn(B, T, z, generator=torch.Generator().manual_seed(3))
+    tt = torch.tensor(times)
+    want = O.denoiser(sd, arch, x, torch.full((B,), 77), mask)
+    got = eng.denoise(eng.stage_latent(x.to(DEV)), lens, B, T, torch.tensor([77], dtype=i32, device=DEV)).view(B, T, -1)[..., :z].cpu()
+    assert float((got - want)[mask].abs().max()) <= 5e-2 * float(want[mask].std()) + 2e-2
+    rec_w, log_w = O.vae_decode(sd, arch, x, mask)
+    rec_g, log_g = eng.decode(eng.stage_latent(x.to(DEV)), lens, B, T)
+    assert float((log_g.cpu()[..., :arch.vocab] - log_w)[mask].abs().max()) <= 5e-2 * float(log_w[mask].std())
+    keys = [k for k in sd if k.startswith("model.") and sd[k].is_floating_point() and "pos_embed" not in k]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    ref = O.train_loss(sd, arch, audio, units, mask, tt, eps_vae, eps0, eps, keeps, 0.1, False)
+    ref["total_loss"].backward()
+    out, grads = DenoiserTrainer(ldm, drop_p=0.1).step(audio.to(DEV), units.to(DEV), lens, times=tt, noise={"vae": eps_vae, "eps0": eps0, "eps": eps},
+                                                        keep_bits=[pack_keep_bits(k).to(DEV) for k in keeps])
+    assert abs(float(out["noise_loss"]) - float(ref["noise_loss"])) <= 2e-2 * float(ref["noise_loss"]) + 1e-4
+    num = sum(float((grads[k[6:]].cpu().reshape(sd[k].shape).double() - sd[k].grad.double()).pow(2).sum()) for k in keys)
+    den = sum(float(sd[k].grad.double().pow(2).sum()) for k in keys)
+    print(f"[parity] z={z}: training grads global rel err {np.sqrt(num / den):.3e}")
+    assert np.sqrt(num / den) < 4e-2
