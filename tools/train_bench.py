@@ -32,6 +32,57 @@ def train_flops_per_frame(z, n):
     return 2.0 * (3 * (d - 12_288 * n) + 3.5 * 12_288 * n + venc + vdec)
 
 
+def vae_bench(a, vae, dev, rank, world, red):
+    """VAE training step: forward, the criterion's arithmetic on the returned logits (plain torch, as fairseq's criterion
+    does), CUDA backward of all 274 tensors, gradient all-reduce."""
+    import torch.nn.functional as F
+    from diffnorm_b200.train_vae import VaeTrainer
+    B, T = a.batch, a.frames
+    tr = VaeTrainer(vae, drop_p=0.1, seed=rank)
+    g = torch.Generator().manual_seed(1234 + rank)
+    audio = torch.randn(B, T, 768, generator=g).to(dev)
+    units = (torch.randint(0, 1000, (B, T), generator=g) + 4).to(dev).view(-1)
+    lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    ntok = B * T
+
+    def step():
+        mse, logits, kl = tr.forward(audio, lens)
+        lg = logits.detach().requires_grad_(True)
+        lp = F.log_softmax(lg, dim=-1).view(-1, lg.shape[-1])
+        nll = -lp.gather(1, units[:, None]).sum()
+        smooth = -lp.sum()
+        e = 0.1 / (lp.shape[-1] - 1)
+        (0.1 * ((1 - 0.1 - e) * nll + e * smooth) / ntok).backward()
+        tr.backward(10.0, lg.grad, 1e-4, grad_hook=red.hook)
+        return mse, red.finish()
+
+    for _ in range(a.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        mse, grads = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"config": "vae_train_step", "metric": "training frames/sec", "value": B * T * world / (ms * 1e-3),
+                          "unit": "frames/s", "n_gpus": world, "steps": a.steps, "ms_per_step": ms, "mse": float(mse),
+                          "workload": f"VAE training step, {B} x {T} frames per GPU, z {a.latent_dim}, dropout 0.1, fwd + bwd + grad all-reduce",
+                          "grad_bytes_allreduced": sum(v.numel() for v in grads.values()) * 4}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=12)
@@ -40,6 +91,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--phases", action="store_true", help="print host/device time of packing, forward, backward (1 GPU)")
+    ap.add_argument("--model", default="denoiser", choices=["denoiser", "vae"],
+                    help="vae: the VAE training step (scripts/vae/train.sh, --max-tokens 15000: use --batch 15)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -54,6 +107,8 @@ def main():
     ldm = LatentDiscreteModel(vae, 512, z, timesteps=200, multitask=False).to(dev).train()
     tr = DenoiserTrainer(ldm, drop_p=0.1, seed=rank)
     red = GradAllReducer()
+    if a.model == "vae":
+        return vae_bench(a, ldm.speech_decoder, dev, rank, world, red)
     g = torch.Generator().manual_seed(1234 + rank)
     audio = torch.randn(B, T, 768, generator=g).to(dev)
     units = (torch.randint(0, 1000, (B, T), generator=g) + 4).to(dev)
