@@ -43,6 +43,39 @@ class _Plans:
     pass
 
 
+class ZeroArena:
+    """Gradient storage of one training step: views into a few large fp32 buffers that are cleared with ONE memset per
+    buffer at the start of backward (a step hands out ~600 accumulators; clearing them one by one was 600 fill launches).
+    Views stay valid until the next step's `reset()`."""
+
+    def __init__(self, device, chunk_elems: int = 1 << 26):
+        self.dev, self.chunk_elems = device, chunk_elems
+        self.chunks, self.used = [], []
+        self.cur = 0
+
+    def reset(self):
+        for c, u in zip(self.chunks, self.used):
+            if u:
+                c[:u].zero_()
+        self.used = [0] * len(self.chunks)
+        self.cur = 0
+
+    def zeros(self, *shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        need = (n + 3) & ~3                       # keep every view 16-byte aligned (TMA / float4)
+        while True:
+            if self.cur == len(self.chunks):
+                self.chunks.append(torch.zeros(max(self.chunk_elems, need), dtype=f32, device=self.dev))
+                self.used.append(0)
+            c, u = self.chunks[self.cur], self.used[self.cur]
+            if u + need <= c.numel():
+                self.used[self.cur] = u + need
+                return c[u:u + n].view(*shape)
+            self.cur += 1
+
+
 class _GradDict(dict):
     """name -> gradient; tells the data-parallel reducer about every gradient the moment it is final."""
 
@@ -93,8 +126,8 @@ class VaeBlocksTrain:
     """Training-mode execution of VAE WaveNet blocks (encoder or decoder side): un-fused forward keeping the pre-gate
     pairs, data-gradient backward, and (when `grads` is given) the weight / bias gradients of every conv in the block."""
 
-    def __init__(self, buf, G: int, S: int, tag: str):
-        self.buf, self.G, self.S, self.tag = buf, G, S, tag
+    def __init__(self, buf, G: int, S: int, tag: str, zeros=None):
+        self.buf, self.G, self.S, self.tag, self.zeros = buf, G, S, tag, zeros
         self.sv: Dict[object, object] = {}
 
     def forward(self, blocks, a, B, T, x_out=None):
@@ -127,7 +160,7 @@ class VaeBlocksTrain:
         buf, G, S, tag, sv = self.buf, self.G, self.S, self.tag, self.sv
         M = B * T
         dev = dcur.device
-        zeros = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
+        zeros = self.zeros or (lambda *shape: torch.zeros(*shape, dtype=f32, device=dev))
         for i in reversed(range(len(blocks))):
             b = blocks[i]
             cp, c, cin, p = b.cp, b.cout, b.cin, b.p
@@ -191,8 +224,9 @@ class FrozenDecoderTrain:
     data-gradient backward down to the latent, and optionally (VAE training) every weight gradient.  Inside a multitask
     diffusion step the VAE is frozen (diff_discrete.py:79-81): packed once, no dropout, no weight gradients."""
 
-    def __init__(self, sd: Optional[Dict[str, torch.Tensor]], cfg: DiffNormConfig, dev, buf, pre: str = "speech_decoder."):
-        self.cfg, self.dev, self.buf = cfg, dev, buf
+    def __init__(self, sd: Optional[Dict[str, torch.Tensor]], cfg: DiffNormConfig, dev, buf, pre: str = "speech_decoder.",
+                 zeros=None):
+        self.cfg, self.dev, self.buf, self.zeros = cfg, dev, buf, zeros
         c = cfg
         self.zp = rup(c.latent_dim, 64)
         self.D, self.H, self.dh = c.feat_dim, c.vae_heads, c.vae_dim_head
@@ -200,7 +234,7 @@ class FrozenDecoderTrain:
         self.ip = rup(self.inner, 128)
         self.vl = rup(c.vocab, 64)                 # dlogits row width (K of the lm-head data gradient)
         self.G, self.S = c.vae_layers, c.vae_stacks
-        self.wn = VaeBlocksTrain(buf, self.G, self.S, "v")
+        self.wn = VaeBlocksTrain(buf, self.G, self.S, "v", zeros)
         rm = geglu_row_map(self.inner)
         self.geglu_src, self.geglu_dst = torch.nonzero(rm >= 0).squeeze(1).to(dev), rm[rm >= 0].to(dev)
         self.sv: Dict[object, object] = {}
@@ -277,7 +311,7 @@ class FrozenDecoderTrain:
         buf, sv, c = self.buf, self.sv, self.cfg
         M, D, H, dh, ip, inner = B * T, self.D, self.H, self.dh, self.ip, self.inner
         dev = dlogits.device
-        zeros = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
+        zeros = self.zeros or (lambda *shape: torch.zeros(*shape, dtype=f32, device=dev))
         wg = None
         if grads is not None:
             def wg(dY, X, n_rows, k_cols, shift=0):
@@ -376,6 +410,7 @@ class DenoiserTrainer:
         self._pack_graph = None
         self._pack_plans = None
         self._pack_ptrs = None
+        self.arena = ZeroArena(self.dev)
         self.dec = FrozenDecoderTrain(sd, self.cfg, self.dev, self.buf) if self.multitask else None
 
     # ------------------------------------------------------------------------------------------------ helpers
@@ -606,7 +641,8 @@ class DenoiserTrainer:
 
         # ================================================================================================ backward
         grads: Dict[str, torch.Tensor] = _GradDict(grad_hook)
-        zeros = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
+        self.arena.reset()
+        zeros = self.arena.zeros          # gradient tensors are views into the arena: valid until the next step
 
         def wg(dY, X, n_rows, k_cols, dy_col0=0, x_col0=0, shift=0, flat=True):
             dW = zeros(n_rows, rup(k_cols, 4))

@@ -15,7 +15,7 @@ import torch
 from . import ops
 from .config import DiffNormConfig
 from .packing import rup
-from .train import FrozenDecoderTrain, VaeBlocksTrain, _GradDict, _pack_vae_wavenet
+from .train import FrozenDecoderTrain, VaeBlocksTrain, ZeroArena, _GradDict, _pack_vae_wavenet
 
 bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
 
@@ -32,8 +32,9 @@ class VaeTrainer:
         self.ws: Dict[tuple, torch.Tensor] = {}
         c = self.cfg
         self.G, self.S = c.vae_layers, c.vae_stacks
-        self.enc = VaeBlocksTrain(self.buf, self.G, self.S, "e")
-        self.dec = FrozenDecoderTrain(None, c, self.dev, self.buf)
+        self.arena = ZeroArena(self.dev)
+        self.enc = VaeBlocksTrain(self.buf, self.G, self.S, "e", self.arena.zeros)
+        self.dec = FrozenDecoderTrain(None, c, self.dev, self.buf, zeros=self.arena.zeros)
         self._pack_graph, self._pack_ptrs, self.enc_blocks = None, None, None
         self.ctx = None
 
@@ -117,6 +118,7 @@ class VaeTrainer:
         B, T, lens = cx["B"], cx["T"], cx["lens"]
         M, z = B * T, c.latent_dim
         grads = _GradDict(grad_hook)
+        self.arena.reset()                # gradient tensors are views into the arena: valid until the next backward
         dlogits = self.buf("v.dlogits", M, self.dec.vl, zero=g_logits is None)
         if g_logits is not None:
             ops.cast_pad_bf16(g_logits.float().contiguous().view(M, -1), self.dec.vl, out=dlogits)
