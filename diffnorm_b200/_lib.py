@@ -59,6 +59,13 @@ class WgradDesc(C.Structure):
     ]
 
 
+class ResidNormDesc(C.Structure):
+    _fields_ = [
+        ("M", i32), ("A", vp), ("lda", i32), ("k_blocks", i32), ("W", vp), ("ldw", i32), ("bias", vp), ("x", vp), ("hb", vp),
+        ("gamma_p", vp), ("gb", vp), ("gb_t_stride", i64), ("t_idx", vp),
+    ]
+
+
 EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_WN_GATE = range(5)
 GEMM_TCGEN05, GEMM_SIMT_CHECK, GEMM_TCGEN05_2CTA = 0, 1, 2
 
@@ -83,6 +90,7 @@ _SIGS = {
     "dn_attention": [vp, vp, vp, i32, i32, i32, i32, vp],
     # training step
     "dn_wgrad": [C.POINTER(WgradDesc), vp],
+    "dn_gemm_resid_norm": [C.POINTER(ResidNormDesc), vp],
     "dn_colsum_bf16": [vp, i64, i32, i32, i32, vp, vp],
     "dn_geglu_fwd": [vp, i64, i32, vp, vp],
     "dn_geglu_bwd": [vp, vp, i64, i32, vp, vp],

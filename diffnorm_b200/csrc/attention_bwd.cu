@@ -152,7 +152,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                    float scale, float scale_log2) {
     constexpr int OP = AbCfg<DH>::OP;
     extern __shared__ uint8_t ab_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = ab_smem_raw + ((1024u - (smem_u32(ab_smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS
     uint8_t* sQ = smem;                     // resident: Q tile, dO tile
     uint8_t* sDO = smem + OP;
     uint8_t* sStage = smem + 2 * OP;        // 2 stages x (K, V)
@@ -311,7 +311,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     // strictly one after the other.
     constexpr bool EARLY = DH == 64;
     extern __shared__ uint8_t ab_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = ab_smem_raw + ((1024u - (smem_u32(ab_smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS
     uint8_t* sK = smem;                     // resident: K tile, V tile
     uint8_t* sV = smem + OP;
     uint8_t* sStage = smem + 2 * OP;        // 2 stages x (Q, dO)

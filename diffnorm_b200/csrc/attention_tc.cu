@@ -47,7 +47,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                     const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2,
                     const uint32_t* __restrict__ keep, float keep_scale) {
     extern __shared__ uint8_t ta_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ta_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = ta_smem_raw + ((1024u - (smem_u32(ta_smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS
     uint8_t* sQ = smem;
     uint8_t* sK = smem + TA_TILE;      // two stages
     uint8_t* sV = smem + 3 * TA_TILE;  // two stages

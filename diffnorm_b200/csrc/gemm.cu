@@ -69,7 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int STAGE_BYTES = Ring<CTAS>::STAGE_BYTES;
     static_assert(STAGES * STAGE_BYTES == 4 * (A_BYTES + B_BYTES), "both ring forms use the same 192 KB");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ CUtensorMap tmOut, const WgParams p) {
     extern __shared__ uint8_t wg_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = wg_smem_raw + ((1024u - (smem_u32(wg_smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + WG_STAGES;

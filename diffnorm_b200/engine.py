@@ -8,6 +8,8 @@ transposes anywhere (the reference flips between [B,C,T] and [B,T,C] around ever
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -61,6 +63,8 @@ class DiffNormEngine:
         self.cfg = cfg or DiffNormConfig.from_state_dict(sd)
         self.dev = torch.device(device)
         self.ws: Dict[tuple, torch.Tensor] = {}
+        # residual GEMM + following adaptive RMSNorm in one kernel (dn_gemm_resid_norm); DN_FUSE_NORM=0 keeps the pair
+        self.fuse_norm = os.environ.get("DN_FUSE_NORM", "0") == "1"
         self.gemm_impl = None   # None = automatic (CTA-pair kernel when the launch has >= 74 pair tiles); tests force others
         self._graphs: Dict[tuple, object] = {}
         self._graph_kernels: Dict[tuple, int] = {}
@@ -260,13 +264,29 @@ class DiffNormEngine:
         return out
 
     def _transformer(self, layers, ip, x, B, T, dim, heads, dh, lengths, tag, cond_layer0=None, t_idx=None,
-                     t_idx_stride=0):
+                     t_idx_stride=0, final_gamma=None):
         M = B * T
         hb = self.buf(tag + ".h", M, dim)
         qkv = self.buf(tag + ".qkv", M, 3 * heads * dh)
         ao = self.buf(tag + ".ao", M, heads * dh)
         m1 = self.buf(tag + ".m1", M, ip)
         m2 = self.buf(tag + ".m2", M, ip)
+        if final_gamma is not None:
+            # row-complete fused form (shared timestep, width 512): every residual GEMM also writes the next norm's output
+            def cond(i):
+                return self.table_flat[(cond_layer0 + i) * self.gb_w:]
+            ops.adarmsnorm(x, hb, B, T, None, cond(0), self.gb_t_stride, t_idx, 0)
+            for l, L in enumerate(layers):
+                self._run(L.qkv, hb, qkv, B, T)
+                ops.attention(qkv, ao, lengths, B, T, heads, dh)
+                ops.gemm_resid_norm(L.out, ao, x, hb, None, cond(2 * l + 1), self.gb_t_stride, t_idx)
+                self._run(L.ff1, hb, m1, B, T)
+                self._run(L.ffc, m1, m2, B, T)
+                if l + 1 < len(layers):
+                    ops.gemm_resid_norm(L.ff3, m2, x, hb, None, cond(2 * l + 2), self.gb_t_stride, t_idx)
+                else:
+                    ops.gemm_resid_norm(L.ff3, m2, x, hb, final_gamma)
+            return x
         for l, L in enumerate(layers):
             for which in (0, 1):
                 if cond_layer0 is not None:
@@ -294,10 +314,13 @@ class DiffNormEngine:
         x = self.buf("d.x", M, c.hid, f32)
         self._wavenet(self.d_wn, h0, x, B, T, "d.wn", gb_layer0=0, t_idx=t_idx, t_idx_stride=t_idx_stride,
                       pe=self.pe_table(T), lengths=lengths)
+        fuse = self.fuse_norm and t_idx_stride == 0 and c.hid == 512
         self._transformer(self.d_layers, self.d_ip, x, B, T, c.hid, c.heads, c.dim_head, lengths, "d.tf",
-                          cond_layer0=c.wn_stacks * c.wn_layers, t_idx=t_idx, t_idx_stride=t_idx_stride)
+                          cond_layer0=c.wn_stacks * c.wn_layers, t_idx=t_idx, t_idx_stride=t_idx_stride,
+                          final_gamma=self.d_pred_gamma if fuse else None)
         hb = self.buf("d.tf.h", M, c.hid)
-        ops.adarmsnorm(x, hb, B, T, self.d_pred_gamma)
+        if not fuse:
+            ops.adarmsnorm(x, hb, B, T, self.d_pred_gamma)
         pb = self.buf("d.pred", M, c.hid)
         self._run(self.d_pred, hb, pb, B, T)
         eh = self.buf("d.eps", M, self.zn, f32)

@@ -234,6 +234,19 @@ class GemmPlan:
         return out
 
 
+def gemm_resid_norm(plan: GemmPlan, A, x, hb, gamma_p=None, gb=None, gb_t_stride: int = 0, t_idx=None):
+    """x += A W^T + bias and hb = adaptive-RMSNorm(x) in one kernel (dn_gemm_resid_norm): `plan` is a plain
+    EPI_RESID linear of width 512; gb / t_idx select ONE table row for the whole batch (shared timestep)."""
+    _chk(A, bf16, "A"), _chk(x, f32, "x"), _chk(hb, bf16, "hb")
+    assert plan.n_out == 512 and x.shape[-1] == 512 and hb.shape[-1] == 512 and plan._flat_ok and len(plan.segs) == 1
+    d = _lib.ResidNormDesc()
+    d.M, d.A, d.lda, d.k_blocks = x.shape[0], _p(A), A.shape[-1], plan.segs[0][2]
+    d.W, d.ldw, d.bias, d.x, d.hb = _p(plan.W), plan.W.shape[1], _p(plan.bias), _p(x), _p(hb)
+    d.gamma_p, d.gb, d.gb_t_stride, d.t_idx = _p(gamma_p), _p(gb), gb_t_stride, _p(t_idx)
+    check(lib.dn_gemm_resid_norm(C.byref(d), _stream()), f"dn_gemm_resid_norm[{plan.name}]")
+    return x
+
+
 # ------------------------------------------------------------------------------------------------ training step
 def wgrad(dY, X, dW, B: int, T: int, n_rows: int, k_cols: int, dy_col0: int = 0, x_col0: int = 0, shift: int = 0,
           splits: int = 0, groups: int = 1, g_dy_col: int = 0, g_x_col: int = 0, shift_shl_group: bool = False):

@@ -104,6 +104,24 @@ int dn_advance_step(int32_t* t_idx, int32_t delta, void* stream);
 int dn_adarmsnorm(const float* x, void* out, int32_t B, int32_t T, int32_t C, const float* gamma_p, const float* gb,
                   int64_t gb_t_stride, const int32_t* t_idx, int32_t t_idx_stride, void* stream);
 
+/* Residual GEMM fused with the adaptive RMSNorm that follows it in the transformer block (LM:692 -> :629-639 of the
+ * next sub-layer; LM:704 -> the next layer's first norm / the final to_pred norm), hidden width C = 512 only:
+ *     x[m, :] += A[m, :] W^T + bias ;   hb[m, :] = bf16(adaptive-RMSNorm(x[m, :]))        in one pass over x.
+ * A bf16 [M, lda] (k_blocks*64 columns used), W bf16 [512, ldw] (K-major, as dn_gemm packs it), bias fp32 [512] or null,
+ * x fp32 [M, 512] in/out, hb bf16 [M, 512] out.  gamma_p / gb as in dn_adarmsnorm, with ONE table row for the whole batch
+ * (gb + t_idx[0] * gb_t_stride: the sampler's shared timestep); per-utterance timesteps use the un-fused pair. */
+typedef struct {
+    int32_t M;
+    const void* A; int32_t lda; int32_t k_blocks;
+    const void* W; int32_t ldw;
+    const float* bias;
+    float* x;
+    void* hb;
+    const float* gamma_p;
+    const float* gb; int64_t gb_t_stride; const int32_t* t_idx;
+} dn_resid_norm_desc;
+int dn_gemm_resid_norm(const dn_resid_norm_desc* d, void* stream);
+
 /* Stand-alone WaveNet gate (LM:524-533): y = tanh(u') * sigmoid(u') + res, u' = u * gamma + beta (gb optional).
  * u, res, y bf16 [B*T, C].  (The denoiser path uses the same math fused into dn_gemm's epilogue.) */
 int dn_wavenet_gate(const void* u, const void* res, void* y, int32_t B, int32_t T, int32_t C, const float* gb,
