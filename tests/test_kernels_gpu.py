@@ -358,6 +358,42 @@ def test_gemm_persistent_many_tiles():
     torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("M,K,bias,cond", [(128, 512, False, True), (1000, 512, False, True), (12000, 1365, True, True),
+                                           (777, 1365, True, False), (40000, 512, True, True)])
+def test_gemm_resid_norm_matches_unfused_pair(M, K, bias, cond):
+    """dn_gemm_resid_norm (2-CTA cluster, DSMEM row-sum exchange) against EPI_RESID dn_gemm + dn_adarmsnorm: the
+    residual stream bit-identical (same (acc + bias) + x order), the normalised bf16 operand within one bf16 ulp (the
+    row sum of squares is formed in a different order).  Sizes cover one tile, ragged last tiles, > 74 clusters' worth
+    of tiles (several tiles per cluster: ring wrap-around, both accumulators, the 4-deep partial-sum slots)."""
+    W = rnd(512, K, seed=M + 1, scale=K ** -0.5)
+    b = rnd(512, seed=M + 2) if bias else None
+    plan = packing.pack_linear(W.cpu(), None if b is None else b.cpu(), epi=_lib.EPI_RESID, name="t").to(DEV)
+    A = torch.zeros(M, plan.W.shape[1], dtype=torch.bfloat16, device=DEV)
+    A[:, :K] = rnd(M, K, seed=M + 3).bfloat16()
+    x0 = rnd(M, 512, seed=M + 4, scale=3.0)
+    table = rnd(7, 1024, seed=M + 5)
+    table[:, :512] += 1.0
+    t_idx = torch.tensor([3], dtype=torch.int32, device=DEV)
+    gp = rnd(512, seed=M + 6, scale=0.1) + 1
+    x1, x2 = x0.clone(), x0.clone()
+    h1 = torch.zeros(M, 512, dtype=torch.bfloat16, device=DEV)
+    h2 = torch.zeros_like(h1)
+    plan.run(A, x1, 1, M)
+    if cond:
+        ops.adarmsnorm(x1, h1, 1, M, None, table, 1024, t_idx, 0)
+        ops.gemm_resid_norm(plan, A, x2, h2, None, table, 1024, t_idx)
+    else:
+        ops.adarmsnorm(x1, h1, 1, M, gp)
+        ops.gemm_resid_norm(plan, A, x2, h2, gp)
+    torch.cuda.synchronize()
+    assert torch.equal(x1, x2)
+    d = (h1.float() - h2.float()).abs()
+    assert bool((d <= h1.float().abs() * 2 ** -7 + 1e-6).all()), f"max |dh| {d.max().item()}"
+    # and the pair itself against fp32 torch (tolerance of a bf16-operand GEMM)
+    want = x0 + A[:, :K].float() @ W.bfloat16().float().T + (0 if b is None else b)
+    torch.testing.assert_close(x2, want, rtol=2e-2, atol=2e-2)
+
+
 def test_kmeans_quantizer_matches_sklearn_and_oracle():
     """dn_split_bf16x3 + dn_gemm (K = 3 x 768) + dn_argmax_units vs scikit-learn's labels (golden) and the float64 oracle.
     Bar: identical labels wherever the float64 top-2 squared-distance gap exceeds 1e-3 (near-ties below that are within

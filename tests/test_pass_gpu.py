@@ -108,6 +108,32 @@ def test_stages_and_pass_against_golden(name):
             assert out["index_to_keep"][b, :r].cpu().tolist() == kp
 
 
+def test_fused_resid_norm_denoiser_call_matches_unfused():
+    """engine.fuse_norm (dn_gemm_resid_norm in the transformer stack) against the default un-fused stack on the same
+    denoiser call: eps_hat within the bf16 rounding noise of the stack (hb differs by <= 1 bf16 ulp per norm)."""
+    g, arch, sd, eng = setup_case("pass_z16_parity")
+    t = lambda k: torch.from_numpy(g[k])
+    B, T, _ = t("feat").shape
+    lens = torch.from_numpy(g["lengths"]).to(torch.int32).to(DEV)
+    mask_cpu = O.lengths_to_mask(torch.from_numpy(g["lengths"]), T)
+    xb = eng.stage_latent(t("x_start").to(DEV))
+    t_idx = torch.tensor([int(g["start_step"]) - 1], dtype=torch.int32, device=DEV)
+    was = eng.fuse_norm
+    try:
+        eng.fuse_norm = False
+        a = eng.denoise(xb, lens, B, T, t_idx).clone()
+        eng.fuse_norm = True
+        b = eng.denoise(xb, lens, B, T, t_idx).clone()
+    finally:
+        eng.fuse_norm = was
+    z = arch.latent_dim
+    a, b = a.view(B, T, -1)[..., :z].cpu()[mask_cpu], b.view(B, T, -1)[..., :z].cpu()[mask_cpu]
+    d = stats("eps fused vs unfused", b, a)
+    assert d.max() <= 2e-2 * a.std() + 5e-3
+    want = t("eps_first")[mask_cpu]
+    assert (b - want).abs().max() <= 5e-2 * want.std() + 2e-2
+
+
 def test_sampler_variants_against_reference_generic_lib():
     """Config-3 samplers: ancestral DDPM (fixed-small / fixed-large variance) and strided DDIM against outputs of the
     reference's generic diffusion lib (gaussian_diffusion.py p_sample / ddim_sample + respace.SpacedDiffusion) minted

@@ -1,4 +1,7 @@
-"""Wait-cycle profile of dn_gemm_resid_norm (needs the library built with -DRN_PROFILE; debugging aid)."""
+"""Wait-cycle profile of dn_gemm_resid_norm (debugging aid).  Needs the instrumented build of that one file:
+    cd diffnorm_b200/csrc && nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
+        -DRN_PROFILE -c gemm_rownorm.cu -o gemm_rownorm.o && make      # relinks; `touch gemm_rownorm.cu && make` undoes it
+Output of the round-1 runs: profiles/r01_rn_resid_norm_wait_cycles.txt."""
 import ctypes as C
 import os
 import sys
