@@ -65,6 +65,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     float* xmax = reinterpret_cast<float*>(bars + 16);   // [2 parities][2 halves][128 rows] partial row maxima
     float* lsum = xmax + 4 * TA_BM;                      // [2 halves][128 rows] partial row sums
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * TA_BM, h = blockIdx.y, b = blockIdx.z;
     int len = lengths ? lengths[b] : T;
@@ -95,6 +96,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();       // qkv comes from the kernel before (lengths, read above, is an input of the whole pass)
     // TMEM columns: S fp32 [0,128) | O fp32 [128,192) | P bf16x2 [192,256) (two keys per 32-bit column)
     const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
 
@@ -318,11 +320,11 @@ int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int 
     dim3 grid((T + TA_BM - 1) / TA_BM, H, B);
     const float scale_log2 = (1.0f / sqrtf((float)TA_DH)) * 1.4426950408889634f;
     if (train)
-        attention_tc_kernel<true><<<grid, TA_THREADS, TA_SMEM, st>>>(m, reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H,
-                                                                    scale_log2, lse2, keep, keep_scale);
+        DN_CUDA_OK(launch_ex(attention_tc_kernel<true>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
+                             lengths, T, H, scale_log2, lse2, keep, keep_scale));
     else
-        attention_tc_kernel<false><<<grid, TA_THREADS, TA_SMEM, st>>>(m, reinterpret_cast<__nv_bfloat16*>(out), lengths, T,
-                                                                     H, scale_log2, nullptr, nullptr, 1.f);
+        DN_CUDA_OK(launch_ex(attention_tc_kernel<false>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
+                             lengths, T, H, scale_log2, (float*)nullptr, (const uint32_t*)nullptr, 1.f));
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

@@ -19,6 +19,37 @@ inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
         if (_e != cudaSuccess) return (int)_e;    \
     } while (0)
 
+// Programmatic dependent launch (DN_PDL=1): a kernel launched with the attribute may start while its predecessor in the
+// stream drains; it runs its prologue (barrier init, TMEM alloc, descriptor prefetch) and then blocks in pdl_wait() until
+// the predecessor has completed and flushed.  Without the attribute both instructions are no-ops.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t st, int cluster,
+                             Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = n ? at : nullptr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define DN_LAUNCH_CHECK()                         \
     do {                                          \
         cudaError_t _e = cudaGetLastError();      \
@@ -26,6 +57,9 @@ inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
     } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

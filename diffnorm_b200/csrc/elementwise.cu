@@ -218,6 +218,8 @@ adarmsnorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, 
                   const float* __restrict__ gamma_p, const float* __restrict__ gb, long long gb_t_stride,
                   const int* __restrict__ t_idx, int t_idx_stride) {
     constexpr int V = C / 128;  // float4 per lane
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long rows = (long long)B * T;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -478,11 +480,11 @@ extern "C" int dn_adarmsnorm(const float* x, void* out, int32_t B, int32_t T, in
     const int grid = ew_grid(rows, EW_THREADS / 32);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     switch (C) {
-        case 128: adarmsnorm_kernel<128><<<grid, EW_THREADS, 0, ST(stream)>>>(x, o, B, T, gamma_p, gb, gb_t_stride, t_idx, t_idx_stride); break;
-        case 256: adarmsnorm_kernel<256><<<grid, EW_THREADS, 0, ST(stream)>>>(x, o, B, T, gamma_p, gb, gb_t_stride, t_idx, t_idx_stride); break;
-        case 512: adarmsnorm_kernel<512><<<grid, EW_THREADS, 0, ST(stream)>>>(x, o, B, T, gamma_p, gb, gb_t_stride, t_idx, t_idx_stride); break;
-        case 768: adarmsnorm_kernel<768><<<grid, EW_THREADS, 0, ST(stream)>>>(x, o, B, T, gamma_p, gb, gb_t_stride, t_idx, t_idx_stride); break;
-        case 1024: adarmsnorm_kernel<1024><<<grid, EW_THREADS, 0, ST(stream)>>>(x, o, B, T, gamma_p, gb, gb_t_stride, t_idx, t_idx_stride); break;
+        case 128: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<128>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
+        case 256: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<256>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
+        case 512: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<512>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
+        case 768: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<768>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
+        case 1024: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<1024>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
         default: return DN_EINVAL;
     }
     DN_LAUNCH_CHECK();

@@ -77,6 +77,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tempty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+    pdl_trigger();    // the next kernel may be scheduled onto SMs as this grid's CTAs retire
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
@@ -117,6 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CTAS == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();       // everything above touched only this CTA's smem / TMEM; inputs are read from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -492,6 +494,15 @@ static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, 
     return r == CUDA_SUCCESS ? 0 : DN_EINVAL;
 }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DN_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int num_sms() {
     static int n = 0;
     if (!n) {
@@ -515,23 +526,7 @@ static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorM
     const long long total = (long long)d.groups * d.B * tiles_t * d.n_tiles;
     const int units = num_sms() / CTAS;   // CTAs (or CTA pairs) resident at once
     const int grid = (int)(total < units ? total : units) * CTAS;
-    if (CTAS == 1) {
-        gemm_tc_kernel<EPI, 1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a, w, w128, w64, o, d);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(GEMM_THREADS);
-        cfg.dynamicSmemBytes = GEMM_SMEM;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        DN_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI, 2>, a, w, w128, w64, o, d));
-    }
+    DN_CUDA_OK(launch_ex(gemm_tc_kernel<EPI, CTAS>, grid, GEMM_THREADS, GEMM_SMEM, st, CTAS, a, w, w128, w64, o, d));
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
