@@ -26,10 +26,10 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-# ncu --set full, gemm_tc_kernel<EPI_BF16> on the FFN causal conv at B 64 x T 1000 (profiles/r01_u1_gemm_layer_ncu_summary.txt):
-# dram__bytes_read.sum 192.19 MB + dram__bytes_write.sum 147.37 MB per launch (part of the 180 MB output is still in L2
-# when the kernel ends); algorithmic bytes = 180 MB bf16 A + 180 MB bf16 out + 12 MB weights.
-NCU_CONV_DRAM_BYTES = 192_193_024 + 147_372_032
+# ncu --set full, gemm_tc_kernel<EPI_BF16, 2> on the FFN causal conv at B 64 x T 1000 (profiles/r01_fin_gemm_layer_ncu_summary.txt):
+# dram__bytes_read.sum 192.28 MB + dram__bytes_write.sum 156.20 MB per launch of the CTA-pair kernel (part of the 180 MB
+# output is still in L2 when the kernel ends); algorithmic bytes = 180 MB bf16 A + 180 MB bf16 out + 12 MB weights.
+NCU_CONV_DRAM_BYTES = 192_277_248 + 156_203_776
 
 METRIC = "normalized frames/sec"
 UNIT = "frames/s"
@@ -266,7 +266,7 @@ def run_ours(args):
                     "M=B*T, N=1365, K=4095)", "achieved": ach, "peak": peaks["sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["sustained"], "traffic": NCU_CONV_DRAM_BYTES if (B, T, z) == (64, 1000, 16) else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one ncu --set "
-                                      "full capture (profiles/r01_u1_gemm_layer_ncu_summary.txt); algorithmic A + out = 360 MB",
+                                      "full capture (profiles/r01_fin_gemm_layer_ncu_summary.txt); algorithmic A + out = 360 MB",
                     "peak_source": peaks["source"] + " sustained bf16 (the launches are timed back to back inside one denoiser "
                                    "call right after the timed passes, i.e. under the same power-capped clocks)",
                     "frac_of_burst_peak": ach / peaks["burst"], "burst_peak": peaks["burst"],
