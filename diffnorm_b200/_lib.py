@@ -59,6 +59,16 @@ class WgradDesc(C.Structure):
     ]
 
 
+class PackOp(C.Structure):
+    _fields_ = [
+        ("src", vp), ("dst", vp), ("s_row", i64), ("s_col", i64), ("s_tap", i64),
+        ("rows", i32), ("cols", i32), ("taps", i32), ("ldd", i32),
+        ("row0", i32), ("rblk", i32), ("rblk_stride", i32),
+        ("col0", i32), ("cblk", i32), ("cblk_stride", i32), ("tap_cols", i32),
+        ("tap_pos", i32 * 3), ("src_r_fastest", i32), ("out_f32", i32), ("tile0", i32), ("tiles_c", i32),
+    ]
+
+
 class ResidNormDesc(C.Structure):
     _fields_ = [
         ("M", i32), ("A", vp), ("lda", i32), ("k_blocks", i32), ("W", vp), ("ldw", i32), ("bias", vp), ("x", vp), ("hb", vp),
@@ -91,6 +101,7 @@ _SIGS = {
     # training step
     "dn_wgrad": [C.POINTER(WgradDesc), vp],
     "dn_gemm_resid_norm": [C.POINTER(ResidNormDesc), vp],
+    "dn_pack_weights": [vp, i32, i32, vp],
     "dn_colsum_bf16": [vp, i64, i32, i32, i32, vp, vp],
     "dn_geglu_fwd": [vp, i64, i32, vp, vp],
     "dn_geglu_bwd": [vp, vp, i64, i32, vp, vp],

@@ -13,6 +13,7 @@ Gradients are returned as fp32 tensors keyed like ``Model.named_parameters()``.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -23,6 +24,7 @@ from .config import DiffNormConfig
 from .ops import GemmPlan
 from .packing import (BK, WT, geglu_row_map, pack_conv3, pack_geglu, pack_linear, pack_skip_sum, pack_wavenet_level,
                       pack_wavenet_level_dgrad, rup)
+from .repack import PackTable
 from .schedule import DDPMScheduler
 
 bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
@@ -395,10 +397,7 @@ class DenoiserTrainer:
         self.coef = torch.from_numpy(coef).to(self.dev)
         self.beta0 = float(np.float32(s.betas[0]))
         self.ws: Dict[tuple, torch.Tensor] = {}
-        self.cond_names = [f"wavenet.stacks.{st}.blocks.{i}.to_time_cond" for st in range(c.wn_stacks)
-                           for i in range(c.wn_layers)]
-        for l in range(c.depth):
-            self.cond_names += [f"transformer.layers.{l}.0.to_gamma_beta", f"transformer.layers.{l}.4.to_gamma_beta"]
+        self.cond_names = self.cond_layer_names(c)
         self.n_cond, self.gbw = len(self.cond_names), 2 * c.hid
         self.inner = DiffNormConfig.ff_inner(c.hid)
         self.ip = rup(self.inner, 128)
@@ -408,12 +407,22 @@ class DenoiserTrainer:
         self.zp, self.zn = rup(c.latent_dim, 64), rup(c.latent_dim, 16)
         self._pe: Dict[int, torch.Tensor] = {}
         self._pack_graph = None
+        self._pack_table = None
         self._pack_plans = None
         self._pack_ptrs = None
         self.arena = ZeroArena(self.dev)
         self.dec = FrozenDecoderTrain(sd, self.cfg, self.dev, self.buf) if self.multitask else None
 
     # ------------------------------------------------------------------------------------------------ helpers
+    @staticmethod
+    def cond_layer_names(c: DiffNormConfig) -> List[str]:
+        """The time-conditioned layers in table order: WaveNet blocks (LM:500-507), then per transformer layer the two
+        adaptive norms (LM:666-674)."""
+        names = [f"wavenet.stacks.{st}.blocks.{i}.to_time_cond" for st in range(c.wn_stacks) for i in range(c.wn_layers)]
+        for l in range(c.depth):
+            names += [f"transformer.layers.{l}.0.to_gamma_beta", f"transformer.layers.{l}.4.to_gamma_beta"]
+        return names
+
     def buf(self, name: str, rows: int, width: int, dtype=bf16, zero: bool = False) -> torch.Tensor:
         key = (name, width, dtype)
         t = self.ws.get(key)
@@ -429,76 +438,129 @@ class DenoiserTrainer:
         return plan.run(A, out, B, T, **kw)
 
     # ------------------------------------------------------------------------------------------------ packing (per step)
-    def _pack(self) -> _Plans:
+    def _pack(self, rec=None) -> _Plans:
+        """Packs every weight with diffnorm_b200.packing.  `rec` (a repack.PackTable) additionally records, next to each
+        pack call, which parameter feeds which packed tensor, so later steps refresh the same tensors with one launch."""
         c, P, ip, dev = self.cfg, self.P, self.ip, self.dev
         C = c.hid
         pl = _Plans()
         w = lambda k: P[k].detach()
-        pl.init = pack_linear(w("init_conv.weight"), w("init_conv.bias"), k_pad=self.zp, name="init_conv")
-        pl.wn_init = pack_conv3(w("wavenet.init_conv.weight"), w("wavenet.init_conv.bias"), cin_pad=C, n_pad=C, name="wn.init")
-        pl.wn_init_T = pack_conv3(w("wavenet.init_conv.weight").permute(1, 0, 2), None, cin_pad=C, n_pad=C, shift_sign=-1,
-                                  name="wn.init^T")
+
+        def lin(name, wk, bk=None, T=False, **kw):
+            """pack_linear of parameter wk (transposed if T) + its record."""
+            W = w(wk)
+            plan = pack_linear(W.reshape(W.shape[0], -1).t() if T else W, None if bk is None else w(bk), name=name, **kw)
+            if rec is not None:
+                rec.linear(W, plan.W, transposed=T)
+                if bk is not None:
+                    rec.vector(w(bk), plan.bias)
+            return plan
+
+        def conv(name, wk, bk=None, T=False, **kw):
+            W = w(wk)
+            plan = pack_conv3(W.permute(1, 0, 2) if T else W, None if bk is None else w(bk), name=name,
+                              shift_sign=-1 if T else 1, **kw)
+            if rec is not None:
+                rec.conv3(W, plan.W, kw["cin_pad"], transposed=T)
+                if bk is not None:
+                    rec.vector(w(bk), plan.bias)
+            return plan
+
+        pl.init = lin("init_conv", "init_conv.weight", "init_conv.bias", k_pad=self.zp)
+        pl.wn_init = conv("wn.init", "wavenet.init_conv.weight", "wavenet.init_conv.bias", cin_pad=C, n_pad=C)
+        pl.wn_init_T = conv("wn.init^T", "wavenet.init_conv.weight", T=True, cin_pad=C, n_pad=C)
         pl.lvl, pl.lvl_T = [], []
         G = c.wn_layers
         for s in range(c.wn_stacks):
             blk = [f"wavenet.stacks.{s}.blocks.{i}." for i in range(G)]
             convs, ress = [w(b + "conv.weight") for b in blk], [w(b + "res_conv.weight") for b in blk]
-            lv = pack_wavenet_level(convs, [w(b + "conv.bias") for b in blk], ress, [w(b + "res_conv.bias") for b in blk], C,
-                                    name=f"wn.lvl{s}")
+            conv_b, res_b = [w(b + "conv.bias") for b in blk], [w(b + "res_conv.bias") for b in blk]
+            lv = pack_wavenet_level(convs, conv_b, ress, res_b, C, name=f"wn.lvl{s}")
             # un-fused form: plain +bias epilogue over the same packed tiles -> [conv 128 | res 128] column blocks
             tiles = C // 128
             bi = torch.stack([lv.bias.view(G, tiles, 128), lv.bias2.view(G, tiles, 128)], dim=2).reshape(-1).contiguous()
             fwd = GemmPlan(lv.W, lv.segs, 2 * C, tiles, _lib.EPI_BF16, bias=bi, groups=G, g_w_row=lv.g_w_row, g_bias=2 * C,
                            dilation=1, dilation_shl_group=1, name=f"wn.lvl{s}.ur")
             pl.lvl.append(fwd)
-            pl.lvl_T.append(pack_wavenet_level_dgrad(convs, ress, C, name=f"wn.lvl{s}^T"))
+            lvT = pack_wavenet_level_dgrad(convs, ress, C, name=f"wn.lvl{s}^T")
+            pl.lvl_T.append(lvT)
+            if rec is not None:
+                rec.wavenet_level(convs, conv_b, ress, res_b, lv.W, C, bi=bi)
+                rec.wavenet_level_dgrad(convs, ress, lvT.W, C)
         last = [f"wavenet.stacks.{c.wn_stacks - 1}.blocks.{i}." for i in range(G)]
-        skips = [w(b + "skip_conv.weight") for b in last]
-        pl.skip = pack_skip_sum(skips, [w(b + "skip_conv.bias") for b in last], C, name="wn.skip")
+        skips, skip_b = [w(b + "skip_conv.weight") for b in last], [w(b + "skip_conv.bias") for b in last]
+        pl.skip = pack_skip_sum(skips, skip_b, C, name="wn.skip")
         pl.skip_T = pack_linear(torch.cat([sk.reshape(C, C).t() for sk in skips], 0), None, k_pad=C, n_pad=G * C, name="wn.skip^T")
-        pl.wn_final = pack_linear(w("wavenet.final_conv.weight"), w("wavenet.final_conv.bias"), epi=_lib.EPI_F32, k_pad=C,
-                                  n_pad=C, name="wn.final")
-        pl.wn_final_T = pack_linear(w("wavenet.final_conv.weight").reshape(C, C).t(), None, k_pad=C, n_pad=C, name="wn.final^T")
+        if rec is not None:
+            rec.skip_sum(skips, skip_b, pl.skip.W, pl.skip.bias, C)
+            for g, sk in enumerate(skips):
+                rec.linear(sk, pl.skip_T.W, transposed=True, row0=g * C)
+        pl.wn_final = lin("wn.final", "wavenet.final_conv.weight", "wavenet.final_conv.bias", epi=_lib.EPI_F32, k_pad=C, n_pad=C)
+        pl.wn_final_T = lin("wn.final^T", "wavenet.final_conv.weight", T=True, k_pad=C, n_pad=C)
         pl.layers = []
         for l in range(c.depth):
             p = f"transformer.layers.{l}."
             L = _Plans()
-            wqkv = torch.cat([w(p + "1.to_q.weight"), w(p + "1.to_kv.weight")], 0)
+            wq, wkv = w(p + "1.to_q.weight"), w(p + "1.to_kv.weight")
+            wqkv = torch.cat([wq, wkv], 0)
             L.qkv = pack_linear(wqkv, None, name=p + "qkv")
             L.qkv_T = pack_linear(wqkv.t(), None, name=p + "qkv^T")
-            L.out = pack_linear(w(p + "1.to_out.weight"), None, epi=_lib.EPI_RESID, name=p + "to_out")
-            L.out_T = pack_linear(w(p + "1.to_out.weight").t(), None, name=p + "to_out^T")
+            if rec is not None:
+                rec.linear(wq, L.qkv.W)
+                rec.linear(wkv, L.qkv.W, row0=wq.shape[0])
+                rec.linear(wq, L.qkv_T.W, transposed=True)
+                rec.linear(wkv, L.qkv_T.W, transposed=True, col0=wq.shape[0])
+            L.out = lin(p + "to_out", p + "1.to_out.weight", epi=_lib.EPI_RESID)
+            L.out_T = lin(p + "to_out^T", p + "1.to_out.weight", T=True)
             g = pack_geglu(w(p + "5.0.weight"), w(p + "5.0.bias"), name=p + "ff.geglu")
             L.ff1 = GemmPlan(g.W, g.segs, 2 * ip, g.n_tiles, _lib.EPI_BF16, bias=g.bias, name=p + "ff.h")
             L.ff1_T = GemmPlan(g.W.t().contiguous(), [(0, 0, 2 * ip // BK, 0, 0)], C, (C + WT - 1) // WT, _lib.EPI_BF16,
                                name=p + "ff.h^T")
-            wc = w(p + "5.2.1.weight")
-            L.ffc = pack_conv3(wc, w(p + "5.2.1.bias"), cin_pad=ip, n_pad=ip, name=p + "ff.conv")
-            L.ffc_T = pack_conv3(wc.permute(1, 0, 2), None, cin_pad=ip, n_pad=ip, shift_sign=-1, name=p + "ff.conv^T")
-            L.ff3 = pack_linear(w(p + "5.3.weight"), w(p + "5.3.bias"), epi=_lib.EPI_RESID, k_pad=ip, name=p + "ff.out")
-            L.ff3_T = pack_linear(w(p + "5.3.weight").t(), None, k_pad=C, n_pad=ip, name=p + "ff.out^T")
+            if rec is not None:
+                rec.geglu(w(p + "5.0.weight"), w(p + "5.0.bias"), g.W, g.bias, L.ff1_T.W)
+            L.ffc = conv(p + "ff.conv", p + "5.2.1.weight", p + "5.2.1.bias", cin_pad=ip, n_pad=ip)
+            L.ffc_T = conv(p + "ff.conv^T", p + "5.2.1.weight", T=True, cin_pad=ip, n_pad=ip)
+            L.ff3 = lin(p + "ff.out", p + "5.3.weight", p + "5.3.bias", epi=_lib.EPI_RESID, k_pad=ip)
+            L.ff3_T = lin(p + "ff.out^T", p + "5.3.weight", T=True, k_pad=C, n_pad=ip)
             pl.layers.append(L)
-        pl.pred = pack_linear(w("transformer.to_pred.1.weight"), None, name="to_pred")
-        pl.pred_T = pack_linear(w("transformer.to_pred.1.weight").t(), None, name="to_pred^T")
-        pl.proj = pack_linear(w("final_proj.weight"), w("final_proj.bias"), epi=_lib.EPI_F32, n_pad=self.zn, name="final_proj")
-        pl.proj_T = pack_linear(w("final_proj.weight").t(), None, k_pad=self.zp, n_pad=C, name="final_proj^T")
+        pl.pred = lin("to_pred", "transformer.to_pred.1.weight")
+        pl.pred_T = lin("to_pred^T", "transformer.to_pred.1.weight", T=True)
+        pl.proj = lin("final_proj", "final_proj.weight", "final_proj.bias", epi=_lib.EPI_F32, n_pad=self.zn)
+        pl.proj_T = lin("final_proj^T", "final_proj.weight", T=True, k_pad=self.zp, n_pad=C)
         pl.Wcat = torch.cat([w(n + ".weight") for n in self.cond_names], 0).contiguous()       # [56 * 1024, 2048]
         pl.bcat = torch.cat([w(n + ".bias") for n in self.cond_names], 0).contiguous()
+        if rec is not None:
+            r0 = 0
+            for n in self.cond_names:
+                Wn, bn = w(n + ".weight"), w(n + ".bias")
+                rec.linear(Wn, pl.Wcat, row0=r0)
+                rec.vector(bn, pl.bcat, row0=r0)
+                r0 += Wn.shape[0]
         return pl
 
     def _packed(self) -> _Plans:
-        """The per-step re-packing is ~500 small indexing kernels over fixed addresses (the fp32 masters are updated in
-        place by the optimizer): it is captured once in a CUDA graph and replayed (one launch) every step.  A change of
-        any parameter's storage (e.g. `.to()`, a new tensor assigned) re-captures."""
+        """Weights are packed with diffnorm_b200.packing once (which also zero-fills the padding); every later step
+        refreshes the same packed tensors in place from the fp32 masters (updated in place by the optimizer) with ONE
+        dn_pack_weights launch over the recorded descriptor table (diffnorm_b200.repack).  A change of any parameter's
+        storage (e.g. `.to()`, a new tensor assigned) packs and records again.  DN_REPACK=torch keeps the previous form:
+        the ~500 torch indexing kernels captured in a CUDA graph and replayed."""
         ptrs = tuple(p.data_ptr() for p in self.P.values())
-        if self._pack_graph is None or ptrs != self._pack_ptrs:
-            self._pack()                      # warm-up outside capture (allocator, lazy init)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._pack_plans = self._pack()
-            self._pack_graph, self._pack_ptrs = g, ptrs
-        self._pack_graph.replay()
+        if os.environ.get("DN_REPACK", "kernel") == "torch":
+            if self._pack_graph is None or ptrs != self._pack_ptrs:
+                self._pack()                      # warm-up outside capture (allocator, lazy init)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._pack_plans = self._pack()
+                self._pack_graph, self._pack_ptrs = g, ptrs
+            self._pack_graph.replay()
+            return self._pack_plans
+        if self._pack_table is None or ptrs != self._pack_ptrs:
+            rec = PackTable()
+            self._pack_plans = self._pack(rec)
+            self._pack_table, self._pack_ptrs = rec.finalize(self.dev), ptrs
+            return self._pack_plans               # fresh from packing.*: nothing to refresh this step
+        self._pack_table.run()
         return self._pack_plans
 
     def pe_table(self, T: int) -> torch.Tensor:

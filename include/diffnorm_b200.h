@@ -318,6 +318,30 @@ int dn_time_features_bwd(const int32_t* steps, const float* w, const float* dfea
 int dn_add_bf16_to_f32(const void* src, int64_t rows, int32_t ld, int32_t col0, int32_t C, float* dst, int32_t ldd,
                        int32_t accumulate, void* stream);
 
+/* Per-step weight re-packing of the training step: the optimizer updates the fp32 master weights in place, the GEMMs read
+ * bf16 K-major tiles (and their transposes for the data gradients).  ONE launch walks a table of copy descriptors that lives
+ * in device memory: dst[rowmap(r), colmap(c, k)] = cast(src[r * s_row + c * s_col + k * s_tap]) for r < rows, c < cols,
+ * k < taps, with  rowmap(r) = row0 + (r / rblk) * rblk_stride + r % rblk,
+ *                 colmap(c, k) = col0 + tap_pos[k] * tap_cols + (c / cblk) * cblk_stride + c % cblk
+ * (nn.Linear / conv weights, optionally transposed, the 3 taps of a k = 3 conv side by side, the 128-row interleave of the
+ * GEGLU and WaveNet tiles; padding rows / columns are never written and stay zero).  Tiles of 64 x 64 (x taps): tile0 =
+ * number of tiles of all earlier ops, tiles_c = ceil(cols / 64).  Replaces the ~500 torch indexing kernels of
+ * diffnorm_b200.packing on the training path (same bits: fp32 -> bf16 round-to-nearest-even, or a plain fp32 copy). */
+typedef struct {
+    const float* src;
+    void* dst;
+    int64_t s_row, s_col, s_tap;          /* element strides of src */
+    int32_t rows, cols, taps;             /* taps <= 3 */
+    int32_t ldd;                          /* dst leading dimension (elements) */
+    int32_t row0, rblk, rblk_stride;
+    int32_t col0, cblk, cblk_stride, tap_cols;
+    int32_t tap_pos[3];
+    int32_t src_r_fastest;                /* 1: src is contiguous along r (and k): transposed through shared memory */
+    int32_t out_f32;                      /* dst dtype: 0 = bf16, 1 = fp32 */
+    int32_t tile0, tiles_c;
+} dn_pack_op;
+int dn_pack_weights(const dn_pack_op* ops_device, int32_t n_ops, int32_t total_tiles, void* stream);
+
 /* ---- host-side helper (no CUDA) --------------------------------------------------------------------------- */
 
 /* Length-bucketed batching under a padded-token budget; same contract and results as the reference's Cython

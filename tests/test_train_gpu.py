@@ -231,6 +231,50 @@ def test_train_step_against_oracle_autograd(drop_p, multitask, extreme_t):
     assert np.sqrt(tot_num / tot_den) < (8e-2 if extreme_t else 4e-2)
 
 
+def test_repack_kernel_bit_identical_to_packing_on_full_model(monkeypatch):
+    """dn_pack_weights (one launch over the recorded descriptor table) against diffnorm_b200.packing on every packed tensor
+    of the full-size denoiser after an in-place weight update (bit-identical); then two SGD steps with the kernel refresh
+    and with the torch-indexing refresh agree (to the run-to-run noise of the step's atomically reduced gradients)."""
+    from diffnorm_b200.repack import plan_tensors
+    arch, sd, ldm = _build(16, 3)
+    tr = DenoiserTrainer(ldm, drop_p=0.0)
+    plans = tr._packed()                      # packing.* + record
+    named = plan_tensors(plans)
+    before = {n: t.clone() for n, t in named}
+    g = torch.Generator(device=DEV).manual_seed(5)
+    with torch.no_grad():
+        for p in tr.P.values():
+            p.add_(torch.randn(p.shape, generator=g, device=DEV) * 0.02)
+    assert tr._packed() is plans              # refreshed in place by the kernel
+    torch.cuda.synchronize()
+    fresh = dict(plan_tensors(tr._pack()))
+    assert len(named) > 150
+    for n, t in named:
+        assert torch.equal(t, fresh[n]), n
+        assert not torch.equal(t, before[n]), n
+
+    z, B, T, lengths, times = 16, 2, 24, [24, 17], [37, 142]
+    audio, units, mask, eps_vae, eps0, eps, _ = O.train_case_inputs(z, B, T, lengths, 21, 0.0)
+    res = {}
+    for mode in ("kernel", "torch"):
+        monkeypatch.setenv("DN_REPACK", mode)
+        arch, sd, ldm = _build(16, 3)
+        tr = DenoiserTrainer(ldm, drop_p=0.0)
+        losses = []
+        for it in range(2):
+            out, grads = tr.step(audio.to(DEV), units.to(DEV), torch.tensor(lengths, dtype=i32, device=DEV),
+                                 times=torch.tensor(times), noise={"vae": eps_vae, "eps0": eps0, "eps": eps})
+            losses.append(float(out["total_loss"]))
+            with torch.no_grad():             # plain SGD on the masters, in place
+                for k, p in tr.P.items():
+                    p.add_(grads[k].reshape(p.shape), alpha=-1e-3)
+        res[mode] = losses
+    print(f"[parity] two SGD steps, total_loss: kernel repack {res['kernel']}, torch repack {res['torch']}")
+    assert abs(res["kernel"][0] - res["kernel"][1]) > 0.05          # the update did something
+    for a, b in zip(res["kernel"], res["torch"]):
+        assert abs(a - b) <= 5e-3 * abs(b)
+
+
 def test_plugin_forward_backward_through_autograd():
     """The fairseq-facing entry: model(...) -> loss dict; loss.backward() fills .grad of every denoiser parameter with
     the CUDA step's gradients; eval mode runs without dropout and without backward (valid_step)."""

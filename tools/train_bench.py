@@ -141,7 +141,8 @@ def main():
             return (t1 - t0) / n * 1e3, (t2 - t0) / n * 1e3
 
         print("phase: host-enqueue ms / wall ms (3 runs each)")
-        print("  pack weights      %.1f / %.1f" % timed(tr._pack))
+        print("  pack weights      %.1f / %.1f   (packing.* torch indexing, eager)" % timed(tr._pack))
+        print("  per-step refresh  %.2f / %.2f   (DN_REPACK=%s)" % (*timed(tr._packed), os.environ.get("DN_REPACK", "kernel")))
         print("  forward only      %.1f / %.1f" % timed(lambda: tr.step(audio, units, lens, backward=False)))
         print("  forward+backward  %.1f / %.1f" % timed(lambda: tr.step(audio, units, lens)))
         print("  + grad allreduce  %.1f / %.1f" % timed(step))
