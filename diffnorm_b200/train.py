@@ -91,27 +91,37 @@ class _GradDict(dict):
             self._hook(k, v)
 
 
-def _pack_vae_wavenet(w, p: str, cin: int, cout: int, cin_pad: int, G: int, S: int, last_f32: bool, dev) -> _Plans:
+def _pack_vae_wavenet(w, p: str, cin: int, cout: int, cin_pad: int, G: int, S: int, last_f32: bool, dev, rec=None) -> _Plans:
     """Forward (un-fused) and data-gradient packings of one VAE WavenetEncoder block (LM:1003-1032): init conv k3
-    cin -> cout, S levels x G chains (dilation 2^g, unconditioned), skip sum, final 1x1.  Channel extents are padded to 128."""
+    cin -> cout, S levels x G chains (dilation 2^g, unconditioned), skip sum, final 1x1.  Channel extents are padded to 128.
+    `rec` (repack.PackTable) records each packing for the one-launch per-step refresh."""
     cp = rup(cout, 128)
     b = _Plans()
     b.p, b.cin, b.cout, b.cp, b.cin_pad, b.last = p, cin, cout, cp, cin_pad, last_f32
     b.init = pack_conv3(w(p + "init_conv.weight"), w(p + "init_conv.bias"), cin_pad=cin_pad, n_pad=cp, name=p + "init")
     b.init_T = pack_conv3(w(p + "init_conv.weight").permute(1, 0, 2), None, cin_pad=cp, n_pad=cin_pad, shift_sign=-1, name=p + "init^T")
+    if rec is not None:
+        rec.conv3(w(p + "init_conv.weight"), b.init.W, cin_pad)
+        rec.vector(w(p + "init_conv.bias"), b.init.bias)
+        rec.conv3(w(p + "init_conv.weight"), b.init_T.W, cp, transposed=True)
     b.lvl, b.lvl_T = [], []
     tiles = cp // 128
     for s_ in range(S):
         blk = [f"{p}stacks.{s_}.blocks.{g}." for g in range(G)]
         convs, ress = [w(k + "conv.weight") for k in blk], [w(k + "res_conv.weight") for k in blk]
-        lv = pack_wavenet_level(convs, [w(k + "conv.bias") for k in blk], ress, [w(k + "res_conv.bias") for k in blk], cp)
+        conv_b, res_b = [w(k + "conv.bias") for k in blk], [w(k + "res_conv.bias") for k in blk]
+        lv = pack_wavenet_level(convs, conv_b, ress, res_b, cp)
         bi = torch.stack([lv.bias.view(G, tiles, 128), lv.bias2.view(G, tiles, 128)], dim=2).reshape(-1).contiguous()
         b.lvl.append(GemmPlan(lv.W, lv.segs, 2 * cp, tiles, _lib.EPI_BF16, bias=bi, groups=G, g_w_row=lv.g_w_row,
                               g_bias=2 * cp, dilation=1, dilation_shl_group=1, name=f"{p}lvl{s_}.ur"))
-        b.lvl_T.append(pack_wavenet_level_dgrad(convs, ress, cp, name=f"{p}lvl{s_}^T"))
+        lvT = pack_wavenet_level_dgrad(convs, ress, cp, name=f"{p}lvl{s_}^T")
+        b.lvl_T.append(lvT)
+        if rec is not None:
+            rec.wavenet_level(convs, conv_b, ress, res_b, lv.W, cp, bi=bi)
+            rec.wavenet_level_dgrad(convs, ress, lvT.W, cp)
     lastb = [f"{p}stacks.{S - 1}.blocks.{g}." for g in range(G)]
-    skips = [w(k + "skip_conv.weight") for k in lastb]
-    b.skip = pack_skip_sum(skips, [w(k + "skip_conv.bias") for k in lastb], cp, name=p + "skip")
+    skips, skip_b = [w(k + "skip_conv.weight") for k in lastb], [w(k + "skip_conv.bias") for k in lastb]
+    b.skip = pack_skip_sum(skips, skip_b, cp, name=p + "skip")
     WsT = torch.zeros(G * cp, cp, device=dev)
     for g in range(G):
         WsT[g * cp:g * cp + cout, :cout] = skips[g].reshape(cout, cout).t()
@@ -121,6 +131,13 @@ def _pack_vae_wavenet(w, p: str, cin: int, cout: int, cin_pad: int, G: int, S: i
                           k_pad=cp, n_pad=b.n_final, name=p + "final")
     b.final_T = pack_linear(w(p + "final_conv.weight").reshape(cout, cout).t(), None, k_pad=rup(cout, 64) if last_f32 else cp,
                             n_pad=cp, name=p + "final^T")
+    if rec is not None:
+        rec.skip_sum(skips, skip_b, b.skip.W, b.skip.bias, cp)
+        for g, sk in enumerate(skips):
+            rec.linear(sk, b.skip_T.W, transposed=True, row0=g * cp)
+        rec.linear(w(p + "final_conv.weight"), b.final.W)
+        rec.vector(w(p + "final_conv.bias"), b.final.bias)
+        rec.linear(w(p + "final_conv.weight"), b.final_T.W, transposed=True)
     return b
 
 
@@ -243,39 +260,72 @@ class FrozenDecoderTrain:
         if sd is not None:
             self.pack(lambda k: sd[pre + k].detach().to(dev).float())
 
-    def pack(self, w):
+    def pack(self, w, rec=None):
         c, dev, D, ip = self.cfg, self.dev, self.D, self.ip
         self.blocks = []
         cin_pad = self.zp
         dec_w = c.dec_widths()
         for i, (cin, cout) in enumerate(dec_w):
-            b = _pack_vae_wavenet(w, f"decoder_wave.{i}.", cin, cout, cin_pad, self.G, self.S, i == len(dec_w) - 1, dev)
+            b = _pack_vae_wavenet(w, f"decoder_wave.{i}.", cin, cout, cin_pad, self.G, self.S, i == len(dec_w) - 1, dev, rec)
             self.blocks.append(b)
             cin_pad = b.cp
+
+        def lin(name, wk, bk=None, T=False, **kw):
+            W = w(wk)
+            plan = pack_linear(W.t() if T else W, None if bk is None else w(bk), name=name, **kw)
+            if rec is not None:
+                rec.linear(W, plan.W, transposed=T)
+                if bk is not None:
+                    rec.vector(w(bk), plan.bias)
+            return plan
+
+        def conv(name, wk, bk=None, T=False, **kw):
+            W = w(wk)
+            plan = pack_conv3(W.permute(1, 0, 2) if T else W, None if bk is None else w(bk), name=name,
+                              shift_sign=-1 if T else 1, **kw)
+            if rec is not None:
+                rec.conv3(W, plan.W, kw["cin_pad"], transposed=T)
+                if bk is not None:
+                    rec.vector(w(bk), plan.bias)
+            return plan
+
+        def gamma(k):
+            g = w(k).float().contiguous().clone()
+            if rec is not None:
+                rec.vector(w(k), g)
+            return g
+
         self.layers = []
         for l in range(c.vae_depth):
             p = f"decoder_tf.layers.{l}."
             L = _Plans()
             L.p = p
-            wqkv = torch.cat([w(p + "1.to_q.weight"), w(p + "1.to_kv.weight")], 0)
+            wq, wkv = w(p + "1.to_q.weight"), w(p + "1.to_kv.weight")
+            wqkv = torch.cat([wq, wkv], 0)
             L.qkv, L.qkv_T = pack_linear(wqkv, None, name=p + "qkv"), pack_linear(wqkv.t(), None, name=p + "qkv^T")
-            L.out = pack_linear(w(p + "1.to_out.weight"), None, epi=_lib.EPI_RESID, name=p + "to_out")
-            L.out_T = pack_linear(w(p + "1.to_out.weight").t(), None, name=p + "to_out^T")
+            if rec is not None:
+                rec.linear(wq, L.qkv.W)
+                rec.linear(wkv, L.qkv.W, row0=wq.shape[0])
+                rec.linear(wq, L.qkv_T.W, transposed=True)
+                rec.linear(wkv, L.qkv_T.W, transposed=True, col0=wq.shape[0])
+            L.out = lin(p + "to_out", p + "1.to_out.weight", epi=_lib.EPI_RESID)
+            L.out_T = lin(p + "to_out^T", p + "1.to_out.weight", T=True)
             g = pack_geglu(w(p + "5.0.weight"), w(p + "5.0.bias"))
             L.ff1 = GemmPlan(g.W, g.segs, 2 * ip, g.n_tiles, _lib.EPI_BF16, bias=g.bias, name=p + "ff.h")
             L.ff1_T = GemmPlan(g.W.t().contiguous(), [(0, 0, 2 * ip // BK, 0, 0)], D, (D + WT - 1) // WT, _lib.EPI_BF16, name=p + "ff.h^T")
-            wc = w(p + "5.2.1.weight")
-            L.ffc = pack_conv3(wc, w(p + "5.2.1.bias"), cin_pad=ip, n_pad=ip, name=p + "ff.conv")
-            L.ffc_T = pack_conv3(wc.permute(1, 0, 2), None, cin_pad=ip, n_pad=ip, shift_sign=-1, name=p + "ff.conv^T")
-            L.ff3 = pack_linear(w(p + "5.3.weight"), w(p + "5.3.bias"), epi=_lib.EPI_RESID, k_pad=ip, name=p + "ff.out")
-            L.ff3_T = pack_linear(w(p + "5.3.weight").t(), None, k_pad=D, n_pad=ip, name=p + "ff.out^T")
-            L.g1, L.g2 = w(p + "0.gamma").float().contiguous().clone(), w(p + "4.gamma").float().contiguous().clone()
+            if rec is not None:
+                rec.geglu(w(p + "5.0.weight"), w(p + "5.0.bias"), g.W, g.bias, L.ff1_T.W)
+            L.ffc = conv(p + "ff.conv", p + "5.2.1.weight", p + "5.2.1.bias", cin_pad=ip, n_pad=ip)
+            L.ffc_T = conv(p + "ff.conv^T", p + "5.2.1.weight", T=True, cin_pad=ip, n_pad=ip)
+            L.ff3 = lin(p + "ff.out", p + "5.3.weight", p + "5.3.bias", epi=_lib.EPI_RESID, k_pad=ip)
+            L.ff3_T = lin(p + "ff.out^T", p + "5.3.weight", T=True, k_pad=D, n_pad=ip)
+            L.g1, L.g2 = gamma(p + "0.gamma"), gamma(p + "4.gamma")
             self.layers.append(L)
-        self.pred_gamma = w("decoder_tf.to_pred.0.gamma").float().contiguous().clone()
-        self.pred = pack_linear(w("decoder_tf.to_pred.1.weight"), None, epi=_lib.EPI_F32, name="vae.to_pred")
-        self.pred_T = pack_linear(w("decoder_tf.to_pred.1.weight").t(), None, name="vae.to_pred^T")
-        self.lm = pack_linear(w("decoder_lm.weight"), w("decoder_lm.bias"), epi=_lib.EPI_F32, n_pad=rup(c.vocab, 16), name="vae.lm")
-        self.lm_T = pack_linear(w("decoder_lm.weight").t(), None, epi=_lib.EPI_F32, k_pad=self.vl, n_pad=D, name="vae.lm^T")
+        self.pred_gamma = gamma("decoder_tf.to_pred.0.gamma")
+        self.pred = lin("vae.to_pred", "decoder_tf.to_pred.1.weight", epi=_lib.EPI_F32)
+        self.pred_T = lin("vae.to_pred^T", "decoder_tf.to_pred.1.weight", T=True)
+        self.lm = lin("vae.lm", "decoder_lm.weight", "decoder_lm.bias", epi=_lib.EPI_F32, n_pad=rup(c.vocab, 16))
+        self.lm_T = lin("vae.lm^T", "decoder_lm.weight", T=True, epi=_lib.EPI_F32, k_pad=self.vl, n_pad=D)
 
     def forward(self, xb, lens, B, T, keep_bits=None, keep_scale: float = 1.0):
         """xb bf16 [B*T, zp] -> (recon fp32 [B*T, 768], logits fp32 [B*T, vp]); keeps activations for backward()."""

@@ -8,6 +8,7 @@ speech_vae_decoder_loss.py:60-82) and returns fp32 gradients keyed like ``Speech
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -15,6 +16,7 @@ import torch
 from . import ops
 from .config import DiffNormConfig
 from .packing import rup
+from .repack import PackTable
 from .train import FrozenDecoderTrain, VaeBlocksTrain, ZeroArena, _GradDict, _pack_vae_wavenet
 
 bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
@@ -35,7 +37,7 @@ class VaeTrainer:
         self.arena = ZeroArena(self.dev)
         self.enc = VaeBlocksTrain(self.buf, self.G, self.S, "e", self.arena.zeros)
         self.dec = FrozenDecoderTrain(None, c, self.dev, self.buf, zeros=self.arena.zeros)
-        self._pack_graph, self._pack_ptrs, self.enc_blocks = None, None, None
+        self._pack_graph, self._pack_ptrs, self.enc_blocks, self._pack_table = None, None, None, None
         self.ctx = None
 
     def buf(self, name: str, rows: int, width: int, dtype=bf16, zero: bool = False) -> torch.Tensor:
@@ -50,28 +52,39 @@ class VaeTrainer:
         return v
 
     # ------------------------------------------------------------------------------------------------ packing
-    def _pack(self):
+    def _pack(self, rec=None):
         c = self.cfg
         w = lambda k: self.P[k].detach().float()
         blocks, cin_pad = [], c.feat_dim
         enc_w = c.enc_widths()
         for i, (cin, cout) in enumerate(enc_w):
-            b = _pack_vae_wavenet(w, f"encoder_wave.{i}.", cin, cout, cin_pad, self.G, self.S, i == len(enc_w) - 1, self.dev)
+            b = _pack_vae_wavenet(w, f"encoder_wave.{i}.", cin, cout, cin_pad, self.G, self.S, i == len(enc_w) - 1, self.dev, rec)
             blocks.append(b)
             cin_pad = b.cp
-        self.dec.pack(w)
+        self.dec.pack(w, rec)
         return blocks
 
     def _packed(self):
+        """Packed once with diffnorm_b200.packing; every later step refreshes the same packed tensors in place from the
+        fp32 masters with ONE dn_pack_weights launch (see DenoiserTrainer._packed; DN_REPACK=torch = the CUDA-graph replay of
+        the torch indexing kernels)."""
         ptrs = tuple(p.data_ptr() for p in self.P.values())
-        if self._pack_graph is None or ptrs != self._pack_ptrs:
-            self._pack()
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.enc_blocks = self._pack()
-            self._pack_graph, self._pack_ptrs = g, ptrs
-        self._pack_graph.replay()
+        if os.environ.get("DN_REPACK", "kernel") == "torch":
+            if self._pack_graph is None or ptrs != self._pack_ptrs:
+                self._pack()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.enc_blocks = self._pack()
+                self._pack_graph, self._pack_ptrs = g, ptrs
+            self._pack_graph.replay()
+            return self.enc_blocks
+        if self._pack_table is None or ptrs != self._pack_ptrs:
+            rec = PackTable()
+            self.enc_blocks = self._pack(rec)
+            self._pack_table, self._pack_ptrs = rec.finalize(self.dev), ptrs
+            return self.enc_blocks
+        self._pack_table.run()
         return self.enc_blocks
 
     # ------------------------------------------------------------------------------------------------ forward / backward

@@ -53,3 +53,37 @@ def test_table_tiles_are_a_partition():
         assert tile0 == nxt and tiles_c == -(-o["cols"] // 64)
         nxt += -(-o["rows"] // 64) * tiles_c
     assert nxt == total
+
+
+def test_vae_recorded_table_reproduces_packing_after_weight_update():
+    """Same check for the VAE training step's packings (WaveNet encoder / decoder blocks with channel padding, the
+    768-wide decoder transformer, the per-layer gamma copies)."""
+    from diffnorm_b200.plugin.latent_module import SpeechVAEEncoderDecoder
+    from diffnorm_b200.train import FrozenDecoderTrain
+    from diffnorm_b200.train_vae import VaeTrainer
+    torch.manual_seed(1)
+    vae = SpeechVAEEncoderDecoder(192, 16)        # narrow features keep the CPU test small; same code paths
+    cfg = vae.cfg
+    cfg.vae_depth = 1
+    tr = object.__new__(VaeTrainer)
+    tr.cfg, tr.P, tr.dev = cfg, dict(vae.named_parameters()), torch.device("cpu")
+    tr.G, tr.S = cfg.vae_layers, cfg.vae_stacks
+    tr.dec = FrozenDecoderTrain(None, cfg, tr.dev, None)
+    rec = PackTable()
+    enc_blocks = tr._pack(rec)
+
+    def tree():
+        return plan_tensors([enc_blocks, tr.dec.blocks, tr.dec.layers, tr.dec.pred, tr.dec.pred_T, tr.dec.lm, tr.dec.lm_T,
+                             tr.dec.pred_gamma])
+    named = tree()
+    before = {n: t.clone() for n, t in named}
+    with torch.no_grad():
+        for p in tr.P.values():
+            p.add_(torch.randn_like(p) * 0.05)
+    rec.run_reference()
+    enc_blocks = tr._pack()
+    fresh = dict(tree())
+    assert len(named) > 60
+    for n, t in named:
+        assert torch.equal(t, fresh[n]), f"{n}: table and packing.* disagree"
+        assert not torch.equal(t, before[n]), f"{n} is not covered by the table"

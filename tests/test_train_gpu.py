@@ -305,6 +305,35 @@ def test_plugin_forward_backward_through_autograd():
     assert abs(float(ev["total_loss"]) - 0.904014) < 2e-2 * 0.904014   # the oracle's no-dropout loss for this case
 
 
+@pytest.mark.parametrize("z", [16, 128])
+def test_vae_repack_kernel_bit_identical_to_packing(z):
+    """The VAE training step's one-launch weight refresh against diffnorm_b200.packing on the full-size VAE (channel-padded
+    WaveNet blocks, 768-wide decoder transformer, gamma copies) after an in-place weight update."""
+    from diffnorm_b200.plugin.latent_module import SpeechVAEEncoderDecoder
+    from diffnorm_b200.repack import plan_tensors
+    from diffnorm_b200.train_vae import VaeTrainer
+    torch.manual_seed(2)
+    tr = VaeTrainer(SpeechVAEEncoderDecoder(768, z).to(DEV), drop_p=0.1)
+
+    def tree(enc_blocks):
+        d = tr.dec
+        return plan_tensors([enc_blocks, d.blocks, d.layers, d.pred, d.pred_T, d.lm, d.lm_T, d.pred_gamma])
+    named = tree(tr._packed())
+    before = {n: t.clone() for n, t in named}
+    g = torch.Generator(device=DEV).manual_seed(6)
+    with torch.no_grad():
+        for p in tr.P.values():
+            p.add_(torch.randn(p.shape, generator=g, device=DEV) * 0.02)
+    tr._packed()                               # kernel refresh, in place
+    torch.cuda.synchronize()
+    kept = [(n, t.clone()) for n, t in named]
+    fresh = dict(tree(tr._pack()))             # packing.* from the updated masters (rebinds tr.dec.*)
+    assert len(kept) > 150
+    for n, t in kept:
+        assert torch.equal(t, fresh[n]), n
+        assert not torch.equal(t, before[n]), n
+
+
 @pytest.mark.parametrize("z,wseed", [(16, 4), (128, 6)])
 def test_vae_train_step_against_oracle_autograd(z, wseed):
     """VAE training: SpeechVAEEncoderDecoder.forward -> (mse, lm_pred, kl) and the gradients of the criterion's
