@@ -328,7 +328,7 @@ def test_vae_repack_kernel_bit_identical_to_packing(z):
     torch.cuda.synchronize()
     kept = [(n, t.clone()) for n, t in named]
     fresh = dict(tree(tr._pack()))             # packing.* from the updated masters (rebinds tr.dec.*)
-    assert len(kept) > 150
+    assert len(kept) > 100
     for n, t in kept:
         assert torch.equal(t, fresh[n]), n
         assert not torch.equal(t, before[n]), n
