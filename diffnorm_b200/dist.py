@@ -7,7 +7,7 @@ the backward pass.  ``finish()`` waits, divides by the world size (DDP's mean, t
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 import torch.distributed as dist

@@ -12,7 +12,6 @@ CUDA kernel on the full model.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Callable, List, Optional, Sequence
 
 import torch
