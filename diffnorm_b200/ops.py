@@ -180,6 +180,7 @@ def attention(qkv, out, lengths, B: int, T: int, H: int, dh: int):
 import os as _os
 
 _USE_2CTA = _os.environ.get("DN_GEMM_2CTA", "1") != "0"   # A/B switch for measurements; results are bit-identical
+_WASTE_AWARE = _os.environ.get("DN_GEMM_WASTE_AWARE", "1") != "0"
 
 
 class GemmPlan:
@@ -209,9 +210,13 @@ class GemmPlan:
             # run across utterance boundaries (T = 1000 would otherwise waste 24 of every 1024 tile rows)
             B, T = 1, B * T
         if impl is None:
-            # CTA-pair form (tcgen05 cta_group::2, M = 256 tiles) whenever it still fills the machine: 74 pairs of SMs
+            # CTA-pair form (tcgen05 cta_group::2, M = 256 tiles) whenever it still fills the machine: 74 pairs of SMs ...
             pair_tiles = self.groups * B * ((T + 255) // 256) * self.n_tiles
             impl = _lib.GEMM_TCGEN05_2CTA if (_USE_2CTA and pair_tiles >= 74) else _lib.GEMM_TCGEN05
+            # ... unless its 256-row tiles, which cannot cross utterances when taps are shifted, pad a ragged T by more than
+            # the pair form gains (~10 % per row): T = 600 is 3 x 256 = 768 rows as pairs but 5 x 128 = 640 rows single
+            if impl == _lib.GEMM_TCGEN05_2CTA and _WASTE_AWARE and (T + 127) // 128 * 128 * 1.10 < (T + 255) // 256 * 256:
+                impl = _lib.GEMM_TCGEN05
         _chk(A, bf16, "A")
         _chk(out, f32 if epi in (_lib.EPI_F32, _lib.EPI_RESID) else bf16, "out")
         d = GemmDesc()
