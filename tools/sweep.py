@@ -114,8 +114,8 @@ def dataset(a, eng, dev, rank, world):
                           "device_s_per_rank": [round(float(x), 3) for x in g[:, 0]], "max_device_s": tmax,
                           "valid_frames_per_s": float(g[:, 2].sum()) / tmax,
                           "padded_frames_per_s": float(g[:, 3].sum()) / tmax,
-                          "note": "includes one CUDA-graph capture (+1 warm-up step) per distinct (B,T) shape and the "
-                                  "pinned-host H2D of every batch's features"}), flush=True)
+                          "note": "includes the pinned-host H2D of every batch's features; (B,T) shapes seen once run eager, a "
+                                  "shape that comes back is captured as a CUDA graph (engine.graph_after)"}), flush=True)
 
 
 def main():
