@@ -376,9 +376,50 @@ def make_batcher():
     print("batcher cases", n_cases)
 
 
+def make_vocoder():
+    """SURVEY §8f-4 groundwork: the reference's CodeGenerator (codehifigan.py / hifigan.py / fastspeech2.VariancePredictor,
+    loaded untouched by ref_loader.load_vocoder) on the oracle's seeded weights -> tests/golden/vocoder_code_hifigan.npz.
+    Cases: durations predicted; durations off; a unit stream that is first reduced by the driver's process_units and carries
+    invalid (negative) codes, which CodeHiFiGANVocoder.forward drops (vocoder.py:231-237)."""
+    from oracle import vocoder_oracle as V
+    voc = ref_loader.load_vocoder()
+    seed = 7
+    sd = V.init_state_dict(seed)
+    m = voc.CodeGenerator(dict(V.VOCODER_CFG)).eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(3)
+    out = {"weight_seed": seed}
+    codes = {"dur": torch.randint(0, 1000, (40,), generator=g), "nodur": torch.randint(0, 1000, (25,), generator=g)}
+    raw = torch.randint(0, 6, (60,), generator=g) * 150 + 3           # few distinct units -> runs of duplicates
+    raw[[5, 17, 18]] = -1
+    reduced = V.process_units(raw.tolist(), reduce=True)
+    codes["reduced"] = torch.tensor(reduced)
+    out["raw_units"] = raw.numpy()
+    for name, code in codes.items():
+        dp = name != "nodur"
+        with torch.no_grad():
+            x = {"code": code.view(1, -1).clone()}
+            mask = x["code"] >= 0                                        # vocoder.py:234-235
+            x["code"] = x["code"][mask].unsqueeze(0)
+            wav = m(**x, dur_prediction=dp).detach().squeeze()
+            emb = m.dict(x["code"])
+            dur = torch.clamp(torch.round(torch.exp(m.dur_predictor(emb)) - 1).long(), min=1).view(-1) if dp \
+                else torch.ones(x["code"].shape[1], dtype=torch.long)
+        w2, d2 = V.code_to_waveform(sd, code, dur_prediction=dp)
+        err = float((wav - w2).abs().max())
+        assert torch.equal(dur, d2) and wav.shape == w2.shape and err < 5e-6, (name, err)
+        assert wav.numel() == V.HOP * int(dur.sum())
+        print(f"vocoder {name}: {code.numel()} codes -> {int(dur.sum())} frames -> {wav.numel()} samples, dur max {int(dur.max())}, "
+              f"wave std {float(wav.std()):.3f}, oracle max err {err:.2e}")
+        out[f"{name}_code"], out[f"{name}_dur"], out[f"{name}_wave"] = code.numpy(), dur.numpy(), wav.numpy()
+    np.savez_compressed(os.path.join(GOLD, "vocoder_code_hifigan.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
+    if "--vocoder-only" in sys.argv:
+        return make_vocoder()
     if "--batcher-only" in sys.argv:
         return make_batcher()
     if "--train-only" in sys.argv:
@@ -403,6 +444,7 @@ def main():
     for name in VAE_TRAIN_CASES:
         make_vae_train(name)
     make_kmeans()
+    make_vocoder()
 
 
 if __name__ == "__main__":

@@ -120,6 +120,43 @@ def load():
     return ns
 
 
+def load_vocoder():
+    """The reference's unit vocoder classes, loaded by path from the untouched files: hifigan.py (torch only),
+    fastspeech2.py (for VariancePredictor; its other fairseq imports are stubbed with the semantics the class needs:
+    FairseqDropout = nn.Dropout, LayerNorm = nn.LayerNorm) and codehifigan.py.  Returns the module of codehifigan.py."""
+    if "voc" in _cache:
+        return _cache["voc"]
+    load()                                    # registers the fairseq.* stub packages
+    fmodels, fmodules = sys.modules["fairseq.models"], sys.modules["fairseq.modules"]
+
+    class FairseqDropout(nn.Dropout):          # fairseq/modules/fairseq_dropout.py: nn.Dropout with a module name
+        def __init__(self, p, module_name=None):
+            super().__init__(p)
+
+    fmodules.FairseqDropout, fmodules.LayerNorm = FairseqDropout, nn.LayerNorm
+    fmodules.MultiheadAttention = getattr(fmodules, "MultiheadAttention", nn.MultiheadAttention)
+    fmodels.FairseqEncoderModel = getattr(fmodels, "FairseqEncoderModel", nn.Module)
+    deco = lambda *a, **k: (lambda f: f)
+    fmodels.register_model = getattr(fmodels, "register_model", deco)
+    fmodels.register_model_architecture = getattr(fmodels, "register_model_architecture", deco)
+    if "fairseq.data" not in sys.modules:
+        d = types.ModuleType("fairseq.data")
+        d.__path__ = []
+        sys.modules["fairseq.data"] = d
+    du = types.ModuleType("fairseq.data.data_utils")
+    du.lengths_to_padding_mask = lambda lens: torch.arange(int(lens.max()))[None, :] >= lens[:, None]
+    sys.modules["fairseq.data.data_utils"] = du
+    for name, attr in (("hub_interface", "TTSHubInterface"), ("tacotron2", "Postnet")):
+        m = types.ModuleType("fairseq.models.text_to_speech." + name)
+        setattr(m, attr, type(attr, (nn.Module,), {}))
+        sys.modules[m.__name__] = m
+    _load("fairseq.models.text_to_speech.hifigan", os.path.join(_TTS, "hifigan.py"))
+    _load("fairseq.models.text_to_speech.fastspeech2", os.path.join(_TTS, "fastspeech2.py"))
+    voc = _load("fairseq.models.text_to_speech.codehifigan", os.path.join(_TTS, "codehifigan.py"))
+    _cache["voc"] = voc
+    return voc
+
+
 def build_reference_model(latent_dim: int = 16, hid: int = 512, timesteps: int = 200, multitask: bool = False):
     """The reference's own modules: LatentDiscreteModel(vae, hid, z) (latent_module.py:1300)."""
     ns = load()

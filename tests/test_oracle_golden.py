@@ -198,3 +198,25 @@ def test_oracle_kmeans_predict_matches_sklearn_golden():
     centers, feats = O.kmeans_case(int(g["seed"]), int(g["K"]), int(g["D"]), int(g["N"]))
     got = O.kmeans_predict(centers, feats)
     assert (got == g["labels"].astype(np.int64)).mean() == 1.0
+
+
+def test_vocoder_oracle_matches_reference_golden():
+    """SURVEY §8f-4 groundwork: oracle/vocoder_oracle.py (CodeHiFiGAN generator + duration predictor + the driver's unit
+    handling) against the waveforms the untouched reference modules produced on the same seeded weights
+    (oracle/make_golden.py --vocoder-only).  Durations are integers: bit-exact; waveform fp32 vs fp32: 1e-5."""
+    from oracle import vocoder_oracle as V
+    g = np.load(os.path.join(GOLD, "vocoder_code_hifigan.npz"))
+    sd = V.init_state_dict(int(g["weight_seed"]))
+    assert [k for k, _ in V.weight_norm_keys()] == list(sd) and len(sd) == 302
+    reduced = V.process_units(g["raw_units"].tolist(), reduce=True)
+    assert reduced == g["reduced_code"].tolist() and len(reduced) < len(g["raw_units"])
+    assert V.process_units([3, 3, 4, 4, 4, 3], reduce=True) == [3, 4, 3] and V.process_units([3, 3], reduce=False) == [3, 3]
+    for name, dp in (("dur", True), ("nodur", False), ("reduced", True)):
+        wav, dur = V.code_to_waveform(sd, torch.from_numpy(g[f"{name}_code"]), dur_prediction=dp)
+        assert dur.tolist() == g[f"{name}_dur"].tolist()
+        assert wav.numel() == V.HOP * int(dur.sum())
+        want = torch.from_numpy(g[f"{name}_wave"])
+        assert float((wav - want).abs().max()) < 1e-5
+        assert 0.05 < float(want.std()) < 0.5 and float(want.abs().max()) < 0.999     # audible, un-saturated signal
+    assert int(g["dur_dur"].max()) > 3 and int(g["dur_dur"].min()) == 1              # the duration head is exercised
+    assert (g["reduced_code"] < 0).sum() == 2                                         # invalid codes reach, and are dropped by, the model wrapper
