@@ -255,7 +255,7 @@ def run_ours(args):
         # ---- dominant kernel: the tcgen05 GEMM on the FFN causal conv (64 % of transformer MACs); timed live with
         # CUDA events around each of its launches during one eager denoiser call after the timed region
         t_idx = torch.tensor([start - 1], dtype=torch.int32, device=dev)
-        xb = eng.buf("s.xb", B * T, eng.zp)
+        xb = eng.buf("s.xb", B * T, eng.xw)
         times = eng.profile_launches("model.transformer.layers", lambda: eng.denoise(xb, lens, B, T, t_idx))
         conv = [ms_ for n, ms_ in times if n.endswith("ff.conv")]
         inner = 1365

@@ -34,17 +34,21 @@ class GemmSeg(C.Structure):
     _fields_ = [("a_col0", i32), ("shift_mul", i32), ("k_blocks", i32), ("w_k0", i32), ("n_mma", i32)]
 
 
+MAX_SEGS = 12   # DN_MAX_SEGS
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("B", i32), ("T", i32), ("groups", i32),
         ("A", vp), ("lda", i32), ("a_cols", i32), ("a_batch_stride", i64), ("g_a_col", i32),
         ("W", vp), ("ldw", i32), ("w_rows", i32), ("g_w_row", i32),
-        ("num_segs", i32), ("seg", GemmSeg * 4),
+        ("num_segs", i32), ("seg", GemmSeg * MAX_SEGS),
         ("dilation", i32), ("dilation_shl_group", i32), ("n_tiles", i32), ("n_out", i32), ("epi", i32),
         ("bias", vp), ("bias2", vp), ("g_bias", i32),
         ("gb", vp), ("gb_t_stride", i64), ("g_gb", i32), ("gb_half", i32), ("t_idx", vp), ("t_idx_stride", i32),
         ("out", vp), ("ldo", i32), ("out_batch_stride", i64), ("g_out_col", i32),
         ("pe", vp), ("lengths", vp),
+        ("a_fmt", i32), ("w_fmt", i32), ("out_fmt", i32), ("out_lo_col", i32),
     ]
 
 
@@ -78,6 +82,8 @@ class ResidNormDesc(C.Structure):
 
 EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_WN_GATE = range(5)
 GEMM_TCGEN05, GEMM_SIMT_CHECK, GEMM_TCGEN05_2CTA = 0, 1, 2
+FMT_BF16, FMT_F16 = 0, 1
+ABI_VERSION = 2
 
 # name -> argtypes ; every function returns int status except the two info calls
 _SIGS = {
@@ -86,18 +92,19 @@ _SIGS = {
     "dn_unit_accuracy": [vp, vp, vp, i32, i32, vp, vp],
     "dn_gather_pack": [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp],
     "dn_cast_pad_bf16": [vp, i64, i32, i32, vp, i32, vp],
+    "dn_cast_split": [vp, i64, i32, i32, vp, i32, i32, vp],
     "dn_vae_reparam": [vp, i32, vp, i32, i32, i32, i32, vp, vp],
     "dn_split_bf16x3": [vp, i64, i32, vp, vp],
-    "dn_q_sample": [vp, vp, f32, f32, i64, i32, vp, vp, i32, vp],
-    "dn_ddim_step": [vp, vp, i32, vp, vp, i64, i32, i32, vp, i32, vp],
-    "dn_ddpm_step": [vp, vp, i32, vp, vp, vp, i64, i32, vp, i32, vp],
+    "dn_q_sample": [vp, vp, f32, f32, i64, i32, vp, vp, i32, i32, vp],
+    "dn_ddim_step": [vp, vp, i32, vp, vp, i64, i32, i32, vp, i32, i32, vp],
+    "dn_ddpm_step": [vp, vp, i32, vp, vp, vp, i64, i32, vp, i32, i32, vp],
     "dn_advance_step": [vp, i32, vp],
-    "dn_adarmsnorm": [vp, vp, i32, i32, i32, vp, vp, i64, vp, i32, vp],
+    "dn_adarmsnorm": [vp, vp, i32, i32, i32, vp, vp, i64, vp, i32, i32, i32, vp],
     "dn_wavenet_gate": [vp, vp, vp, i32, i32, i32, vp, i64, vp, i32, vp],
     "dn_linear_f32": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "dn_time_features": [vp, vp, i32, i32, vp, vp],
     "dn_gemm": [C.POINTER(GemmDesc), i32, vp],
-    "dn_attention": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "dn_attention": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     # training step
     "dn_wgrad": [C.POINTER(WgradDesc), vp],
     "dn_gemm_resid_norm": [C.POINTER(ResidNormDesc), vp],

@@ -29,20 +29,29 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(smem_u32(p)));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (F16)
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 constexpr int ATT_BM = 64, ATT_BN = 64, ATT_THREADS = 128;
 
-template <int DH>
+// F16: q, k, v and the probabilities are fp16 (3 more mantissa bits than bf16; the precise VAE decoder).  out_lo_col != 0:
+// the output row is a split-precision bf16 pair [hi | lo at out_lo_col] with row stride 2 * out_lo_col.
+template <int DH, bool F16>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                  const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2,
-                 const uint32_t* __restrict__ keep, float keep_scale) {
+                 const uint32_t* __restrict__ keep, float keep_scale, int out_lo_col) {
     constexpr int LDS = DH + 8;       // padded smem row (elements): conflict-free ldmatrix
     constexpr int CH = DH / 8;        // 16-byte chunks per row
     constexpr int KS = DH / 16;       // k-steps over the head dim
@@ -119,8 +128,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
                 const int r = nb2 * 16 + (lane & 7) + (lane >> 4) * 8;
                 const int c = kk * 16 + ((lane >> 3) & 1) * 8;
                 ldsm_x4(bf, k + r * LDS + c);
-                mma_bf16(s[nb2 * 2], qf[kk], bf[0], bf[1]);
-                mma_bf16(s[nb2 * 2 + 1], qf[kk], bf[2], bf[3]);
+                mma_16<F16>(s[nb2 * 2], qf[kk], bf[0], bf[1]);
+                mma_16<F16>(s[nb2 * 2 + 1], qf[kk], bf[2], bf[3]);
             }
         }
         // ---- mask + online softmax (exp2 domain)
@@ -173,8 +182,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
                 p2 = ((wb >> (kk & 31)) & 1u) ? p2 * keep_scale : 0.f;
                 p3 = ((wb >> ((kk + 1) & 31)) & 1u) ? p3 * keep_scale : 0.f;
             }
-            pf[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(p0, p1);
-            pf[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(p2, p3);
+            pf[nb >> 1][(nb & 1) * 2 + 0] = pack16<F16>(p0, p1);
+            pf[nb >> 1][(nb & 1) * 2 + 1] = pack16<F16>(p2, p3);
         }
         l0 = l0 * a0 + rs0;
         l1 = l1 * a1 + rs1;
@@ -192,8 +201,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
                 const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int c = db2 * 16 + (lane >> 4) * 8;
                 ldsm_x4_t(bf, v + r * LDS + c);
-                mma_bf16(o[db2 * 2], pf[kk], bf[0], bf[1]);
-                mma_bf16(o[db2 * 2 + 1], pf[kk], bf[2], bf[3]);
+                mma_16<F16>(o[db2 * 2], pf[kk], bf[0], bf[1]);
+                mma_16<F16>(o[db2 * 2 + 1], pf[kk], bf[2], bf[3]);
             }
         }
         __syncthreads();
@@ -212,51 +221,66 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
         if (r0 < T) lp[r0] = m0 + log2f(l0);
         if (r1 < T) lp[r1] = m1 + log2f(l1);
     }
-    __nv_bfloat16* ob = out + (long long)b * T * (H * DH) + h * DH + (lane & 3) * 2;
+    const int ldo = out_lo_col ? 2 * out_lo_col : H * DH;
+    __nv_bfloat16* ob = out + (long long)b * T * ldo + h * DH + (lane & 3) * 2;
 #pragma unroll
     for (int i = 0; i < DH / 8; ++i) {
-        if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * (H * DH) + i * 8) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
-        if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * (H * DH) + i * 8) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
+        uint32_t h0, l0, h1, l1;
+        split_bf16(o[i][0] * i0, o[i][1] * i0, h0, l0);
+        split_bf16(o[i][2] * i1, o[i][3] * i1, h1, l1);
+        if (r0 < T) {
+            *reinterpret_cast<uint32_t*>(ob + (long long)r0 * ldo + i * 8) = h0;
+            if (out_lo_col) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * ldo + out_lo_col + i * 8) = l0;
+        }
+        if (r1 < T) {
+            *reinterpret_cast<uint32_t*>(ob + (long long)r1 * ldo + i * 8) = h1;
+            if (out_lo_col) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * ldo + out_lo_col + i * 8) = l1;
+        }
     }
 }
 
-template <int DH>
+template <int DH, bool F16 = false>
 static int launch_attention(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
-                            float* lse2 = nullptr, const uint32_t* keep = nullptr, float keep_scale = 1.f) {
+                            float* lse2 = nullptr, const uint32_t* keep = nullptr, float keep_scale = 1.f, int out_lo_col = 0) {
     constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * (DH + 8) * 2;
     static bool attr_set = false;
     if (!attr_set) {
-        DN_CUDA_OK(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_kernel<DH, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     dim3 grid((T + ATT_BM - 1) / ATT_BM, H, B);
     const float scale_log2 = (1.0f / sqrtf((float)DH)) * 1.4426950408889634f;
-    attention_kernel<DH><<<grid, ATT_THREADS, SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                         reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H, scale_log2,
-                                                         lse2, keep, keep_scale);
+    attention_kernel<DH, F16><<<grid, ATT_THREADS, SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                              reinterpret_cast<__nv_bfloat16*>(out), lengths, T, H, scale_log2,
+                                                              lse2, keep, keep_scale, out_lo_col);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
 }
 
 int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
-                        float* lse2, const uint32_t* keep, float keep_scale, bool train);
+                        float* lse2, const uint32_t* keep, float keep_scale, bool train, bool f16);
 
 }  // namespace dn
 
 extern "C" int dn_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H,
-                            int32_t dh, void* stream) {
+                            int32_t dh, int32_t fmt, int32_t out_lo_col, void* stream) {
     if (!qkv || !out || B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535) return DN_EINVAL;
+    if ((unsigned)fmt > 1u || (out_lo_col && dh != 96) || (fmt == DN_FMT_F16 && dh != 96 && dh != 64)) return DN_EINVAL;
+    if (out_lo_col && (out_lo_col < H * dh || out_lo_col % 2)) return DN_EINVAL;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dh == 96 && fmt == DN_FMT_F16)
+        return dn::launch_attention<96, true>(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, out_lo_col);
     if (dh == 64) {
         // tcgen05/TMEM kernel (attention_tc.cu); DN_ATTN_IMPL=mma selects the mma.sync kernel (bring-up / A-B timing)
         const char* e = getenv("DN_ATTN_IMPL");
         const bool use_mma = e && e[0] == 'm';
         if (!use_mma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
-            return dn::launch_attention_tc(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, false);
+            return dn::launch_attention_tc(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, false, fmt == DN_FMT_F16);
+        if (fmt == DN_FMT_F16) return DN_EINVAL;   // the mma.sync dh-64 kernel is the bf16 A/B reference only
         return dn::launch_attention<64>(qkv, out, lengths, B, T, H, st);
     }
-    if (dh == 96) return dn::launch_attention<96>(qkv, out, lengths, B, T, H, st);
+    if (dh == 96) return dn::launch_attention<96>(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, out_lo_col);
     if (dh == 32) return dn::launch_attention<32>(qkv, out, lengths, B, T, H, st);
     return DN_EINVAL;
 }
@@ -270,5 +294,5 @@ extern "C" int dn_attention_train(const void* qkv, void* out, float* lse2, const
                                         keep_scale);
     if (dh != 64) return DN_EINVAL;
     return dn::launch_attention_tc(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
-                                   keep_scale, true);
+                                   keep_scale, true, false);
 }

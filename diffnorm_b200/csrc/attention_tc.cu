@@ -34,14 +34,17 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-// instruction descriptor: bf16 x bf16 -> fp32, M = 128, runtime N, A K-major, B K-major (0) or MN-major (1)
-__device__ __forceinline__ uint32_t ta_idesc(uint32_t n, uint32_t b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: 16-bit x 16-bit -> fp32 (both operands bf16, or both fp16), M = 128, runtime N, A K-major,
+// B K-major (0) or MN-major (1)
+__device__ __forceinline__ uint32_t ta_idesc(uint32_t n, uint32_t b_mn_major, bool f16) {
+    const uint32_t fm = f16 ? 0u : 1u;
+    return (1u << 4) | (fm << 7) | (fm << 10) | (b_mn_major << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // TRAIN: additionally applies the attention-dropout keep bits (LM:338; keep [B,H,T,ceil(T/32)] words, bit k%32 of word
 // k/32 = key k kept; P is scaled by keep_scale = 1/(1-p) after the row sum) and saves L2 = m + log2(l) per query row.
-template <bool TRAIN>
+// F16: q, k, v, the probabilities P and the output are fp16 instead of bf16 (the sampler loop's format).
+template <bool TRAIN, bool F16>
 __global__ void __launch_bounds__(TA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
                     const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2,
@@ -117,7 +120,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
         }
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
-            const uint32_t id_s = ta_idesc(TA_BN, 0), id_o = ta_idesc(TA_DH, 1);
+            const uint32_t id_s = ta_idesc(TA_BN, 0, F16), id_o = ta_idesc(TA_DH, 1, F16);
             const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
             auto issue_s = [&](int j) {
                 const int st = j & 1;
@@ -231,7 +234,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
                         e0 = ((kw >> i) & 1u) ? e0 * keep_scale : 0.f;
                         e1 = ((kw >> (i + 1)) & 1u) ? e1 * keep_scale : 0.f;
                     }
-                    w[i >> 1] = pack_bf16(e0, e1);
+                    w[i >> 1] = pack16<F16>(e0, e1);
                 }
             };
             uint32_t w0[16], w1[16];
@@ -284,8 +287,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
                     *reinterpret_cast<uint4*>(op + i) =
-                        make_uint4(pack_bf16(o[i] * inv, o[i + 1] * inv), pack_bf16(o[i + 2] * inv, o[i + 3] * inv),
-                                   pack_bf16(o[i + 4] * inv, o[i + 5] * inv), pack_bf16(o[i + 6] * inv, o[i + 7] * inv));
+                        make_uint4(pack16<F16>(o[i] * inv, o[i + 1] * inv), pack16<F16>(o[i + 2] * inv, o[i + 3] * inv),
+                                   pack16<F16>(o[i + 4] * inv, o[i + 5] * inv), pack16<F16>(o[i + 6] * inv, o[i + 7] * inv));
                 }
             }
         } else if (t < T) {
@@ -303,13 +306,15 @@ int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
                     const cuuint32_t* box);
 
 int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
-                        float* lse2, const uint32_t* keep, float keep_scale, bool train) {
+                        float* lse2, const uint32_t* keep, float keep_scale, bool train, bool f16) {
     static bool attr_set = false;
     if (!attr_set) {
-        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         attr_set = true;
     }
+    if (train && f16) return DN_EINVAL;
     CUtensorMap m;
     const int ld = 3 * H * TA_DH;
     cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
@@ -320,10 +325,13 @@ int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int 
     dim3 grid((T + TA_BM - 1) / TA_BM, H, B);
     const float scale_log2 = (1.0f / sqrtf((float)TA_DH)) * 1.4426950408889634f;
     if (train)
-        DN_CUDA_OK(launch_ex(attention_tc_kernel<true>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
+        DN_CUDA_OK(launch_ex(attention_tc_kernel<true, false>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
                              lengths, T, H, scale_log2, lse2, keep, keep_scale));
+    else if (f16)
+        DN_CUDA_OK(launch_ex(attention_tc_kernel<false, true>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
+                             lengths, T, H, scale_log2, (float*)nullptr, (const uint32_t*)nullptr, 1.f));
     else
-        DN_CUDA_OK(launch_ex(attention_tc_kernel<false>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
+        DN_CUDA_OK(launch_ex(attention_tc_kernel<false, false>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
                              lengths, T, H, scale_log2, (float*)nullptr, (const uint32_t*)nullptr, 1.f));
     DN_LAUNCH_CHECK();
     count_launch();

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -278,6 +279,13 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// instruction descriptor of kind::f16: fp32 accumulate, both operands K-major, M = m (128, or 256 for a CTA pair), runtime
+// N (multiple of 16); the 16-bit formats of A and B are independent fields (bits 7-9 / 10-12: 0 = fp16, 1 = bf16)
+__device__ __forceinline__ uint32_t umma_idesc_16(uint32_t m, uint32_t n, int a_fmt, int b_fmt) {
+    return (1u << 4) | ((a_fmt == DN_FMT_BF16 ? 1u : 0u) << 7) | ((b_fmt == DN_FMT_BF16 ? 1u : 0u) << 10) | ((n >> 3) << 17) |
+           ((m >> 4) << 24);
+}
+
 // ---------------------------------------------------------------- CTA pair (cta_group::2): two SMs work on one M = 256 tile
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -434,6 +442,27 @@ __device__ __forceinline__ float wn_gate(float u) { return tanh_fast(u) * (0.5f 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+// fp16 pair, saturating at the largest finite value (an out-of-range activation must not become inf / NaN downstream)
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    uint32_t r;   // one F2FP.SATFINITE.F16.F32.PACK_AB (first source operand lands in the upper half)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+    if constexpr (F16) return pack_f16(a, b);
+    else return pack_bf16(a, b);
+}
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16(v)); }
+// split-precision pair: hi = bf16(v), lo = bf16(v - hi); hi + lo carries v to ~2^-17 relative
+__device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16(a, b);
+    lo = pack_bf16(a - round_bf16(a), b - round_bf16(b));
+}
+__device__ __forceinline__ float load16(uint16_t bits, int fmt) {
+    if (fmt == DN_FMT_F16) return __half2float(*reinterpret_cast<const __half*>(&bits));
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&bits));
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

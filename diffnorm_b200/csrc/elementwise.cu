@@ -30,6 +30,27 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, i
     }
 }
 
+// split-precision staging: hi = bf16(x) in [0, C), lo = bf16(x - hi) in [lo_col, lo_col + C), zeros elsewhere
+__global__ void cast_split_kernel(const float* __restrict__ src, long long rows, int C, int lds,
+                                  __nv_bfloat16* __restrict__ dst, int ldo, int lo_col) {
+    const int groups = ldo / 8;
+    const long long total = rows * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int c = (int)(i % groups) * 8;
+        const bool is_lo = c >= lo_col;
+        const int cs = is_lo ? c - lo_col : c;      // source column
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = (cs + k < C) ? src[r * lds + cs + k] : 0.f;
+            if (is_lo) v[k] -= round_bf16(v[k]);
+        }
+        *reinterpret_cast<uint4*>(dst + r * ldo + c) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- bf16 split staging
 // fp32 [rows, C] -> bf16 [rows, 3C] = [hi | hi | lo] with hi = bf16(x), lo = bf16(x - hi): against weights packed as
 // [hi | lo | hi] one bf16 GEMM over K = 3C computes x.w to ~2^-16 relative (the lo.lo term is dropped) — the fp32-grade
@@ -166,9 +187,11 @@ struct DdpmOp {
     static constexpr bool reads_x = true;
 };
 
+// xlo != 0: the staging row is a split-precision pair: hi in [0, z), lo = bf16(v - hi) in [xlo, xlo + z); the columns in
+// between and after are pad (zero).  The thread that owns latent columns [c, c+4) writes both halves.
 template <class Op>
 __device__ __forceinline__ void latent_update_loop(const Op& op, float* __restrict__ x, long long rows, int z,
-                                                   __nv_bfloat16* __restrict__ xb, int ldx) {
+                                                   __nv_bfloat16* __restrict__ xb, int ldx, int xlo) {
     const int zc = xb ? ldx : z;  // iterate over the padded width so the pad columns get zeroed
     const int groups = zc / 4;
     const long long total = rows * groups;
@@ -180,8 +203,13 @@ __device__ __forceinline__ void latent_update_loop(const Op& op, float* __restri
             if (Op::reads_x) xv = *reinterpret_cast<const float4*>(x + r * z + c);
             const float4 v = op(r, c, z, xv);
             *reinterpret_cast<float4*>(x + r * z + c) = v;
-            if (xb) store_bf16x4(xb + r * ldx + c, v.x, v.y, v.z, v.w);
-        } else {
+            if (xb) {
+                store_bf16x4(xb + r * ldx + c, v.x, v.y, v.z, v.w);
+                if (xlo)
+                    store_bf16x4(xb + r * ldx + xlo + c, v.x - round_bf16(v.x), v.y - round_bf16(v.y), v.z - round_bf16(v.z),
+                                 v.w - round_bf16(v.w));
+            }
+        } else if (!xlo || c < xlo || c >= xlo + z) {
             store_bf16x4(xb + r * ldx + c, 0.f, 0.f, 0.f, 0.f);
         }
     }
@@ -189,34 +217,36 @@ __device__ __forceinline__ void latent_update_loop(const Op& op, float* __restri
 
 __global__ void __launch_bounds__(EW_THREADS)
 q_sample_kernel(const float* __restrict__ z_lat, const float* __restrict__ eps, float ca, float cb, long long rows, int z,
-                float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int ldx) {
-    latent_update_loop(QSampleOp{z_lat, eps, ca, cb}, x, rows, z, xb, ldx);
+                float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int ldx, int xlo) {
+    latent_update_loop(QSampleOp{z_lat, eps, ca, cb}, x, rows, z, xb, ldx, xlo);
 }
 
 __global__ void __launch_bounds__(EW_THREADS)
 ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eh, int lde, const float* __restrict__ table,
-                 const int* __restrict__ t_idx, long long rows, int z, int mode, __nv_bfloat16* __restrict__ xb, int ldx) {
+                 const int* __restrict__ t_idx, long long rows, int z, int mode, __nv_bfloat16* __restrict__ xb, int ldx,
+                 int xlo) {
     const float* cf = table + (long long)t_idx[0] * 8;
-    latent_update_loop(DdimOp{eh, lde, mode, cf[0], cf[1], cf[2], cf[3], cf[4], cf[5]}, x, rows, z, xb, ldx);
+    latent_update_loop(DdimOp{eh, lde, mode, cf[0], cf[1], cf[2], cf[3], cf[4], cf[5]}, x, rows, z, xb, ldx, xlo);
 }
 
 __global__ void __launch_bounds__(EW_THREADS)
 ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eh, int lde, const float* __restrict__ noise,
                  const float* __restrict__ table, const int* __restrict__ t_idx, long long rows, int z,
-                 __nv_bfloat16* __restrict__ xb, int ldx) {
+                 __nv_bfloat16* __restrict__ xb, int ldx, int xlo) {
     const float* cf = table + (long long)t_idx[0] * 8;
-    latent_update_loop(DdpmOp{eh, noise, lde, cf[0], cf[1], cf[2], cf[3], cf[4]}, x, rows, z, xb, ldx);
+    latent_update_loop(DdpmOp{eh, noise, lde, cf[0], cf[1], cf[2], cf[3], cf[4]}, x, rows, z, xb, ldx, xlo);
 }
 
 __global__ void advance_step_kernel(int* t_idx, int delta) { t_idx[0] += delta; }
 
 // ---------------------------------------------------------------------------------------------- adaptive RMSNorm
 // one warp per frame; C in {512, 768} (any multiple of 128 up to 1024): each lane owns C/32 values as float4s
-template <int C>
+// OUT 0: bf16 [rows, C]; OUT 1: split pair, row = [hi (C) | ... | lo at lo_col (C)] with row stride 2 * lo_col; OUT 2: fp16
+template <int C, int OUT>
 __global__ void __launch_bounds__(EW_THREADS)
 adarmsnorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int T,
                   const float* __restrict__ gamma_p, const float* __restrict__ gb, long long gb_t_stride,
-                  const int* __restrict__ t_idx, int t_idx_stride) {
+                  const int* __restrict__ t_idx, int t_idx_stride, int lo_col) {
     constexpr int V = C / 128;  // float4 per lane
     pdl_trigger();
     pdl_wait();
@@ -255,7 +285,15 @@ adarmsnorm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, 
                 o[0] = o[0] * ga.x + be.x; o[1] = o[1] * ga.y + be.y;
                 o[2] = o[2] * ga.z + be.z; o[3] = o[3] * ga.w + be.w;
             }
-            *reinterpret_cast<uint2*>(out + r * C + c) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+            if constexpr (OUT == 1) {
+                uint32_t h0, l0, h1, l1;
+                split_bf16(o[0], o[1], h0, l0);
+                split_bf16(o[2], o[3], h1, l1);
+                *reinterpret_cast<uint2*>(out + r * 2 * lo_col + c) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(out + r * 2 * lo_col + lo_col + c) = make_uint2(l0, l1);
+            } else {
+                *reinterpret_cast<uint2*>(out + r * C + c) = make_uint2(pack16<OUT == 2>(o[0], o[1]), pack16<OUT == 2>(o[2], o[3]));
+            }
         }
     }
 }
@@ -402,6 +440,17 @@ extern "C" int dn_cast_pad_bf16(const float* src, int64_t rows, int32_t C, int32
     return 0;
 }
 
+extern "C" int dn_cast_split(const float* src, int64_t rows, int32_t C, int32_t lds, void* dst, int32_t ldo, int32_t lo_col,
+                             void* stream) {
+    if (!src || !dst || rows <= 0 || ldo % 8 || lo_col % 8 || lo_col < 0) return DN_EINVAL;
+    if (lo_col ? (C > lo_col || lo_col + C > ldo) : C > ldo) return DN_EINVAL;
+    cast_split_kernel<<<ew_grid(rows * (ldo / 8), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
+        src, rows, C, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldo, lo_col ? lo_col : ldo);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
 extern "C" int dn_split_bf16x3(const float* src, int64_t rows, int32_t C, void* dst, void* stream) {
     if (!src || !dst || rows <= 0 || C <= 0 || C % 4 || (reinterpret_cast<uintptr_t>(src) & 15)) return DN_EINVAL;
     split_bf16x3_kernel<<<ew_grid(rows * (C / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(src, rows, C,
@@ -427,38 +476,42 @@ extern "C" int dn_vae_reparam(const float* params, int32_t ldp, const float* eps
 }
 
 extern "C" int dn_q_sample(const float* z_lat, const float* eps, float sqrt_ab, float sqrt_1m_ab, int64_t rows,
-                           int32_t z, float* x, void* x_bf16, int32_t ldx, void* stream) {
+                           int32_t z, float* x, void* x_bf16, int32_t ldx, int32_t x_lo_col, void* stream) {
     if (!z_lat || !eps || !x || rows <= 0 || z <= 0 || z % 4 || (x_bf16 && (ldx < z || ldx % 4))) return DN_EINVAL;
+    if (x_lo_col && (!x_bf16 || x_lo_col % 4 || x_lo_col < z || x_lo_col + z > ldx)) return DN_EINVAL;
     if ((reinterpret_cast<uintptr_t>(z_lat) | reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(x)) & 15)
         return DN_EINVAL;
     q_sample_kernel<<<ew_grid(rows * ((x_bf16 ? ldx : z) / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
-        z_lat, eps, sqrt_ab, sqrt_1m_ab, rows, z, x, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx);
+        z_lat, eps, sqrt_ab, sqrt_1m_ab, rows, z, x, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx, x_lo_col);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
 }
 
 extern "C" int dn_ddim_step(float* x, const float* eps_hat, int32_t lde, const float* coef_table, const int32_t* t_idx,
-                            int64_t rows, int32_t z, int32_t mode, void* x_bf16, int32_t ldx, void* stream) {
+                            int64_t rows, int32_t z, int32_t mode, void* x_bf16, int32_t ldx, int32_t x_lo_col, void* stream) {
     if (!x || !eps_hat || !coef_table || !t_idx || rows <= 0 || z <= 0 || lde < z) return DN_EINVAL;
+    if (x_lo_col && (!x_bf16 || x_lo_col % 4 || x_lo_col < z || x_lo_col + z > ldx)) return DN_EINVAL;
     if (z % 4 || lde % 4 || (x_bf16 && (ldx < z || ldx % 4)) ||
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps_hat)) & 15))
         return DN_EINVAL;
     ddim_step_kernel<<<ew_grid(rows * ((x_bf16 ? ldx : z) / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
-        x, eps_hat, lde, coef_table, t_idx, rows, z, mode, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx);
+        x, eps_hat, lde, coef_table, t_idx, rows, z, mode, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx, x_lo_col);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
 }
 
 extern "C" int dn_ddpm_step(float* x, const float* eps_hat, int32_t lde, const float* noise, const float* coef_table,
-                            const int32_t* t_idx, int64_t rows, int32_t z, void* x_bf16, int32_t ldx, void* stream) {
+                            const int32_t* t_idx, int64_t rows, int32_t z, void* x_bf16, int32_t ldx, int32_t x_lo_col,
+                            void* stream) {
     if (!x || !eps_hat || !noise || !coef_table || !t_idx || rows <= 0 || z <= 0 || lde < z) return DN_EINVAL;
+    if (x_lo_col && (!x_bf16 || x_lo_col % 4 || x_lo_col < z || x_lo_col + z > ldx)) return DN_EINVAL;
     if (z % 4 || lde % 4 || (x_bf16 && (ldx < z || ldx % 4)) ||
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps_hat) | reinterpret_cast<uintptr_t>(noise)) & 15))
         return DN_EINVAL;
     ddpm_step_kernel<<<ew_grid(rows * ((x_bf16 ? ldx : z) / 4), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
-        x, eps_hat, lde, noise, coef_table, t_idx, rows, z, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx);
+        x, eps_hat, lde, noise, coef_table, t_idx, rows, z, reinterpret_cast<__nv_bfloat16*>(x_bf16), ldx, x_lo_col);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -474,19 +527,34 @@ extern "C" int dn_advance_step(int32_t* t_idx, int32_t delta, void* stream) {
 
 extern "C" int dn_adarmsnorm(const float* x, void* out, int32_t B, int32_t T, int32_t C, const float* gamma_p,
                              const float* gb, int64_t gb_t_stride, const int32_t* t_idx, int32_t t_idx_stride,
-                             void* stream) {
+                             int32_t out_lo_col, int32_t out_fmt, void* stream) {
     if (!x || !out || B <= 0 || T <= 0 || (gb && !t_idx)) return DN_EINVAL;
+    if (out_lo_col && (out_lo_col < C || out_lo_col % 4 || out_fmt != DN_FMT_BF16)) return DN_EINVAL;
+    if ((unsigned)out_fmt > 1u) return DN_EINVAL;
     const long long rows = (long long)B * T;
     const int grid = ew_grid(rows, EW_THREADS / 32);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#define DN_NORM_CASE(CC)                                                                                                        \
+    case CC:                                                                                                                    \
+        if (out_lo_col)                                                                                                         \
+            DN_CUDA_OK(launch_ex(adarmsnorm_kernel<CC, 1>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb,         \
+                                 (long long)gb_t_stride, t_idx, t_idx_stride, out_lo_col));                                     \
+        else if (out_fmt == DN_FMT_F16)                                                                                         \
+            DN_CUDA_OK(launch_ex(adarmsnorm_kernel<CC, 2>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb,         \
+                                 (long long)gb_t_stride, t_idx, t_idx_stride, 0));                                              \
+        else                                                                                                                    \
+            DN_CUDA_OK(launch_ex(adarmsnorm_kernel<CC, 0>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb,         \
+                                 (long long)gb_t_stride, t_idx, t_idx_stride, 0));                                              \
+        break;
     switch (C) {
-        case 128: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<128>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
-        case 256: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<256>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
-        case 512: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<512>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
-        case 768: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<768>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
-        case 1024: DN_CUDA_OK(launch_ex(adarmsnorm_kernel<1024>, grid, EW_THREADS, 0, ST(stream), 1, x, o, B, T, gamma_p, gb, (long long)gb_t_stride, t_idx, t_idx_stride)); break;
+        DN_NORM_CASE(128)
+        DN_NORM_CASE(256)
+        DN_NORM_CASE(512)
+        DN_NORM_CASE(768)
+        DN_NORM_CASE(1024)
         default: return DN_EINVAL;
     }
+#undef DN_NORM_CASE
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

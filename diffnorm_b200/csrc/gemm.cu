@@ -60,7 +60,9 @@ __device__ __forceinline__ const float* gb_row(const dn_gemm_desc& p, int b, int
 // loads its own 128 A rows and HALF of the W tile's rows, the leader CTA issues the MMAs for both, completion is
 // multicast to both CTAs' barriers, and each CTA runs the unchanged epilogue on its own 128 accumulator rows.  Per flop
 // the pair reads a third less shared memory and fetches each W tile once instead of twice.
-template <int EPI, int CTAS>
+// MODE 0: 16-bit outputs are bf16; MODE 1: split-precision output (hi | lo bf16 pairs, full-precision erf / tanh / exp in
+// the GEGLU / gate epilogues); MODE 2: fp16 output (one saturating F2FP per pair, same cost as the bf16 pack).
+template <int EPI, int CTAS, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmW128, const __grid_constant__ CUtensorMap tmW64,
@@ -181,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int s = 0; s < p.num_segs; ++s) {
                     const dn_gemm_seg sg = p.seg[s];
                     const uint32_t nrows = sg.n_mma ? sg.n_mma : n_full;
-                    const uint32_t idesc = CTAS == 2 ? umma_idesc_bf16_m256(nrows) : umma_idesc_bf16_m128(nrows);
+                    const uint32_t idesc = umma_idesc_16(CTAS == 2 ? 256u : 128u, nrows, p.a_fmt, p.w_fmt);
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
@@ -241,9 +243,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.lengths && t >= p.lengths[c.b]) pos = 0;
                     pe_row = (long long)pos * p.n_out;
                 }
+                constexpr int npass = (EPI == DN_EPI_BF16 && MODE == 1) ? 2 : 1;   // split output: hi pass, then lo = v - hi
                 for (int u = half; u < WT / UCOLS; u += 2) {
                     const int col = c.n * WT + u * UCOLS;
                     if (col >= p.n_out) break;
+                    for (int pass = 0; pass < npass; ++pass) {
                     if (issuer) bulk_wait_read0();          // previous store has finished reading the unit
                     named_bar_sync(bar_id, 128);
 #pragma unroll
@@ -264,10 +268,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             o[3] = v[j * 8 + 3] + b0.w; o[4] = v[j * 8 + 4] + b1.x; o[5] = v[j * 8 + 5] + b1.y;
                             o[6] = v[j * 8 + 6] + b1.z; o[7] = v[j * 8 + 7] + b1.w;
                             if constexpr (EPI == DN_EPI_BF16) {
-                                const int chunk = sub * 4 + j;  // 16-byte chunk = 8 bf16
+                                if (MODE == 1 && pass) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) o[i] -= round_bf16(o[i]);
+                                }
+                                const int chunk = sub * 4 + j;  // 16-byte chunk = 8 x 16 bit
                                 *reinterpret_cast<uint4*>(srow + ((chunk ^ sw) << 4)) =
-                                    make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                               pack_bf16(o[6], o[7]));
+                                    make_uint4(pack16<MODE == 2>(o[0], o[1]), pack16<MODE == 2>(o[2], o[3]),
+                                               pack16<MODE == 2>(o[4], o[5]), pack16<MODE == 2>(o[6], o[7]));
                             } else {
                                 if (EPI == DN_EPI_F32 && pe_row >= 0 && cj + 8 <= p.n_out) {
                                     const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.pe + pe_row + cj));
@@ -288,8 +296,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if constexpr (EPI == DN_EPI_RESID)
                             tma_reduce_add_3d(&tmOut, stage_buf, ocol0 + col, c.t0, c.b);
                         else
-                            tma_store_3d(&tmOut, stage_buf, ocol0 + col, c.t0, c.b);
+                            tma_store_3d(&tmOut, stage_buf, ocol0 + col + pass * p.out_lo_col, c.t0, c.b);
                         bulk_commit();
+                    }
                     }
                 }
             } else {
@@ -297,6 +306,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float* gbr = (EPI == DN_EPI_WN_GATE) ? gb_row(p, c.b, c.g) : nullptr;
                 const int col = c.n * 128 + half * 64;  // logical output column of this warpgroup's unit
                 if (col < p.n_out) {
+                    constexpr bool precise = MODE == 1;   // split output: full-precision erf / tanh / exp, then hi | lo
+                    for (int pass = 0; pass < (precise ? 2 : 1); ++pass) {
                     if (issuer) bulk_wait_read0();
                     if constexpr (EPI == DN_EPI_GEGLU) {
                         // this warpgroup's 64 x-bias + 64 gate-bias values of the tile: one global load per thread, shared
@@ -336,10 +347,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const float4 b0 = *reinterpret_cast<const float4*>(sbias + 64 + cc), b1 = *reinterpret_cast<const float4*>(sbias + 64 + cc + 4);
                                 pa[0] = a0.x; pa[1] = a0.y; pa[2] = a0.z; pa[3] = a0.w; pa[4] = a1.x; pa[5] = a1.y; pa[6] = a1.z; pa[7] = a1.w;
                                 pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
+                                if constexpr (precise) {
 #pragma unroll
-                                for (int i = 0; i < 8; i += 2)
-                                    geglu2(hi[j * 8 + i], hi[j * 8 + i + 1], pb[i], pb[i + 1], lo[j * 8 + i], lo[j * 8 + i + 1],
-                                           pa[i], pa[i + 1], o[i], o[i + 1]);
+                                    for (int i = 0; i < 8; ++i) o[i] = gelu_erf(hi[j * 8 + i] + pb[i]) * (lo[j * 8 + i] + pa[i]);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; i += 2)
+                                        geglu2(hi[j * 8 + i], hi[j * 8 + i + 1], pb[i], pb[i + 1], lo[j * 8 + i], lo[j * 8 + i + 1],
+                                               pa[i], pa[i + 1], o[i], o[i + 1]);
+                                }
                             } else {
                                 const int oc = c.g * p.g_bias + cj;
                                 float ga[8], be[8];
@@ -350,20 +366,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const float uu = fmaf(lo[j * 8 + i] + pa[i], ga[i], be[i]);
-                                    o[i] = wn_gate(uu) + hi[j * 8 + i] + pb[i];
+                                    const float gt = precise ? tanhf(uu) / (1.f + expf(-uu)) : wn_gate(uu);
+                                    o[i] = gt + hi[j * 8 + i] + pb[i];
                                 }
+                            }
+                            if (precise && pass) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o[i] -= round_bf16(o[i]);
                             }
                             const int chunk = sub * 4 + j;
                             *reinterpret_cast<uint4*>(srow + ((chunk ^ sw) << 4)) =
-                                make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                           pack_bf16(o[6], o[7]));
+                                make_uint4(pack16<MODE == 2>(o[0], o[1]), pack16<MODE == 2>(o[2], o[3]),
+                                           pack16<MODE == 2>(o[4], o[5]), pack16<MODE == 2>(o[6], o[7]));
                         }
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(bar_id, 128);
                     if (issuer) {
-                        tma_store_3d(&tmOut, stage_buf, ocol0 + col, c.t0, c.b);
+                        tma_store_3d(&tmOut, stage_buf, ocol0 + col + pass * p.out_lo_col, c.t0, c.b);
                         bulk_commit();
+                    }
                     }
                 }
             }
@@ -406,27 +428,39 @@ __global__ void gemm_check_kernel(const dn_gemm_desc p) {
         const bool dual = p.epi == DN_EPI_GEGLU || p.epi == DN_EPI_WN_GATE;
         const int wrow_lo = g * p.g_w_row + (dual ? (oc / 128) * WT + (oc % 128) : oc);
         const int wrow_hi = wrow_lo + 128;
-        const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(p.A);
-        const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(p.W);
+        const uint16_t* A = reinterpret_cast<const uint16_t*>(p.A);
+        const uint16_t* W = reinterpret_cast<const uint16_t*>(p.W);
         float lo = 0.f, hi = 0.f;
         for (int s = 0; s < p.num_segs; ++s) {
             const dn_gemm_seg sg = p.seg[s];
             const int ts = t - sg.shift_mul * d;
             if (ts < 0) continue;
-            const __nv_bfloat16* a = A + (long long)b * p.a_batch_stride + (long long)ts * p.lda + sg.a_col0 + g * p.g_a_col;
-            const __nv_bfloat16* wl = W + (long long)wrow_lo * p.ldw + sg.w_k0;
-            const __nv_bfloat16* wh = W + (long long)wrow_hi * p.ldw + sg.w_k0;
+            const uint16_t* a = A + (long long)b * p.a_batch_stride + (long long)ts * p.lda + sg.a_col0 + g * p.g_a_col;
+            const uint16_t* wl = W + (long long)wrow_lo * p.ldw + sg.w_k0;
+            const uint16_t* wh = W + (long long)wrow_hi * p.ldw + sg.w_k0;
             const int klen = sg.k_blocks * BK;
             for (int k = 0; k < klen; ++k) {
                 // columns past the tensor extent read as zero (TMA out-of-bounds fill)
-                const float av = (sg.a_col0 + g * p.g_a_col + k < p.a_cols) ? __bfloat162float(a[k]) : 0.f;
-                lo += av * __bfloat162float(wl[k]);
-                if (dual && sg.n_mma == 0) hi += av * __bfloat162float(wh[k]);
+                const float av = (sg.a_col0 + g * p.g_a_col + k < p.a_cols) ? load16(a[k], p.a_fmt) : 0.f;
+                lo += av * load16(wl[k], p.w_fmt);
+                if (dual && sg.n_mma == 0) hi += av * load16(wh[k], p.w_fmt);
             }
         }
         const long long o = (long long)b * p.out_batch_stride + (long long)t * p.ldo + g * p.g_out_col + oc;
+        // 16-bit outputs: bf16 | fp16 | split bf16 pair (hi at o, lo = v - hi at o + out_lo_col)
+        auto store16 = [&](float v) {
+            if (p.out_lo_col) {
+                const __nv_bfloat16 h = __float2bfloat16(v);
+                reinterpret_cast<__nv_bfloat16*>(p.out)[o] = h;
+                reinterpret_cast<__nv_bfloat16*>(p.out)[o + p.out_lo_col] = __float2bfloat16(v - __bfloat162float(h));
+            } else if (p.out_fmt == DN_FMT_F16) {
+                reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+            } else {
+                reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(v);
+            }
+        };
         if (p.epi == DN_EPI_BF16) {
-            reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f));
+            store16(lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f));
         } else if (p.epi == DN_EPI_F32) {
             float v = lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f);
             if (p.pe) {
@@ -441,13 +475,13 @@ __global__ void gemm_check_kernel(const dn_gemm_desc p) {
             const int wr = g * p.g_bias + (oc / 128) * WT + (oc % 128);
             const float x = lo + (p.bias ? p.bias[wr] : 0.f);
             const float gt = hi + (p.bias ? p.bias[wr + 128] : 0.f);
-            reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(gelu_erf(gt) * x);
+            store16(gelu_erf(gt) * x);
         } else {
             float u = lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f);
             const float rr = hi + (p.bias2 ? p.bias2[g * p.g_bias + oc] : 0.f);
             const float* gbr = gb_row(p, b, g);
             if (gbr) u = u * gbr[oc] + gbr[p.gb_half + oc];
-            reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(tanhf(u) / (1.f + expf(-u)) + rr);
+            store16(tanhf(u) / (1.f + expf(-u)) + rr);
         }
     }
 }
@@ -514,19 +548,19 @@ int num_sms() {
     return n;
 }
 
-template <int EPI, int CTAS>
+template <int EPI, int CTAS, int MODE>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& w128, const CUtensorMap& w64,
                      const CUtensorMap& o, const dn_gemm_desc& d, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        DN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_set = true;
     }
     const int tiles_t = (d.T + BM * CTAS - 1) / (BM * CTAS);
     const long long total = (long long)d.groups * d.B * tiles_t * d.n_tiles;
     const int units = num_sms() / CTAS;   // CTAs (or CTA pairs) resident at once
     const int grid = (int)(total < units ? total : units) * CTAS;
-    DN_CUDA_OK(launch_ex(gemm_tc_kernel<EPI, CTAS>, grid, GEMM_THREADS, GEMM_SMEM, st, CTAS, a, w, w128, w64, o, d));
+    DN_CUDA_OK(launch_ex(gemm_tc_kernel<EPI, CTAS, MODE>, grid, GEMM_THREADS, GEMM_SMEM, st, CTAS, a, w, w128, w64, o, d));
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -539,12 +573,17 @@ using namespace dn;
 extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
     if (!dp || !dp->A || !dp->W || !dp->out) return DN_EINVAL;
     const dn_gemm_desc& d = *dp;
-    if (d.B <= 0 || d.T <= 0 || d.groups <= 0 || d.num_segs <= 0 || d.num_segs > 4 || d.n_tiles <= 0) return DN_EINVAL;
+    if (d.B <= 0 || d.T <= 0 || d.groups <= 0 || d.num_segs <= 0 || d.num_segs > DN_MAX_SEGS || d.n_tiles <= 0) return DN_EINVAL;
     if (d.n_out % 8 || d.lda % 8 || d.ldw % 8 || d.w_rows % 16) return DN_EINVAL;
     if ((reinterpret_cast<uintptr_t>(d.A) | reinterpret_cast<uintptr_t>(d.W) | reinterpret_cast<uintptr_t>(d.out)) & 15)
         return DN_EINVAL;
     const bool f32out = d.epi == DN_EPI_F32 || d.epi == DN_EPI_RESID;
     if (d.ldo % (f32out ? 4 : 8) || d.g_out_col % 8) return DN_EINVAL;
+    if ((unsigned)d.a_fmt > 1u || (unsigned)d.w_fmt > 1u || (unsigned)d.out_fmt > 1u || d.out_lo_col < 0) return DN_EINVAL;
+    if (d.out_lo_col && (f32out || d.n_out % 64 || d.out_lo_col % 8 || d.out_fmt != DN_FMT_BF16)) return DN_EINVAL;
+    if (d.out_fmt == DN_FMT_F16 && f32out) return DN_EINVAL;
+    if (d.a_fmt != d.w_fmt) return DN_EINVAL;   // kind::f16 MMAs take both operands in ONE 16-bit format (mixing faults)
+    const int mode = d.out_lo_col ? 1 : (d.out_fmt == DN_FMT_F16 ? 2 : 0);
     for (int s = 0; s < d.num_segs; ++s)
         if (d.seg[s].k_blocks <= 0 || (d.seg[s].n_mma != 0 && d.seg[s].n_mma != 128) || d.seg[s].a_col0 % 8 ||
             d.seg[s].w_k0 % 8)
@@ -585,7 +624,7 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
     {
         // output map: columns are clipped at the logical extent so partial tiles never touch neighbouring data
         const int esz = f32out ? 4 : 2;
-        const long long ocols = d.groups > 1 ? (long long)(d.groups - 1) * d.g_out_col + d.n_out : d.n_out;
+        const long long ocols = (d.groups > 1 ? (long long)(d.groups - 1) * d.g_out_col + d.n_out : d.n_out) + d.out_lo_col;
         cuuint64_t dims[3] = {(cuuint64_t)ocols, (cuuint64_t)d.T, (cuuint64_t)d.B};
         cuuint64_t str[2] = {(cuuint64_t)d.ldo * esz, (cuuint64_t)d.out_batch_stride * esz};
         cuuint32_t box[3] = {(cuuint32_t)(f32out ? 32 : 64), BM, 1};
@@ -593,25 +632,17 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
                            dims, str, box);
         if (r) return r;
     }
-    if (impl == DN_GEMM_TCGEN05_2CTA) {
-        switch (d.epi) {
-            case DN_EPI_BF16: return launch_tc<DN_EPI_BF16, 2>(ma, mw, mw128, mw64, mo, d, st);
-            case DN_EPI_F32: return launch_tc<DN_EPI_F32, 2>(ma, mw, mw128, mw64, mo, d, st);
-            case DN_EPI_RESID: return launch_tc<DN_EPI_RESID, 2>(ma, mw, mw128, mw64, mo, d, st);
-            case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU, 2>(ma, mw, mw128, mw64, mo, d, st);
-            case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE, 2>(ma, mw, mw128, mw64, mo, d, st);
-            default: return DN_EINVAL;
-        }
-    }
+#define DN_LAUNCH_TC(EPI, CT, MD) launch_tc<EPI, CT, MD>(ma, mw, mw128, mw64, mo, d, st)
+#define DN_BY_CTAS(EPI, MD) (impl == DN_GEMM_TCGEN05_2CTA ? DN_LAUNCH_TC(EPI, 2, MD) : DN_LAUNCH_TC(EPI, 1, MD))
     switch (d.epi) {
-        case DN_EPI_BF16: return launch_tc<DN_EPI_BF16, 1>(ma, mw, mw128, mw64, mo, d, st);
-        case DN_EPI_F32: return launch_tc<DN_EPI_F32, 1>(ma, mw, mw128, mw64, mo, d, st);
-        case DN_EPI_RESID: return launch_tc<DN_EPI_RESID, 1>(ma, mw, mw128, mw64, mo, d, st);
-        case DN_EPI_GEGLU: return launch_tc<DN_EPI_GEGLU, 1>(ma, mw, mw128, mw64, mo, d, st);
-        case DN_EPI_WN_GATE: return launch_tc<DN_EPI_WN_GATE, 1>(ma, mw, mw128, mw64, mo, d, st);
+        case DN_EPI_BF16: return mode == 1 ? DN_BY_CTAS(DN_EPI_BF16, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_BF16, 2) : DN_BY_CTAS(DN_EPI_BF16, 0);
+        case DN_EPI_F32: return DN_BY_CTAS(DN_EPI_F32, 0);
+        case DN_EPI_RESID: return DN_BY_CTAS(DN_EPI_RESID, 0);
+        case DN_EPI_GEGLU: return mode == 1 ? DN_BY_CTAS(DN_EPI_GEGLU, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_GEGLU, 2) : DN_BY_CTAS(DN_EPI_GEGLU, 0);
+        case DN_EPI_WN_GATE: return mode == 1 ? DN_BY_CTAS(DN_EPI_WN_GATE, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_WN_GATE, 2) : DN_BY_CTAS(DN_EPI_WN_GATE, 0);
         default: return DN_EINVAL;
     }
 }
 
-extern "C" int dn_abi_version(void) { return 1; }
+extern "C" int dn_abi_version(void) { return 2; }
 extern "C" unsigned long long dn_launch_count(void) { return dn::g_launch_count; }

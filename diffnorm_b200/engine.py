@@ -27,24 +27,25 @@ class _Wavenet:
     """Packed WavenetEncoder / Wavenet (LM:585-617, :1003-1032)."""
 
     def __init__(self, sd, pre: str, stacks: int, layers: int, cin_pad: int, final_epi: int, final_n_pad: int,
-                 cond: bool):
+                 cond: bool, fmt: str = "bf16"):
         w = sd[pre + "init_conv.weight"]
         self.c = w.shape[0]
         self.c_pad = rup(self.c, 128)
-        self.G, self.stacks, self.cond = layers, stacks, cond
-        self.init = pack_conv3(w, sd[pre + "init_conv.bias"], cin_pad=cin_pad, n_pad=self.c_pad, name=pre + "init_conv")
+        self.G, self.stacks, self.cond, self.fmt = layers, stacks, cond, fmt
+        self.init = pack_conv3(w, sd[pre + "init_conv.bias"], cin_pad=cin_pad, n_pad=self.c_pad, name=pre + "init_conv",
+                               fmt=fmt)
         self.levels = []
         for s in range(stacks):
             blk = [f"{pre}stacks.{s}.blocks.{i}." for i in range(layers)]
             self.levels.append(pack_wavenet_level(
                 [sd[b + "conv.weight"] for b in blk], [sd[b + "conv.bias"] for b in blk],
                 [sd[b + "res_conv.weight"] for b in blk], [sd[b + "res_conv.bias"] for b in blk], self.c_pad,
-                name=f"{pre}stacks.{s}"))
+                name=f"{pre}stacks.{s}", fmt=fmt))
         last = [f"{pre}stacks.{stacks - 1}.blocks.{i}." for i in range(layers)]
         self.skip = pack_skip_sum([sd[b + "skip_conv.weight"] for b in last], [sd[b + "skip_conv.bias"] for b in last],
-                                  self.c_pad, name=pre + "skip_sum")
+                                  self.c_pad, name=pre + "skip_sum", fmt=fmt)
         self.final = pack_linear(sd[pre + "final_conv.weight"], sd[pre + "final_conv.bias"], epi=final_epi,
-                                 k_pad=self.c_pad, n_pad=final_n_pad, name=pre + "final_conv")
+                                 k_pad=self.c_pad, n_pad=final_n_pad, name=pre + "final_conv", fmt=fmt)
 
     def plans(self):
         return [self.init, *self.levels, self.skip, self.final]
@@ -56,7 +57,7 @@ class _TfLayer:
 
 class DiffNormEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: str = "cuda", cfg: Optional[DiffNormConfig] = None,
-                 vae_only: bool = False):
+                 vae_only: bool = False, wfmt: Optional[str] = None, vae_fmt: Optional[str] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("DiffNormEngine needs a CUDA device: the product has no CPU path")
         sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
@@ -65,6 +66,18 @@ class DiffNormEngine:
         self.ws: Dict[tuple, torch.Tensor] = {}
         # residual GEMM + following adaptive RMSNorm in one kernel (dn_gemm_resid_norm); DN_FUSE_NORM=0 keeps the pair
         self.fuse_norm = os.environ.get("DN_FUSE_NORM", "0") == "1"
+        # Operand formats (DESIGN.md "operand formats"; evidence profiles/r02_a3_precision_probe.jsonl).  The sampler loop
+        # runs fp16 operands (weights AND activations: a tcgen05 kind::f16 MMA takes both in one format): a weight's
+        # rounding error is the same in all 99 calls and adds up coherently (x0 error 0.18 % with bf16 weights, 0.02 % with
+        # fp16, same MMA rate), an activation's is fresh every call and averages out; every fp16 store saturates at +-65504
+        # (DN_WFMT=bf16 keeps the wide-range format).  The once-per-pass VAE encoder / decoder have no such averaging, and
+        # a 1 % logit error flips 2.5 % of near-tie units: they run split-precision (hi | lo bf16 pairs, 3 MMAs per K block).
+        self.wfmt = wfmt or os.environ.get("DN_WFMT", "bf16" if self.fuse_norm else "f16")
+        self.vae_fmt = vae_fmt or os.environ.get("DN_VAE_FMT", "split")
+        if self.wfmt not in ("bf16", "f16") or self.vae_fmt not in ("bf16", "split"):
+            raise ValueError("wfmt must be bf16 | f16 and vae_fmt bf16 | split")
+        self.vsplit = self.vae_fmt == "split"
+        self.adt = torch.float16 if self.wfmt == "f16" else bf16     # 16-bit activation format of the sampler loop
         self.gemm_impl = None   # None = automatic (CTA-pair kernel when the launch has >= 74 pair tiles); tests force others
         self._graphs: Dict[tuple, object] = {}
         self._shape_seen: Dict[tuple, int] = {}
@@ -75,6 +88,7 @@ class DiffNormEngine:
         self._reserve_rows = 0
         c = self.cfg
         self.zp = rup(c.latent_dim, 64)        # latent staging width (K of the first GEMMs)
+        self.xw = 2 * self.zp                  # the staging row is a split-precision pair [hi (zp) | lo (zp)]
         self.zn = rup(c.latent_dim, 16)        # eps_hat row width
         self.vp = rup(c.vocab, 16)             # logits row width
         self.vae_only = vae_only   # training keeps a frozen-VAE engine; the denoiser weights change every step
@@ -91,20 +105,20 @@ class DiffNormEngine:
     def _dev(self, plan):
         return plan.to(self.dev)
 
-    def _pack_tf(self, sd, pre: str, dim: int, depth: int, cond: bool):
+    def _pack_tf(self, sd, pre: str, dim: int, depth: int, cond: bool, fmt: str):
         layers = []
         ip = rup(DiffNormConfig.ff_inner(dim), 128)
         for l in range(depth):
             p = f"{pre}layers.{l}."
             L = _TfLayer()
             L.qkv = self._dev(pack_linear(torch.cat([sd[p + "1.to_q.weight"], sd[p + "1.to_kv.weight"]], 0), None,
-                                          name=p + "qkv"))
-            L.out = self._dev(pack_linear(sd[p + "1.to_out.weight"], None, epi=_lib.EPI_RESID, name=p + "to_out"))
-            L.ff1 = self._dev(pack_geglu(sd[p + "5.0.weight"], sd[p + "5.0.bias"], name=p + "ff.geglu"))
+                                          name=p + "qkv", fmt=fmt))
+            L.out = self._dev(pack_linear(sd[p + "1.to_out.weight"], None, epi=_lib.EPI_RESID, name=p + "to_out", fmt=fmt))
+            L.ff1 = self._dev(pack_geglu(sd[p + "5.0.weight"], sd[p + "5.0.bias"], name=p + "ff.geglu", fmt=fmt))
             L.ffc = self._dev(pack_conv3(sd[p + "5.2.1.weight"], sd[p + "5.2.1.bias"], cin_pad=ip, n_pad=ip,
-                                         name=p + "ff.conv"))
+                                         name=p + "ff.conv", fmt=fmt))
             L.ff3 = self._dev(pack_linear(sd[p + "5.3.weight"], sd[p + "5.3.bias"], epi=_lib.EPI_RESID, k_pad=ip,
-                                          name=p + "ff.out"))
+                                          name=p + "ff.out", fmt=fmt))
             if not cond:
                 L.g1 = sd[p + "0.gamma"].float().to(self.dev)
                 L.g2 = sd[p + "4.gamma"].float().to(self.dev)
@@ -113,17 +127,19 @@ class DiffNormEngine:
 
     def _pack_denoiser(self, sd):
         c = self.cfg
+        w = self.wfmt
+        # the first GEMM reads the fp32 latent as a split-precision pair (K = 64: three K blocks instead of one)
         self.d_init = self._dev(pack_linear(sd["model.init_conv.weight"], sd["model.init_conv.bias"], k_pad=self.zp,
-                                            name="model.init_conv"))
+                                            name="model.init_conv", fmt="split"))
         self.d_wn = _Wavenet(sd, "model.wavenet.", c.wn_stacks, c.wn_layers, cin_pad=c.hid, final_epi=_lib.EPI_F32,
-                             final_n_pad=c.hid, cond=True)
+                             final_n_pad=c.hid, cond=True, fmt=w)
         for p in self.d_wn.plans():
             self._dev(p)
-        self.d_layers, self.d_ip = self._pack_tf(sd, "model.transformer.", c.hid, c.depth, cond=True)
+        self.d_layers, self.d_ip = self._pack_tf(sd, "model.transformer.", c.hid, c.depth, cond=True, fmt=w)
         self.d_pred_gamma = sd["model.transformer.to_pred.0.gamma"].float().to(self.dev)
-        self.d_pred = self._dev(pack_linear(sd["model.transformer.to_pred.1.weight"], None, name="model.to_pred"))
+        self.d_pred = self._dev(pack_linear(sd["model.transformer.to_pred.1.weight"], None, name="model.to_pred", fmt=w))
         self.d_proj = self._dev(pack_linear(sd["model.final_proj.weight"], sd["model.final_proj.bias"],
-                                            epi=_lib.EPI_F32, n_pad=self.zn, name="model.final_proj"))
+                                            epi=_lib.EPI_F32, n_pad=self.zn, name="model.final_proj", fmt=w))
 
     def _pack_vae(self, sd):
         c = self.cfg
@@ -136,7 +152,7 @@ class DiffNormEngine:
             cp = rup(cout, 128)
             wn = _Wavenet(sd, f"{pre}encoder_wave.{i}.", c.vae_stacks, c.vae_layers, cin_pad=cin_pad,
                           final_epi=_lib.EPI_F32 if last else _lib.EPI_BF16, final_n_pad=rup(cout, 16) if last else cp,
-                          cond=False)
+                          cond=False, fmt=self.vae_fmt)
             for p in wn.plans():
                 self._dev(p)
             self.enc.append(wn)
@@ -148,17 +164,19 @@ class DiffNormEngine:
             last = i == len(dec_w) - 1
             cp = rup(cout, 128)
             wn = _Wavenet(sd, f"{pre}decoder_wave.{i}.", c.vae_stacks, c.vae_layers, cin_pad=cin_pad,
-                          final_epi=_lib.EPI_F32 if last else _lib.EPI_BF16, final_n_pad=cout if last else cp, cond=False)
+                          final_epi=_lib.EPI_F32 if last else _lib.EPI_BF16, final_n_pad=cout if last else cp, cond=False,
+                          fmt=self.vae_fmt)
             for p in wn.plans():
                 self._dev(p)
             self.dec.append(wn)
             cin_pad = cp
-        self.v_layers, self.v_ip = self._pack_tf(sd, pre + "decoder_tf.", c.feat_dim, c.vae_depth, cond=False)
+        self.v_layers, self.v_ip = self._pack_tf(sd, pre + "decoder_tf.", c.feat_dim, c.vae_depth, cond=False,
+                                                 fmt=self.vae_fmt)
         self.v_pred_gamma = sd[pre + "decoder_tf.to_pred.0.gamma"].float().to(self.dev)
         self.v_pred = self._dev(pack_linear(sd[pre + "decoder_tf.to_pred.1.weight"], None, epi=_lib.EPI_F32,
-                                            name="vae.to_pred"))
+                                            name="vae.to_pred", fmt=self.vae_fmt))
         self.v_lm = self._dev(pack_linear(sd[pre + "decoder_lm.weight"], sd[pre + "decoder_lm.bias"], epi=_lib.EPI_F32,
-                                          n_pad=self.vp, name="vae.decoder_lm"))
+                                          n_pad=self.vp, name="vae.decoder_lm", fmt=self.vae_fmt))
 
     def _build_time_table(self, sd):
         """gamma/beta of all 32 WaveNet FiLMs + 24 adaptive norms depend only on t (LM:507,:624,:741-745):
@@ -245,12 +263,16 @@ class DiffNormEngine:
             self._prof = None
 
     def _wavenet(self, wn: _Wavenet, A, out, B, T, tag: str, gb_layer0: Optional[int] = None, t_idx=None,
-                 t_idx_stride=0, pe=None, lengths=None):
+                 t_idx_stride=0, pe=None, lengths=None, out_split: bool = False):
+        """split-precision nets (wn.fmt == "split"): every bf16 activation is a [hi | lo] pair of twice the width."""
         M = B * T
         cp, G = wn.c_pad, wn.G
-        h = self.buf(tag + ".h", M, cp)
-        self._run(wn.init, A, h, B, T)
-        ys = [self.buf(tag + ".y0", M, G * cp), self.buf(tag + ".y1", M, G * cp)]
+        sp = wn.fmt == "split"
+        w2 = 2 if sp else 1
+        dt = torch.float16 if wn.fmt == "f16" else bf16
+        h = self.buf(tag + ".h", M, w2 * cp, dt)
+        self._run(wn.init, A, h, B, T, out_split=sp)
+        ys = [self.buf(tag + ".y0", M, w2 * G * cp, dt), self.buf(tag + ".y1", M, w2 * G * cp, dt)]
         src, g_a_col = h, 0
         for s, lvl in enumerate(wn.levels):
             dst = ys[s & 1]
@@ -258,21 +280,24 @@ class DiffNormEngine:
             if gb_layer0 is not None:
                 kw = dict(gb=self.table_flat[(gb_layer0 + s * G) * self.gb_w:], gb_t_stride=self.gb_t_stride,
                           g_gb=self.gb_w, gb_half=self.gb_w // 2, t_idx=t_idx, t_idx_stride=t_idx_stride)
-            self._run(lvl, src, dst, B, T, g_a_col=g_a_col, g_out_col=cp, **kw)
+            self._run(lvl, src, dst, B, T, g_a_col=g_a_col, g_out_col=cp, out_split=sp, **kw)
             src, g_a_col = dst, cp
-        sk = self.buf(tag + ".s", M, cp)
-        self._run(wn.skip, src, sk, B, T)
-        self._run(wn.final, sk, out, B, T, pe=pe, lengths=lengths)
+        sk = self.buf(tag + ".s", M, w2 * cp, dt)
+        self._run(wn.skip, src, sk, B, T, out_split=sp)
+        self._run(wn.final, sk, out, B, T, pe=pe, lengths=lengths, out_split=out_split)
         return out
 
     def _transformer(self, layers, ip, x, B, T, dim, heads, dh, lengths, tag, cond_layer0=None, t_idx=None,
-                     t_idx_stride=0, final_gamma=None):
+                     t_idx_stride=0, final_gamma=None, split: bool = False):
+        """split (the precise VAE decoder): the bf16 operands hb, ao, m1, m2 are [hi | lo] pairs; q, k, v are fp16."""
         M = B * T
-        hb = self.buf(tag + ".h", M, dim)
-        qkv = self.buf(tag + ".qkv", M, 3 * heads * dh)
-        ao = self.buf(tag + ".ao", M, heads * dh)
-        m1 = self.buf(tag + ".m1", M, ip)
-        m2 = self.buf(tag + ".m2", M, ip)
+        w2 = 2 if split else 1
+        dt = bf16 if split else (torch.float16 if layers[0].qkv.fmt == "f16" else bf16)
+        hb = self.buf(tag + ".h", M, w2 * dim, dt)
+        qkv = self.buf(tag + ".qkv", M, 3 * heads * dh, torch.float16 if split else dt)
+        ao = self.buf(tag + ".ao", M, w2 * heads * dh, dt)
+        m1 = self.buf(tag + ".m1", M, w2 * ip, dt)
+        m2 = self.buf(tag + ".m2", M, w2 * ip, dt)
         if final_gamma is not None:
             # row-complete fused form (shared timestep, width 512): every residual GEMM also writes the next norm's output
             def cond(i):
@@ -295,23 +320,23 @@ class DiffNormEngine:
                     gb = self.table_flat[(cond_layer0 + 2 * l + which) * self.gb_w:]
                     ops.adarmsnorm(x, hb, B, T, None, gb, self.gb_t_stride, t_idx, t_idx_stride)
                 else:
-                    ops.adarmsnorm(x, hb, B, T, L.g1 if which == 0 else L.g2)
+                    ops.adarmsnorm(x, hb, B, T, L.g1 if which == 0 else L.g2, split=split)
                 if which == 0:
-                    self._run(L.qkv, hb, qkv, B, T)
-                    ops.attention(qkv, ao, lengths, B, T, heads, dh)
+                    self._run(L.qkv, hb, qkv, B, T, out_f16=split)
+                    ops.attention(qkv, ao, lengths, B, T, heads, dh, out_split=split)
                     self._run(L.out, ao, x, B, T)
                 else:
-                    self._run(L.ff1, hb, m1, B, T)
-                    self._run(L.ffc, m1, m2, B, T)
+                    self._run(L.ff1, hb, m1, B, T, out_split=split)
+                    self._run(L.ffc, m1, m2, B, T, out_split=split)
                     self._run(L.ff3, m2, x, B, T)
         return x
 
     def denoise(self, xb: torch.Tensor, lengths: torch.Tensor, B: int, T: int, t_idx: torch.Tensor,
                 t_idx_stride: int = 0) -> torch.Tensor:
-        """Model.forward (LM:828-876).  xb bf16 [B*T, zp] latent staging; returns eps_hat fp32 [B*T, zn]."""
+        """Model.forward (LM:828-876).  xb bf16 [B*T, 2*zp] latent staging (split pair); returns eps_hat fp32 [B*T, zn]."""
         c = self.cfg
         M = B * T
-        h0 = self.buf("d.h0", M, c.hid)
+        h0 = self.buf("d.h0", M, c.hid, self.adt)
         self._run(self.d_init, xb, h0, B, T)
         x = self.buf("d.x", M, c.hid, f32)
         self._wavenet(self.d_wn, h0, x, B, T, "d.wn", gb_layer0=0, t_idx=t_idx, t_idx_stride=t_idx_stride,
@@ -320,10 +345,10 @@ class DiffNormEngine:
         self._transformer(self.d_layers, self.d_ip, x, B, T, c.hid, c.heads, c.dim_head, lengths, "d.tf",
                           cond_layer0=c.wn_stacks * c.wn_layers, t_idx=t_idx, t_idx_stride=t_idx_stride,
                           final_gamma=self.d_pred_gamma if fuse else None)
-        hb = self.buf("d.tf.h", M, c.hid)
+        hb = self.buf("d.tf.h", M, c.hid, self.adt)
         if not fuse:
             ops.adarmsnorm(x, hb, B, T, self.d_pred_gamma)
-        pb = self.buf("d.pred", M, c.hid)
+        pb = self.buf("d.pred", M, c.hid, self.adt)
         self._run(self.d_pred, hb, pb, B, T)
         eh = self.buf("d.eps", M, self.zn, f32)
         self._run(self.d_proj, pb, eh, B, T)
@@ -333,12 +358,13 @@ class DiffNormEngine:
         """WaveNet encoder stack (LM:1100-1103): feat fp32 [B,T,768] -> posterior params fp32 [B,T,2z]."""
         B, T, Cf = feat.shape
         M = B * T
-        a = self.buf("e.in", M, Cf)
-        ops.cast_pad_bf16(feat.contiguous(), Cf, out=a)
+        sp = self.vsplit
+        a = self.buf("e.in", M, (2 if sp else 1) * Cf)
+        ops.cast_split(feat.contiguous().view(M, Cf), a, Cf if sp else 0)
         for i, wn in enumerate(self.enc):
             last = i == len(self.enc) - 1
-            out = self.buf("e.params", M, wn.final.n_out, f32) if last else self.buf(f"e.o{i}", M, wn.c_pad)
-            self._wavenet(wn, a, out, B, T, f"e.wn{i}")
+            out = self.buf("e.params", M, wn.final.n_out, f32) if last else self.buf(f"e.o{i}", M, (2 if sp else 1) * wn.c_pad)
+            self._wavenet(wn, a, out, B, T, f"e.wn{i}", out_split=sp and not last)
             a = out
         return a.view(B, T, -1)
 
@@ -348,34 +374,44 @@ class DiffNormEngine:
         return ops.vae_reparam(params, eps.contiguous(), self.cfg.latent_dim, eps_channel_first)
 
     def decode(self, xb: torch.Tensor, lengths: torch.Tensor, B: int, T: int):
-        """decode_feature (LM:1109-1116): latent staging bf16 [B*T, zp] -> (recon fp32 [B,T,768], logits fp32 [B,T,vp])."""
+        """decode_feature (LM:1109-1116): latent staging bf16 [B*T, 2*zp] (split pair) -> (recon fp32 [B,T,768], logits
+        fp32 [B,T,vp])."""
         c = self.cfg
         M = B * T
-        a = xb
+        sp = self.vsplit
+        w2 = 2 if sp else 1
+        a = xb if sp else self._hi_only(xb, M)
         x = self.buf("v.x", M, c.feat_dim, f32)
         for i, wn in enumerate(self.dec):
             last = i == len(self.dec) - 1
-            out = x if last else self.buf(f"v.o{i}", M, wn.c_pad)
-            self._wavenet(wn, a, out, B, T, f"v.wn{i}")
+            out = x if last else self.buf(f"v.o{i}", M, w2 * wn.c_pad)
+            self._wavenet(wn, a, out, B, T, f"v.wn{i}", out_split=sp and not last)
             a = out
-        self._transformer(self.v_layers, self.v_ip, x, B, T, c.feat_dim, c.vae_heads, c.vae_dim_head, lengths, "v.tf")
-        hb = self.buf("v.tf.h", M, c.feat_dim)
-        ops.adarmsnorm(x, hb, B, T, self.v_pred_gamma)
+        self._transformer(self.v_layers, self.v_ip, x, B, T, c.feat_dim, c.vae_heads, c.vae_dim_head, lengths, "v.tf",
+                          split=sp)
+        hb = self.buf("v.tf.h", M, w2 * c.feat_dim)
+        ops.adarmsnorm(x, hb, B, T, self.v_pred_gamma, split=sp)
         recon = self.buf("v.recon", M, c.feat_dim, f32)
         self._run(self.v_pred, hb, recon, B, T)
-        rb = self.buf("v.recon_bf16", M, c.feat_dim)
-        ops.cast_pad_bf16(recon, c.feat_dim, out=rb)
+        rb = self.buf("v.recon_bf16", M, w2 * c.feat_dim)
+        ops.cast_split(recon, rb, c.feat_dim if sp else 0)
         logits = self.buf("v.logits", M, self.vp, f32)
         self._run(self.v_lm, rb, logits, B, T)
         return recon.view(B, T, -1), logits.view(B, T, -1)
 
+    def _hi_only(self, xb, M):
+        """bf16-format VAE (DN_VAE_FMT=bf16, A/B runs only): a plain-width copy of the staging row's hi half."""
+        a = self.buf("s.xb_hi", M, self.zp)
+        a.copy_(xb[:, : self.zp])
+        return a
+
     # ------------------------------------------------------------------------------------------------ the pass
     def _ddim_step(self, B, T):
         M, z = B * T, self.cfg.latent_dim
-        x, xb = self.buf("s.x", M, z, f32), self.buf("s.xb", M, self.zp)
+        x, xb = self.buf("s.x", M, z, f32), self.buf("s.xb", M, self.xw)
         t_idx, lens = self.buf("s.t", 1, 1, i32, frames=False).view(-1), self.buf("s.len", B, 1, i32, frames=False).view(-1)
         eh = self.denoise(xb, lens, B, T, t_idx)
-        ops.ddim_step(x, eh, self.ddim_rows, t_idx, 0, xb)
+        ops.ddim_step(x, eh, self.ddim_rows, t_idx, 0, xb, self.zp)
         ops.advance_step(t_idx, -1)
 
     def _ddim_graph(self, B, T):
@@ -426,10 +462,10 @@ class DiffNormEngine:
         out = {}
         zlat = self.encode(feat, eps_vae)
         x = self.buf("s.x", M, z, f32)
-        xb = self.buf("s.xb", M, self.zp)
+        xb = self.buf("s.xb", M, self.xw)
         s = self.sched
         ops.q_sample(zlat, eps_q.contiguous(), float(np.float32(s.sqrt_alphas_cumprod[start_step])),
-                     float(np.float32(s.sqrt_one_minus_alphas_cumprod[start_step])), x, xb)
+                     float(np.float32(s.sqrt_one_minus_alphas_cumprod[start_step])), x, xb, self.zp)
         if collect:
             out["z"] = zlat.clone()
             out["x_start"] = x.view(B, T, z).clone()
@@ -454,7 +490,7 @@ class DiffNormEngine:
             for k in range(n):
                 eh = self.denoise(xb, lens, B, T, t_idx)
                 noise = step_noise[k] if step_noise is not None else torch.randn(B, T, z, device=self.dev, dtype=f32)
-                ops.ddpm_step(x, eh, noise.contiguous(), rows, t_idx, xb)
+                ops.ddpm_step(x, eh, noise.contiguous(), rows, t_idx, xb, self.zp)
                 ops.advance_step(t_idx, -1)
             calls = n
         elif sampler == "ddim_strided":
@@ -465,7 +501,7 @@ class DiffNormEngine:
                 t_idx.fill_(tmap[i])          # the model sees the original step (respace.py:117-129)
                 r_idx.fill_(i)                # the update uses the respaced table row
                 eh = self.denoise(xb, lens, B, T, t_idx)
-                ops.ddim_step(x, eh, rows, r_idx, 1, xb)
+                ops.ddim_step(x, eh, rows, r_idx, 1, xb, self.zp)
                 calls += 1
         else:
             raise ValueError(f"unknown sampler {sampler!r}")
@@ -480,8 +516,12 @@ class DiffNormEngine:
         return out
 
     def stage_latent(self, latent: torch.Tensor) -> torch.Tensor:
-        """fp32 [B,T,z] latent -> bf16 staging buffer [B*T, zp] (for decode / denoise on caller-supplied latents)."""
+        """fp32 [B,T,z] latent -> split-precision bf16 staging buffer [B*T, 2*zp] (for decode / denoise on caller-supplied
+        latents)."""
         B, T, z = latent.shape
-        xb = self.buf("s.xb", B * T, self.zp)
-        ops.cast_pad_bf16(latent.contiguous().view(B * T, z), self.zp, out=xb)
+        xb = self.buf("s.xb", B * T, self.xw)
+        ops.cast_split(latent.contiguous().view(B * T, z), xb, self.zp)
         return xb
+
+    def precision_mode(self) -> str:
+        return f"loop: {self.wfmt} operands (fp32 accumulate, fp32 latent in); VAE encode/decode: {self.vae_fmt}"

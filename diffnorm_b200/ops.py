@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import GemmDesc, GemmSeg, check, lib
 
-bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
+bf16, f16, f32, i32, i64 = torch.bfloat16, torch.float16, torch.float32, torch.int32, torch.int64
 
 
 def _stream() -> int:
@@ -92,6 +92,14 @@ def cast_pad_bf16(src: torch.Tensor, ldo: int, out: Optional[torch.Tensor] = Non
     return out
 
 
+def cast_split(src: torch.Tensor, out: torch.Tensor, lo_col: int):
+    """fp32 [rows, C] -> split-precision bf16 operand [rows, ldo]: hi in [0, C), lo = bf16(x - hi) in [lo_col, lo_col + C)."""
+    _chk(src, f32, "src"), _chk(out, bf16, "out")
+    Cc = src.shape[-1]
+    check(lib.dn_cast_split(_p(src), src.numel() // Cc, Cc, Cc, _p(out), out.shape[-1], lo_col, _stream()), "dn_cast_split")
+    return out
+
+
 def vae_reparam(params, eps, z: int, eps_channel_first: bool, out=None):
     _chk(params, f32, "params"), _chk(eps, f32, "eps")
     B, T, ldp = params.shape
@@ -102,33 +110,33 @@ def vae_reparam(params, eps, z: int, eps_channel_first: bool, out=None):
     return out
 
 
-def q_sample(z_lat, eps, sqrt_ab: float, sqrt_1m_ab: float, x_out, x_bf16=None):
+def q_sample(z_lat, eps, sqrt_ab: float, sqrt_1m_ab: float, x_out, x_bf16=None, x_lo_col: int = 0):
     _chk(z_lat, f32, "z"), _chk(eps, f32, "eps"), _chk(x_out, f32, "x")
     z = z_lat.shape[-1]
     rows = z_lat.numel() // z
     ldx = 0 if x_bf16 is None else x_bf16.shape[-1]
-    check(lib.dn_q_sample(_p(z_lat), _p(eps), sqrt_ab, sqrt_1m_ab, rows, z, _p(x_out), _p(x_bf16), ldx, _stream()),
+    check(lib.dn_q_sample(_p(z_lat), _p(eps), sqrt_ab, sqrt_1m_ab, rows, z, _p(x_out), _p(x_bf16), ldx, x_lo_col, _stream()),
           "dn_q_sample")
     return x_out
 
 
-def ddim_step(x, eps_hat, coef_table, t_idx, mode: int = 0, x_bf16=None):
+def ddim_step(x, eps_hat, coef_table, t_idx, mode: int = 0, x_bf16=None, x_lo_col: int = 0):
     _chk(x, f32, "x"), _chk(eps_hat, f32, "eps_hat"), _chk(coef_table, f32, "coef"), _chk(t_idx, i32, "t_idx")
     z = x.shape[-1]
     rows = x.numel() // z
     ldx = 0 if x_bf16 is None else x_bf16.shape[-1]
     check(lib.dn_ddim_step(_p(x), _p(eps_hat), eps_hat.shape[-1], _p(coef_table), _p(t_idx), rows, z, mode, _p(x_bf16),
-                           ldx, _stream()), "dn_ddim_step")
+                           ldx, x_lo_col, _stream()), "dn_ddim_step")
     return x
 
 
-def ddpm_step(x, eps_hat, noise, coef_table, t_idx, x_bf16=None):
+def ddpm_step(x, eps_hat, noise, coef_table, t_idx, x_bf16=None, x_lo_col: int = 0):
     _chk(x, f32, "x"), _chk(eps_hat, f32, "eps_hat"), _chk(noise, f32, "noise"), _chk(coef_table, f32, "coef")
     z = x.shape[-1]
     rows = x.numel() // z
     ldx = 0 if x_bf16 is None else x_bf16.shape[-1]
     check(lib.dn_ddpm_step(_p(x), _p(eps_hat), eps_hat.shape[-1], _p(noise), _p(coef_table), _p(t_idx), rows, z,
-                           _p(x_bf16), ldx, _stream()), "dn_ddpm_step")
+                           _p(x_bf16), ldx, x_lo_col, _stream()), "dn_ddpm_step")
     return x
 
 
@@ -136,11 +144,15 @@ def advance_step(t_idx, delta: int):
     check(lib.dn_advance_step(_p(t_idx), delta, _stream()), "dn_advance_step")
 
 
-def adarmsnorm(x, out, B: int, T: int, gamma_p=None, gb=None, gb_t_stride: int = 0, t_idx=None, t_idx_stride: int = 0):
-    _chk(x, f32, "x"), _chk(out, bf16, "out")
+def adarmsnorm(x, out, B: int, T: int, gamma_p=None, gb=None, gb_t_stride: int = 0, t_idx=None, t_idx_stride: int = 0,
+               split: bool = False):
+    """out bf16 or fp16 [rows, C]; split: out is a split-precision bf16 operand [rows, 2C] = [hi | lo]."""
+    _chk(x, f32, "x"), _chk(out, bf16 if split or out.dtype != f16 else f16, "out")
     Cc = x.shape[-1]
+    if out.shape[-1] != (2 * Cc if split else Cc):
+        raise ValueError("adarmsnorm: out width must be C (or 2C for a split-precision operand)")
     check(lib.dn_adarmsnorm(_p(x), _p(out), B, T, Cc, _p(gamma_p), _p(gb), gb_t_stride, _p(t_idx), t_idx_stride,
-                            _stream()), "dn_adarmsnorm")
+                            Cc if split else 0, _lib.FMT_F16 if out.dtype == f16 else _lib.FMT_BF16, _stream()), "dn_adarmsnorm")
     return out
 
 
@@ -170,9 +182,16 @@ def time_features(steps, w):
     return out
 
 
-def attention(qkv, out, lengths, B: int, T: int, H: int, dh: int):
-    _chk(qkv, bf16, "qkv"), _chk(out, bf16, "out")
-    check(lib.dn_attention(_p(qkv), _p(out), _p(lengths), B, T, H, dh, _stream()), "dn_attention")
+def attention(qkv, out, lengths, B: int, T: int, H: int, dh: int, out_split: bool = False):
+    """qkv bf16 or fp16 [B*T, 3*H*dh]; out [B*T, H*dh] in qkv's format, or (dh 96) the split-precision bf16 pair
+    [B*T, 2*H*dh]."""
+    if qkv.dtype not in (bf16, f16):
+        raise ValueError("qkv must be bf16 or fp16")
+    _chk(qkv, qkv.dtype, "qkv"), _chk(out, bf16 if out_split else qkv.dtype, "out")
+    if out.shape[-1] != (2 if out_split else 1) * H * dh:
+        raise ValueError("attention: out width")
+    check(lib.dn_attention(_p(qkv), _p(out), _p(lengths), B, T, H, dh, _lib.FMT_F16 if qkv.dtype == f16 else _lib.FMT_BF16,
+                           H * dh if out_split else 0, _stream()), "dn_attention")
     return out
 
 
@@ -189,8 +208,16 @@ class GemmPlan:
 
     def __init__(self, W, segs: Sequence[Sequence[int]], n_out: int, n_tiles: int, epi: int, bias=None, bias2=None,
                  groups: int = 1, g_w_row: int = 0, g_bias: int = 0, dilation: int = 1, dilation_shl_group: int = 0,
-                 name: str = ""):
+                 name: str = "", fmt: str = "bf16"):
+        """fmt: operand format of this plan.  "bf16" / "f16": W is that 16-bit type, A is bf16.  "split": W = [W_hi | W_lo]
+        (bf16 pairs side by side along K) and A = [A_hi | A_lo] (two halves of the row): every K segment runs three times
+        — (A_hi, W_hi), (A_hi, W_lo), (A_lo, W_hi) — which contracts to ~2^-17 relative instead of 2^-9."""
+        if fmt not in ("bf16", "f16", "split"):
+            raise ValueError(fmt)
+        self.fmt = fmt
         self.W, self.segs, self.n_out, self.n_tiles, self.epi = W, [tuple(s) for s in segs], n_out, n_tiles, epi
+        if fmt == "split" and 3 * len(self.segs) > _lib.MAX_SEGS:
+            raise ValueError("too many K segments for a split-precision plan")
         self.bias, self.bias2, self.groups, self.g_w_row, self.g_bias = bias, bias2, groups, g_w_row, g_bias
         self.dilation, self.dilation_shl_group, self.name = dilation, dilation_shl_group, name
         self._flat_ok = groups == 1 and all(sg[1] == 0 for sg in self.segs)
@@ -203,7 +230,9 @@ class GemmPlan:
 
     def run(self, A, out, B: int, T: int, *, g_a_col: int = 0, g_out_col: int = 0, gb=None, gb_t_stride: int = 0,
             g_gb: int = 0, gb_half: int = 0, t_idx=None, t_idx_stride: int = 0, pe=None, lengths=None,
-            epi: Optional[int] = None, impl: Optional[int] = None, a_cols: Optional[int] = None):
+            epi: Optional[int] = None, impl: Optional[int] = None, a_cols: Optional[int] = None, out_split: bool = False,
+            out_f16: bool = False):
+        """out_split: 16-bit output written as a split-precision pair (out is [.., 2 * width]: hi | lo).  out_f16: fp16 output."""
         epi = self.epi if epi is None else epi
         if self._flat_ok and gb is None and pe is None:
             # no frame shifts and no per-utterance epilogue inputs: treat the batch as one long utterance so M tiles
@@ -217,16 +246,28 @@ class GemmPlan:
             # the pair form gains (~10 % per row): T = 600 is 3 x 256 = 768 rows as pairs but 5 x 128 = 640 rows single
             if impl == _lib.GEMM_TCGEN05_2CTA and _WASTE_AWARE and (T + 127) // 128 * 128 * 1.10 < (T + 255) // 256 * 256:
                 impl = _lib.GEMM_TCGEN05
-        _chk(A, bf16, "A")
-        _chk(out, f32 if epi in (_lib.EPI_F32, _lib.EPI_RESID) else bf16, "out")
+        wdt = f16 if self.fmt == "f16" else bf16
+        _chk(A, wdt, "A")     # one 16-bit format per MMA: fp16 plans take fp16 activations
+        f32out = epi in (_lib.EPI_F32, _lib.EPI_RESID)
+        out_f16 = out_f16 or (not f32out and not out_split and out.dtype == f16)
+        _chk(out, f32 if f32out else (f16 if out_f16 else bf16), "out")
+        _chk(self.W, wdt, "W")
         d = GemmDesc()
         d.B, d.T, d.groups = B, T, self.groups
         lda = A.shape[-1]
         d.A, d.lda, d.a_cols, d.a_batch_stride, d.g_a_col = _p(A), lda, (lda if a_cols is None else a_cols), T * lda, g_a_col
         d.W, d.ldw, d.w_rows, d.g_w_row = _p(self.W), self.W.shape[1], self.W.shape[0], self.g_w_row
-        d.num_segs = len(self.segs)
-        for i, s in enumerate(self.segs):
+        segs = self.segs
+        if self.fmt == "split":
+            a_lo, w_lo = lda // 2, self.W.shape[1] // 2
+            segs = [sg for (a0, sh, kb, w0, nm) in self.segs
+                    for sg in ((a0, sh, kb, w0, nm), (a0, sh, kb, w0 + w_lo, nm), (a0 + a_lo, sh, kb, w0, nm))]
+        d.num_segs = len(segs)
+        for i, s in enumerate(segs):
             d.seg[i] = GemmSeg(*s)
+        d.a_fmt = d.w_fmt = _lib.FMT_F16 if self.fmt == "f16" else _lib.FMT_BF16
+        d.out_fmt = _lib.FMT_F16 if out_f16 else _lib.FMT_BF16
+        d.out_lo_col = out.shape[-1] // 2 if out_split else 0
         d.dilation, d.dilation_shl_group = self.dilation, self.dilation_shl_group
         d.n_tiles, d.n_out, d.epi = self.n_tiles, self.n_out, epi
         d.bias, d.bias2, d.g_bias = _p(self.bias), _p(self.bias2), self.g_bias
@@ -244,6 +285,7 @@ def gemm_resid_norm(plan: GemmPlan, A, x, hb, gamma_p=None, gb=None, gb_t_stride
     EPI_RESID linear of width 512; gb / t_idx select ONE table row for the whole batch (shared timestep)."""
     _chk(A, bf16, "A"), _chk(x, f32, "x"), _chk(hb, bf16, "hb")
     assert plan.n_out == 512 and x.shape[-1] == 512 and hb.shape[-1] == 512 and plan._flat_ok and len(plan.segs) == 1
+    assert plan.fmt == "bf16", "dn_gemm_resid_norm multiplies bf16 weights"
     d = _lib.ResidNormDesc()
     d.M, d.A, d.lda, d.k_blocks = x.shape[0], _p(A), A.shape[-1], plan.segs[0][2]
     d.W, d.ldw, d.bias, d.x, d.hb = _p(plan.W), plan.W.shape[1], _p(plan.bias), _p(x), _p(hb)

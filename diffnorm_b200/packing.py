@@ -27,12 +27,18 @@ def rup(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
-def _bf(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).contiguous()
+def _bf(t: torch.Tensor, fmt: str = "bf16") -> torch.Tensor:
+    """fp32 packed weight -> the plan's operand format: bf16, fp16 (saturating), or the split pair [hi | lo] along K."""
+    if fmt == "f16":
+        return t.clamp(-65504.0, 65504.0).to(torch.float16).contiguous()
+    hi = t.to(torch.bfloat16)
+    if fmt == "split":
+        return torch.cat([hi, (t - hi.float()).to(torch.bfloat16)], dim=1).contiguous()
+    return hi.contiguous()
 
 
 def pack_linear(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.EPI_BF16, k_pad: Optional[int] = None,
-                n_pad: Optional[int] = None, name: str = "") -> GemmPlan:
+                n_pad: Optional[int] = None, name: str = "", fmt: str = "bf16") -> GemmPlan:
     """W [N, K] (nn.Linear / 1x1 conv squeezed).  Output columns = n_pad (extra columns compute to bias 0)."""
     W = W.reshape(W.shape[0], -1).float()
     N, K = W.shape
@@ -44,11 +50,12 @@ def pack_linear(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.E
     if bias is not None:
         bp = torch.zeros(Np, device=W.device)
         bp[:N] = bias.float()
-    return GemmPlan(_bf(Wp), [(0, 0, Kp // BK, 0, 0)], Np, (Np + WT - 1) // WT, epi, bias=bp, name=name)
+    return GemmPlan(_bf(Wp, fmt), [(0, 0, Kp // BK, 0, 0)], Np, (Np + WT - 1) // WT, epi, bias=bp, name=name, fmt=fmt)
 
 
 def pack_conv3(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.EPI_BF16, cin_pad: Optional[int] = None,
-               n_pad: Optional[int] = None, dilation: int = 1, name: str = "", shift_sign: int = 1) -> GemmPlan:
+               n_pad: Optional[int] = None, dilation: int = 1, name: str = "", shift_sign: int = 1,
+               fmt: str = "bf16") -> GemmPlan:
     """W [N, Cin, 3] causal conv -> K = [tap0 | tap1 | tap2], shifts (2d, d, 0).
     shift_sign = -1 reads x[t + (2-k) d] instead: the data-gradient of the conv when W is the (Cin, Cout)-transposed
     kernel (dx[t] = sum_k W_k^T dy[t + (2-k) d]; frames past the utterance read as zero)."""
@@ -64,10 +71,10 @@ def pack_conv3(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.EP
         bp = torch.zeros(Np, device=W.device)
         bp[:N] = bias.float()
     segs = [(0, shift_sign * (2 - k), Cp // BK, k * Cp, 0) for k in range(3)]
-    return GemmPlan(_bf(Wp), segs, Np, (Np + WT - 1) // WT, epi, bias=bp, dilation=dilation, name=name)
+    return GemmPlan(_bf(Wp, fmt), segs, Np, (Np + WT - 1) // WT, epi, bias=bp, dilation=dilation, name=name, fmt=fmt)
 
 
-def pack_geglu(W: torch.Tensor, bias: torch.Tensor, name: str = "") -> GemmPlan:
+def pack_geglu(W: torch.Tensor, bias: torch.Tensor, name: str = "", fmt: str = "bf16") -> GemmPlan:
     """W [2*inner, K]: rows [0, inner) = x, [inner, 2 inner) = gate.  Output = inner_pad (multiple of 128) columns;
     padded lanes have zero weights and bias so they produce gelu(0) * 0 = 0 exactly."""
     W = W.float()
@@ -86,11 +93,11 @@ def pack_geglu(W: torch.Tensor, bias: torch.Tensor, name: str = "") -> GemmPlan:
         Wp[j * WT + 128:j * WT + 128 + n, :K] = W[inner + lo:inner + hi]
         bp[j * WT:j * WT + n] = bias[lo:hi].float()
         bp[j * WT + 128:j * WT + 128 + n] = bias[inner + lo:inner + hi].float()
-    return GemmPlan(_bf(Wp), [(0, 0, Kp // BK, 0, 0)], ip, tiles, _lib.EPI_GEGLU, bias=bp, name=name)
+    return GemmPlan(_bf(Wp, fmt), [(0, 0, Kp // BK, 0, 0)], ip, tiles, _lib.EPI_GEGLU, bias=bp, name=name, fmt=fmt)
 
 
 def pack_wavenet_level(convs: List[torch.Tensor], conv_b: List[torch.Tensor], ress: List[torch.Tensor],
-                       res_b: List[torch.Tensor], c_pad: int, name: str = "") -> GemmPlan:
+                       res_b: List[torch.Tensor], c_pad: int, name: str = "", fmt: str = "bf16") -> GemmPlan:
     """One WaveNet stack level = `len(convs)` independent chains (group g has dilation 2^g, LM:553-566), fused
     conv(k3, dilated) + res_conv(1x1) + FiLM/gate epilogue.  convs[g] [C, C, 3], ress[g] [C, C, 1].
     K layout per chain: [tap2 (shift 0, also feeds the res rows) | tap0 (shift 2d) | tap1 (shift d)]."""
@@ -130,11 +137,12 @@ def pack_wavenet_level(convs: List[torch.Tensor], conv_b: List[torch.Tensor], re
             br[g * Cp:g * Cp + Cc] = res_b[g].float()
     kb = Cp // BK
     segs = [(0, 0, kb, 0, 0), (0, 2, kb, Cp, 128), (0, 1, kb, 2 * Cp, 128)]
-    return GemmPlan(_bf(Wp), segs, Cp, tiles, _lib.EPI_WN_GATE, bias=bc, bias2=br, groups=G, g_w_row=rows_g,
-                    g_bias=Cp, dilation=1, dilation_shl_group=1, name=name)
+    return GemmPlan(_bf(Wp, fmt), segs, Cp, tiles, _lib.EPI_WN_GATE, bias=bc, bias2=br, groups=G, g_w_row=rows_g,
+                    g_bias=Cp, dilation=1, dilation_shl_group=1, name=name, fmt=fmt)
 
 
-def pack_skip_sum(skips: List[torch.Tensor], skip_b: List[torch.Tensor], c_pad: int, name: str = "") -> GemmPlan:
+def pack_skip_sum(skips: List[torch.Tensor], skip_b: List[torch.Tensor], c_pad: int, name: str = "",
+                  fmt: str = "bf16") -> GemmPlan:
     """sum_g skip_conv_g(y_g) (LM:580,617) = one GEMM over the concatenated chain outputs [.., G * c_pad].
     Writes all c_pad output columns (the pad columns get exact zeros)."""
     G = len(skips)
@@ -145,7 +153,8 @@ def pack_skip_sum(skips: List[torch.Tensor], skip_b: List[torch.Tensor], c_pad: 
     bp = torch.zeros(c_pad, device=skips[0].device)
     bp[:Cc] = torch.stack([b.float() for b in skip_b]).sum(0)
     Np = Wp.shape[0]
-    return GemmPlan(_bf(Wp), [(0, 0, G * c_pad // BK, 0, 0)], Np, (Np + WT - 1) // WT, _lib.EPI_BF16, bias=bp, name=name)
+    return GemmPlan(_bf(Wp, fmt), [(0, 0, G * c_pad // BK, 0, 0)], Np, (Np + WT - 1) // WT, _lib.EPI_BF16, bias=bp, name=name,
+                    fmt=fmt)
 
 
 # ------------------------------------------------------------------------------------------------ training-step packings

@@ -24,7 +24,7 @@ extern "C" {
 #define DN_EDRIVER (-2)  /* driver entry point (cuTensorMapEncodeTiled) unavailable */
 
 /* ---- library info ------------------------------------------------------------------------------------ */
-int dn_abi_version(void);                 /* = 1 */
+int dn_abi_version(void);                 /* = 2 */
 unsigned long long dn_launch_count(void); /* kernels launched by this library so far (bench.py gpu_launches) */
 
 /* ---- integer kernels --------------------------------------------------------------------------------- */
@@ -60,6 +60,14 @@ int dn_gather_pack(const float* src, const int64_t* src_row0, const int64_t* ind
 /* fp32 [rows, C] -> bf16 [rows, ldo] with zero fill of the pad columns (operand staging for the GEMMs). */
 int dn_cast_pad_bf16(const float* src, int64_t rows, int32_t C, int32_t lds, void* dst, int32_t ldo, void* stream);
 
+/* Split-precision operand staging: fp32 [rows, C] (row stride lds) -> bf16 [rows, ldo] with hi = bf16(x) in columns
+ * [0, C) and lo = bf16(x - hi) in columns [lo_col, lo_col + C); every other column is written with zeros.  A GEMM whose
+ * K-segment program multiplies (hi, W_hi), (hi, W_lo) and (lo, W_hi) then contracts to ~2^-17 relative: the once-per-pass
+ * VAE encoder / decoder run this way (their rounding error decides near-tie units; the 99-call loop averages its own).
+ * lo_col = 0: plain cast (= dn_cast_pad_bf16). */
+int dn_cast_split(const float* src, int64_t rows, int32_t C, int32_t lds, void* dst, int32_t ldo, int32_t lo_col,
+                  void* stream);
+
 /* fp32 [rows, C] -> bf16 [rows, 3C] = [hi | hi | lo] (hi = bf16(x), lo = bf16(x - hi)).  Against weights packed as
  * [hi | lo | hi] a single dn_gemm over K = 3C gives the contraction to ~2^-16 relative: used by the k-means unit
  * quantiser (examples/textless_nlp/gslm/speech2unit/clustering/quantize_with_kmeans.py:109-121). */
@@ -79,30 +87,36 @@ int dn_vae_reparam(const float* params, int32_t ldp, const float* eps, int32_t e
  * DDPM rows: [0] sqrt_recip_ab [1] sqrt_recipm1_ab [2] coef1 [3] coef2 [4] exp(0.5*logvar) (0 when t == 0).
  * `t_idx` is a DEVICE int32 holding the current table row, so one captured CUDA graph serves every step.
  * The three update kernels move 4 latent channels per thread (16-byte accesses): z, lde and ldx must be multiples
- * of 4 and the fp32 pointers 16-byte aligned (z is 16, 32 or 128 on this path, LM:1044-1051), else DN_EINVAL. */
+ * of 4 and the fp32 pointers 16-byte aligned (z is 16, 32 or 128 on this path, LM:1044-1051), else DN_EINVAL.
+ * x_lo_col != 0: the staging copy is split-precision: hi = bf16(x) in columns [0, z), lo = bf16(x - hi) in columns
+ * [x_lo_col, x_lo_col + z) (the denoiser's first GEMM then sees the fp32 latent to ~2^-17). */
 
 /* x = c0 * z + c1 * eps  (q_sample, LM:1405-1409).  Also writes the bf16 staging copy x_bf16 [n/z, ldx] if
  * non-null (zero padded to ldx columns). */
 int dn_q_sample(const float* z_lat, const float* eps, float sqrt_ab, float sqrt_1m_ab, int64_t rows, int32_t z,
-                float* x, void* x_bf16, int32_t ldx, void* stream);
+                float* x, void* x_bf16, int32_t ldx, int32_t x_lo_col, void* stream);
 
 /* Inline DDIM eta=0 update (LM:1419-1442), in place on x [rows, z]; eps_hat [rows, lde] fp32.
  * mode 0: reference inline form with the 1e-10 clamps; mode 1: generic-lib form (gaussian_diffusion.py:513-560). */
 int dn_ddim_step(float* x, const float* eps_hat, int32_t lde, const float* coef_table, const int32_t* t_idx,
-                 int64_t rows, int32_t z, int32_t mode, void* x_bf16, int32_t ldx, void* stream);
+                 int64_t rows, int32_t z, int32_t mode, void* x_bf16, int32_t ldx, int32_t x_lo_col, void* stream);
 
 /* Ancestral DDPM update (gaussian_diffusion.py:232-252,295-344,402-417), in place; noise [rows, z] fp32. */
 int dn_ddpm_step(float* x, const float* eps_hat, int32_t lde, const float* noise, const float* coef_table,
-                 const int32_t* t_idx, int64_t rows, int32_t z, void* x_bf16, int32_t ldx, void* stream);
+                 const int32_t* t_idx, int64_t rows, int32_t z, void* x_bf16, int32_t ldx, int32_t x_lo_col, void* stream);
 
 /* t_idx[0] += delta (device-side step counter so the sampler loop needs no host round trip). */
 int dn_advance_step(int32_t* t_idx, int32_t delta, void* stream);
 
 /* (Adaptive) RMSNorm, LM:629-639:  out = x / max(||x||, 1e-12) * sqrt(C) * gamma_p  [* gamma_t + beta_t].
  * x fp32 [B*T, C]; out bf16 [B*T, C]; gamma_p [C] or null; gb (null = unconditioned) points at a table whose
- * row for utterance b is gb + t_idx[b * t_idx_stride] * gb_t_stride, holding gamma_t[0..C) then beta_t[C..2C). */
+ * row for utterance b is gb + t_idx[b * t_idx_stride] * gb_t_stride, holding gamma_t[0..C) then beta_t[C..2C).
+ * out_lo_col = 0: out bf16 [B*T, C].  out_lo_col != 0 (>= C): out bf16 [B*T, 2 * out_lo_col], hi in columns [0, C), lo in
+ * [out_lo_col, out_lo_col + C) (split-precision operand of the GEMM that follows).  out_fmt: DN_FMT_BF16 | DN_FMT_F16
+ * (un-split outputs only). */
 int dn_adarmsnorm(const float* x, void* out, int32_t B, int32_t T, int32_t C, const float* gamma_p, const float* gb,
-                  int64_t gb_t_stride, const int32_t* t_idx, int32_t t_idx_stride, void* stream);
+                  int64_t gb_t_stride, const int32_t* t_idx, int32_t t_idx_stride, int32_t out_lo_col, int32_t out_fmt,
+                  void* stream);
 
 /* Residual GEMM fused with the adaptive RMSNorm that follows it in the transformer block (LM:692 -> :629-639 of the
  * next sub-layer; LM:704 -> the next layer's first norm / the final to_pred norm), hidden width C = 512 only:
@@ -155,6 +169,8 @@ enum {
     DN_EPI_WN_GATE = 4   /* W tile = 128 conv rows then 128 res rows: y = tanh(u')sigmoid(u') + res (LM:513-536) */
 };
 enum { DN_GEMM_TCGEN05 = 0, DN_GEMM_SIMT_CHECK = 1, DN_GEMM_TCGEN05_2CTA = 2 };
+enum { DN_FMT_BF16 = 0, DN_FMT_F16 = 1 };   /* 16-bit operand / output formats (same tensor-core rate) */
+#define DN_MAX_SEGS 12
 
 typedef struct {
     int32_t B, T;               /* utterances, frames per utterance */
@@ -169,7 +185,7 @@ typedef struct {
     int32_t ldw, w_rows;
     int32_t g_w_row;            /* + g * g_w_row rows for group g */
     int32_t num_segs;
-    dn_gemm_seg seg[4];
+    dn_gemm_seg seg[DN_MAX_SEGS];
     int32_t dilation;           /* d for group 0 */
     int32_t dilation_shl_group; /* 1: d << g (wavenet chain i has dilation 2^i, LM:553) */
     int32_t n_tiles;            /* W tiles (of 256 rows) per group */
@@ -189,6 +205,15 @@ typedef struct {
     int32_t g_out_col;
     const float* pe;            /* [T + 1, n_out] sinusoidal table (row 0 = zeros) or null */
     const int32_t* lengths;     /* [B] valid frames (pe positions), may be null = all valid */
+    /* operand formats; a_fmt must equal w_fmt (a kind::f16 MMA takes both operands in one 16-bit format).  The sampler loop
+     * runs fp16: a weight's rounding error repeats identically in all 99 calls and adds up coherently (x0 error 0.18 % with
+     * bf16 weights against 0.02-0.03 % with fp16, profiles/r02_a3_precision_probe.jsonl); fp16 carries 3 more mantissa bits
+     * at the same MMA rate, and every fp16 store saturates at +-65504 instead of overflowing. */
+    int32_t a_fmt, w_fmt;       /* DN_FMT_* of A and of W */
+    int32_t out_fmt;            /* DN_FMT_* of 16-bit outputs (BF16 / GEGLU / WN_GATE epilogues) */
+    /* != 0: split-precision 16-bit output: column c holds hi = rn(v), column c + out_lo_col holds rn(v - hi); the GEGLU /
+     * WaveNet-gate epilogues then use full-precision erf / tanh / exp.  n_out must be a multiple of 64. */
+    int32_t out_lo_col;
 } dn_gemm_desc;
 
 /* out = epilogue(A (*) W^T): bf16 operands, fp32 accumulation in TMEM (tcgen05.mma fed by TMA).
@@ -203,9 +228,11 @@ int dn_gemm(const dn_gemm_desc* d, int32_t impl, void* stream);
 
 /* Non-causal multi-head attention with key-padding mask (LM:299-343, :945-949), flash-style (no N x N matrix).
  * qkv bf16 [B, T, 3*H*dh] = [q | k | v], each head-major (h d); out bf16 [B, T, H*dh].
- * Keys j >= lengths[b] get exactly zero weight.  dh in {64, 96}. */
+ * Keys j >= lengths[b] get exactly zero weight.  dh in {64, 96}.
+ * fmt = DN_FMT_F16: q, k, v, the probabilities and (dh 64) the output are fp16;
+ * out_lo_col != 0 (dh 96 only): out is split-precision bf16 [B, T, 2 * out_lo_col] (hi | lo, as dn_adarmsnorm). */
 int dn_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H, int32_t dh,
-                 void* stream);
+                 int32_t fmt, int32_t out_lo_col, void* stream);
 
 /* ---- denoiser training step (LatentDiscreteModel.forward, LM:1514-1613, and its backward) ----------------- */
 /* Forward runs the same GEMM / conv / norm kernels as the normalization pass with per-utterance timesteps

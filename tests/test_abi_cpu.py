@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     from diffnorm_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared  # the ctypes binding covers the whole header
-    assert _lib.lib.dn_abi_version() == 1
+    assert _lib.lib.dn_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_argument_errors_are_reported_not_crashed():
@@ -40,7 +40,7 @@ def test_argument_errors_are_reported_not_crashed():
     assert L.dn_reduce_tgt(None, None, 1, 1, None, None, None, None, None) == -1
     assert L.dn_argmax_units(None, 0, 1, 4, 4, 4, None, None) == -1
     assert L.dn_gemm(None, 0, None) == -1
-    assert L.dn_attention(None, None, None, 1, 1, 1, 64, None) == -1
+    assert L.dn_attention(None, None, None, 1, 1, 1, 64, 0, 0, None) == -1
     d = _lib.GemmDesc()
     assert L.dn_gemm(ctypes.byref(d), 0, None) == -1
     with pytest.raises(_lib.DiffNormLibraryError):
@@ -100,3 +100,11 @@ def test_packing_layouts():
     assert torch.equal(pw.W[r0 + 128:r0 + 192, :192].float(), res[1][128:, :, 0].bfloat16().float())
     assert (pw.W[r0 + 128:r0 + 256, 256:] == 0).all()
     assert [tuple(s) for s in pw.segs] == [(0, 0, 4, 0, 0), (0, 2, 4, 256, 128), (0, 1, 4, 512, 128)]
+    # operand formats: fp16 weights (the sampler loop) and split-precision pairs [hi | lo] along K (the VAE)
+    ph = packing.pack_conv3(W, torch.zeros(10), fmt="f16")
+    assert ph.W.dtype == torch.float16 and torch.equal(ph.W[:10, 64:84].float(), W[:, :, 1].half().float())
+    ps = packing.pack_conv3(W, torch.zeros(10), fmt="split")
+    assert ps.W.shape == (16, 2 * 3 * 64) and ps.W.dtype == torch.bfloat16 and ps.fmt == "split"
+    hi, lo = ps.W[:10, 64:84].float(), ps.W[:10, 192 + 64:192 + 84].float()
+    assert torch.equal(hi, W[:, :, 1].bfloat16().float())
+    assert (hi + lo - W[:, :, 1]).abs().max() <= 2.0 ** -16 * W.abs().max()

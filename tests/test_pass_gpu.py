@@ -111,7 +111,8 @@ def test_stages_and_pass_against_golden(name):
 def test_fused_resid_norm_denoiser_call_matches_unfused():
     """engine.fuse_norm (dn_gemm_resid_norm in the transformer stack) against the default un-fused stack on the same
     denoiser call: eps_hat within the bf16 rounding noise of the stack (hb differs by <= 1 bf16 ulp per norm)."""
-    g, arch, sd, eng = setup_case("pass_z16_parity")
+    g, arch, sd, _ = setup_case("pass_z16_parity")
+    eng = DiffNormEngine(sd, DEV, wfmt="bf16")    # dn_gemm_resid_norm multiplies bf16 weights
     t = lambda k: torch.from_numpy(g[k])
     B, T, _ = t("feat").shape
     lens = torch.from_numpy(g["lengths"]).to(torch.int32).to(DEV)

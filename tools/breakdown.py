@@ -28,7 +28,7 @@ def main():
     eng: DiffNormEngine = ldm._engine()
     B, T = a.batch, a.frames
     lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
-    xb = eng.buf("s.xb", B * T, eng.zp)
+    xb = eng.buf("s.xb", B * T, eng.xw)
     t_idx = torch.tensor([50], dtype=torch.int32, device="cuda")
     feat = torch.randn(B, T, 768, device="cuda")
     eps = torch.randn(B, a.latent_dim, T, device="cuda")
