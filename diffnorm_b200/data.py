@@ -183,6 +183,219 @@ class NormalizationRunner:
         return lines
 
 
+# ------------------------------------------------------------------------------------------------ training dataset
+@dataclass
+class ReprToReprDatasetItem:  # repr_to_repr_unit_dataset.py:34-42
+    index: int
+    src_feat: "torch.Tensor"
+    tgt_feat: "torch.Tensor"
+    tgt_unit: "torch.Tensor"
+    reduce_tgt_unit: "torch.Tensor"
+    reduce_tgt_feat: "torch.Tensor"
+
+
+def _feat_manifest(path: str) -> Dict[str, Tuple[str, str]]:
+    """repr_to_repr_unit_dataset.py:311-323: id (file name up to the first dot) -> (feature path, length string)."""
+    root, rows = None, {}
+    with open(path, "r") as f:
+        root = f.readline().strip()
+        for line in f:
+            if len(line.strip()) == 0:
+                continue
+            name, n = line.strip().split("\t")
+            rows[name.split(".")[0]] = (f"{root}/{name}", n)
+    return rows
+
+
+def load_samples_from_tsv(src_feat_dir: str, tgt_feat_dir: str, raw_audio_root: str, split: str, log=print) -> List[Dict]:
+    """ReprToReprUnitDatasetCreator._load_samples_from_tsv (repr_to_repr_unit_dataset.py:309-369): join the source and
+    target feature manifests with the unit TSV; utterances missing from either manifest or whose unit count differs from
+    the target feature length are skipped; non-train splits stop after the 4001st kept utterance (:365-368)."""
+    src = _feat_manifest(f"{src_feat_dir}/{split}.manifest.tsv")
+    tgt = _feat_manifest(f"{tgt_feat_dir}/{split}.manifest.tsv")
+    samples: List[Dict] = []
+    with open(f"{raw_audio_root}/{split}.tsv") as f:
+        f.readline()
+        for line in f:
+            if len(line.strip()) == 0:
+                continue
+            uid, _src_audio, _src_n, units, _tgt_n = line.rstrip().split("\t")
+            if uid not in src or uid not in tgt:
+                log(f"src_id: {uid} not found in feat manifest")
+                continue
+            tokens = [int(x) for x in units.split(" ")]
+            if len(tokens) != int(tgt[uid][1]):
+                log(f"warning: mismatched feature and unit size. tgt_tokens: {len(tokens)}, tgt_feat_len: {tgt[uid][1]}")
+                continue
+            samples.append({"id": uid, "src_audio": src[uid][0], "src_n_frames": src[uid][1], "tgt_audio": tgt[uid][0],
+                            "tgt_unit": tokens, "tgt_n_frames": tgt[uid][1]})
+            if "train" not in split and len(samples) > 4000:
+                break
+    return samples
+
+
+def _dataset_base():
+    try:  # pragma: no cover - only where fairseq is installed
+        from fairseq.data import FairseqDataset  # type: ignore
+        return FairseqDataset
+    except Exception:  # noqa: BLE001
+        import torch.utils.data
+        return torch.utils.data.Dataset
+
+
+class ReprToReprUnitDataset(_dataset_base()):
+    """Training / validation dataset of both tasks (repr_to_repr_unit_dataset.py:46-258): per utterance the source
+    features, the target mHuBERT features, the target units, and their run-length-reduced forms; `collater` builds the
+    sample dict the two criterions read: 0-padding, unit k -> dictionary index k + 4, `ntokens` = sum
+    of the reduced lengths, rows sorted by source length (descending)."""
+
+    def __init__(self, split: str, is_train_split: bool, audio_paths: List[str], tgt_feat_paths: List[str],
+                 tgt_units: List[List[int]], src_n_frames: List[int], tgt_n_frames: List[int], ids: Optional[List[str]] = None,
+                 tgt_dict=None, shuffle: bool = False, cfg=None):
+        self.split, self.cfg, self.tgt_dict = split, cfg, tgt_dict
+        self.src_n_frames, self.tgt_n_frames = list(src_n_frames), list(tgt_n_frames)
+        self.n_samples = len(audio_paths)
+        self.audio_paths, self.tgt_feat_paths, self.tgt_units, self.ids = audio_paths, tgt_feat_paths, tgt_units, ids
+        assert self.n_samples == len(self.src_n_frames) == len(self.tgt_n_frames)
+        assert ids is None or len(ids) == self.n_samples
+        self.shuffle = bool(shuffle) if is_train_split else False   # :75
+        self._lut = None
+
+    # -- the run-length reduction (:92-113); vectorised, same three outputs (index_to_keep as a LongTensor)
+    @staticmethod
+    def _reduce_tgt(tokens):
+        import torch
+        t = np.asarray(tokens, dtype=np.int64)
+        if t.size == 0:
+            return [], [1], torch.zeros(0, dtype=torch.long)   # the unconditional append of :112
+        start = np.ones(t.size, dtype=bool)
+        start[1:] = t[1:] != t[:-1]
+        keep = np.flatnonzero(start)
+        dur = np.diff(np.append(keep, t.size))
+        return t[keep].tolist(), dur.tolist(), torch.from_numpy(keep).long()
+
+    def _encode(self, units) -> "torch.Tensor":
+        """Dictionary.encode_line(" ".join(units), add_if_not_exist=False, append_eos=False).long() (:130-140): symbol
+        str(k) sits at index k + nspecial; anything outside the dictionary maps to <unk>."""
+        import torch
+        d = self.tgt_dict
+        u = np.asarray(units, dtype=np.int64)
+        if self._lut is None:
+            n = len(d) - d.nspecial if hasattr(d, "nspecial") else len(d) - 4
+            self._lut = np.array([d.index(str(k)) for k in range(n)], dtype=np.int64)
+        out = np.full(u.shape, d.unk(), dtype=np.int64)
+        ok = (u >= 0) & (u < len(self._lut))
+        out[ok] = self._lut[u[ok]]
+        return torch.from_numpy(out)
+
+    def __getitem__(self, index: int) -> ReprToReprDatasetItem:
+        import torch
+        src_feat = torch.from_numpy(np.load(self.audio_paths[index])).float()
+        tgt_feat = torch.from_numpy(np.load(self.tgt_feat_paths[index])).float()
+        units = self.tgt_units[index]
+        reduced, _dur, keep = self._reduce_tgt(units)
+        return ReprToReprDatasetItem(index=index, src_feat=src_feat, tgt_feat=tgt_feat, tgt_unit=self._encode(units),
+                                     reduce_tgt_unit=self._encode(reduced), reduce_tgt_feat=tgt_feat[keep])
+
+    def __len__(self):
+        return self.n_samples
+
+    def num_tokens(self, index):
+        return self.tgt_n_frames[index]
+
+    def size(self, index):
+        return self.tgt_n_frames[index]
+
+    @property
+    def sizes(self):
+        return np.array(self.tgt_n_frames)
+
+    @property
+    def can_reuse_epoch_itr_across_epochs(self):
+        return True
+
+    def ordered_indices(self):
+        """:177-184: descending target length, ties in original (or, for shuffled training, random) order."""
+        order = [np.random.permutation(len(self))] if self.shuffle else [np.arange(len(self))]
+        order.append([-n for n in self.tgt_n_frames])
+        return np.lexsort(order)
+
+    def batch_sampler(self, max_tokens: int = 0, max_sentences: int = 0, bsz_mult: int = 1) -> List[np.ndarray]:
+        """Batches of `ordered_indices()` under a padded-token budget (what fairseq's EpochBatchIterator asks
+        `batch_by_size` for), through the native batcher."""
+        idx = self.ordered_indices()
+        sizes = self.sizes[idx]
+        return [idx[s:e] for s, e in batch_by_size(sizes, max_tokens, max_sentences, bsz_mult)]
+
+    def collater(self, samples: List[ReprToReprDatasetItem], return_order: bool = False) -> Dict:
+        """:193-258."""
+        import torch
+        if len(samples) == 0:
+            return {}
+        B = len(samples)
+        indices = torch.tensor([x.index for x in samples], dtype=torch.long)
+        src_len = torch.tensor([x.src_feat.shape[0] for x in samples], dtype=torch.long)
+        tgt_len = torch.tensor([x.tgt_feat.shape[0] for x in samples], dtype=torch.long)
+        red_len = torch.tensor([x.reduce_tgt_unit.shape[0] for x in samples], dtype=torch.long)
+        C = samples[0].src_feat.shape[1]
+        src = samples[0].src_feat.new_zeros(B, int(src_len.max()), C)
+        tgt = samples[0].src_feat.new_zeros(B, int(tgt_len.max()), C)
+        tgt_unit = samples[0].tgt_unit.new_zeros(B, int(tgt_len.max()))
+        red_unit = samples[0].reduce_tgt_unit.new_zeros(B, int(red_len.max()))
+        red_feat = samples[0].reduce_tgt_feat.new_zeros(B, int(red_len.max()), C)
+        for i, x in enumerate(samples):
+            src[i, : x.src_feat.shape[0]] = x.src_feat
+            tgt[i, : x.tgt_feat.shape[0]] = x.tgt_feat
+            tgt_unit[i, : x.tgt_unit.shape[0]] = x.tgt_unit
+            red_unit[i, : x.reduce_tgt_unit.shape[0]] = x.reduce_tgt_unit
+            red_feat[i, : x.reduce_tgt_feat.shape[0]] = x.reduce_tgt_feat
+        src_len, order = src_len.sort(descending=True)   # rows re-ordered by SOURCE length (:228)
+        pick = lambda t: t.index_select(0, order)
+        red_len = pick(red_len)
+        return {
+            "id": pick(indices),
+            "net_input": {"src_tokens": pick(src), "src_lengths": src_len, "prev_output_tokens": None, "tgt_speaker": None},
+            "speaker": None,
+            "target": pick(tgt), "target_unit": pick(tgt_unit),
+            "reduce_target": pick(red_feat), "reduce_target_unit": pick(red_unit),
+            "target_lengths": pick(tgt_len), "reduce_target_lengths": red_len,
+            "ntokens": red_len.sum().item(), "nsentences": B,
+        }
+
+    @classmethod
+    def from_samples(cls, split: str, is_train_split: bool, samples: List[Dict], tgt_dict, shuffle: bool = False, cfg=None):
+        """ReprToReprUnitDatasetCreator._from_list (:274-304)."""
+        return cls(split, is_train_split, [s["src_audio"] for s in samples], [s["tgt_audio"] for s in samples],
+                   [s["tgt_unit"] for s in samples], [int(s["src_n_frames"]) for s in samples],
+                   [int(s["tgt_n_frames"]) for s in samples], ids=[s["id"] for s in samples], tgt_dict=tgt_dict,
+                   shuffle=shuffle, cfg=cfg)
+
+    @classmethod
+    def from_tsv(cls, src_feat_dir: str, tgt_feat_dir: str, audio_root: str, splits: str, is_train_split: bool, tgt_dict,
+                 shuffle: bool = False, cfg=None, **_unused):
+        """ReprToReprUnitDatasetCreator.from_tsv (:371-399); several comma-separated splits concatenate."""
+        parts = [cls.from_samples(sp, is_train_split, load_samples_from_tsv(src_feat_dir, tgt_feat_dir, audio_root, sp),
+                                  tgt_dict, shuffle, cfg) for sp in splits.split(",")]
+        if len(parts) == 1:
+            return parts[0]
+        samples_args = [sum((getattr(p, a) for p in parts), []) for a in
+                        ("audio_paths", "tgt_feat_paths", "tgt_units", "src_n_frames", "tgt_n_frames", "ids")]
+        return cls(splits, is_train_split, *samples_args[:5], ids=samples_args[5], tgt_dict=tgt_dict, shuffle=shuffle, cfg=cfg)
+
+    @classmethod
+    def from_manifest(cls, args, split: str, tgt_dict):
+        """What `task.load_dataset(split)` calls (speech_decoder_task.py:159-170): directories from the task's flags,
+        `shuffle` from the `--dummy-config` YAML (S2SDataConfig.shuffle, data_cfg.py)."""
+        shuffle = False
+        cfg_path = getattr(args, "dummy_config", None)
+        if cfg_path and os.path.isfile(cfg_path):
+            import yaml
+            with open(cfg_path) as f:
+                shuffle = bool((yaml.safe_load(f) or {}).get("shuffle", False))
+        return cls.from_tsv(args.src_feat_dir, args.tgt_feat_dir, args.data, split, split.startswith("train"), tgt_dict,
+                            shuffle=shuffle)
+
+
 def write_tsv(path: str, lines: Iterable[str]):
     with open(path, "w") as f:
         f.write(HEADER + "\n")

@@ -415,9 +415,44 @@ def make_vocoder():
     np.savez_compressed(os.path.join(GOLD, "vocoder_code_hifigan.npz"), **out)
 
 
+def make_dataset():
+    """The reference's own ReprToReprUnitDataset / Creator (repr_to_repr_unit_dataset.py, loaded untouched with its real
+    Dictionary by ref_loader.load_dataset_module) on the synthetic corpus of oracle/dataset_fixture.py ->
+    tests/golden/dataset_collate.npz: the kept utterance ids, ordered_indices, and every field of two collated batches."""
+    import tempfile
+
+    from oracle.dataset_fixture import write_corpus
+    ns = ref_loader.load_dataset_module()
+    d = ns.Dictionary()
+    for i in range(1000):
+        d.add_symbol(str(i))
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        src_dir, tgt_dir, tsv_dir = write_corpus(root)
+        ds = ns.module.ReprToReprUnitDatasetCreator.from_tsv(src_dir, tgt_dir, tsv_dir, ns.S2SDataConfig(shuffle=False), "train",
+                                                             True, 1, 1, tgt_dict=d)
+        out["ids"] = np.array(ds.ids)
+        out["ordered_indices"] = ds.ordered_indices()
+        out["sizes"] = ds.sizes
+        for b, idx in enumerate(([0, 3, 5, 1], [6, 2, 4])):
+            batch = ds.collater([ds[i] for i in idx])
+            out[f"b{b}_idx"] = np.array(idx)
+            for k in ("id", "target", "target_unit", "reduce_target", "reduce_target_unit", "target_lengths",
+                      "reduce_target_lengths"):
+                out[f"b{b}_{k}"] = batch[k].numpy()
+            out[f"b{b}_src_tokens"] = batch["net_input"]["src_tokens"].numpy()
+            out[f"b{b}_src_lengths"] = batch["net_input"]["src_lengths"].numpy()
+            out[f"b{b}_ntokens"] = np.int64(batch["ntokens"])
+            out[f"b{b}_nsentences"] = np.int64(batch["nsentences"])
+    np.savez_compressed(os.path.join(GOLD, "dataset_collate.npz"), **out)
+    print("dataset golden:", out["ids"].tolist(), out["ordered_indices"].tolist())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
+    if "--dataset-only" in sys.argv:
+        return make_dataset()
     if "--vocoder-only" in sys.argv:
         return make_vocoder()
     if "--batcher-only" in sys.argv:
@@ -445,6 +480,7 @@ def main():
         make_vae_train(name)
     make_kmeans()
     make_vocoder()
+    make_dataset()
 
 
 if __name__ == "__main__":

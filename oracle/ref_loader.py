@@ -120,6 +120,67 @@ def load():
     return ns
 
 
+def load_dataset_module():
+    """The reference's training dataset, `fairseq/data/audio/repr_to_repr_unit_dataset.py`, and its real
+    `fairseq/data/dictionary.py` + `fairseq/tokenizer.py`, loaded by path.  The dataset file imports a dozen fairseq.data
+    names it never calls on this path (audio transforms, S2T dataset helpers): those are empty stubs; the data config is a
+    stub exposing the three members the constructor reads (shuffle, get_feature_transforms, get_waveform_transforms)."""
+    if "ds" in _cache:
+        return _cache["ds"]
+    load()   # registers the fairseq / fairseq.utils stubs
+    fs = os.path.join(REF_ROOT, "fairseq")
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class _PathManager:
+        open = staticmethod(open)
+
+    mod("fairseq.file_chunker_utils", Chunker=object, find_offsets=lambda *a, **k: [])
+    mod("fairseq.file_io", PathManager=_PathManager)
+    _load("fairseq.tokenizer", os.path.join(fs, "tokenizer.py"))
+    data = mod("fairseq.data", data_utils=types.ModuleType("fairseq.data.data_utils"))
+    sys.modules["fairseq.data.data_utils"] = data.data_utils
+    dic = _load("fairseq.data.dictionary", os.path.join(fs, "data", "dictionary.py"))
+    data.Dictionary = dic.Dictionary
+    data.FairseqDataset = torch.utils.data.Dataset
+    data.ConcatDataset = torch.utils.data.ConcatDataset
+
+    class _NoTransforms:
+        @classmethod
+        def from_config_dict(cls, cfg=None):
+            return None
+
+    class S2SDataConfig:  # fairseq/data/audio/data_cfg.py: only what repr_to_repr_unit_dataset.py:75-88 reads
+        def __init__(self, shuffle=False):
+            self.shuffle, self.use_audio_input = shuffle, False
+
+        def get_feature_transforms(self, split, is_train):
+            return None
+
+        def get_waveform_transforms(self, split, is_train):
+            return None
+
+    mod("fairseq.data.audio")
+    mod("fairseq.data.audio.audio_utils", get_features_or_waveform=None)
+    mod("fairseq.data.audio.data_cfg", S2SDataConfig=S2SDataConfig)
+    mod("fairseq.data.audio.speech_to_text_dataset", SpeechToTextDataset=object, SpeechToTextDatasetCreator=object,
+        TextTargetMultitaskData=object, _collate_frames=None, _is_int_or_np_int=None)
+    mod("fairseq.data.audio.feature_transforms", CompositeAudioFeatureTransform=_NoTransforms)
+    mod("fairseq.data.audio.waveform_transforms", CompositeAudioWaveformTransform=_NoTransforms)
+    mod("fairseq.data.audio.dataset_transforms", CompositeAudioDatasetTransform=_NoTransforms)
+    mod("fairseq.data.audio.speech_to_speech_dataset", SpeechToSpeechDataset=object)
+    ds = _load("fairseq.data.audio.repr_to_repr_unit_dataset",
+               os.path.join(fs, "data", "audio", "repr_to_repr_unit_dataset.py"))
+    _cache["ds"] = types.SimpleNamespace(module=ds, Dictionary=dic.Dictionary, S2SDataConfig=S2SDataConfig)
+    return _cache["ds"]
+
+
 def load_vocoder():
     """The reference's unit vocoder classes, loaded by path from the untouched files: hifigan.py (torch only),
     fastspeech2.py (for VariancePredictor; its other fairseq imports are stubbed with the semantics the class needs:
