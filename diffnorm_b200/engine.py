@@ -454,7 +454,7 @@ class DiffNormEngine:
         # batches of a dataset are mostly one-off (B, T) shapes and run eager (the host stays ~20x ahead of a 20 ms step)
         seen = self._shape_seen.get((B, T), 0)
         self._shape_seen[(B, T)] = seen + 1
-        want_graph = use_graph and sampler == "ddim" and start_step > 2
+        want_graph = use_graph and sampler == "ddim" and start_step > 2   # (a graph replays t -= 1 steps; 1-2 calls run eager)
         graph = self._ddim_graph(B, T) if want_graph and (seen >= self.graph_after or ("ddim", B, T) in self._graphs) else None
         graph_kernels = self._graph_kernels.get(("ddim", B, T), 0)
         lens = self.buf("s.len", B, 1, i32, frames=False).view(-1)
@@ -473,7 +473,8 @@ class DiffNormEngine:
         calls = 0
         if sampler == "ddim":
             t_idx.fill_(start_step - 1)
-            n = start_step - 1  # t = start-1 .. 1 (LM:1402,1444)
+            # t = start-1 .. 1; the loop breaks after t = 1 (LM:1402,1444), so t = 0 runs only when start_step == 1
+            n = max(start_step - 1, 1)
             if collect and n > 0:
                 out["eps_first"] = self.denoise(xb, lens, B, T, t_idx).view(B, T, -1)[..., :z].clone()
             for _ in range(n):

@@ -21,7 +21,10 @@ def load_model(ckpt_path: str, device: str):
     from_checkpoint=True) -> load_state_dict(strict=True) (fairseq/checkpoint_utils.py:391-493)."""
     from .plugin import compat
     state = torch.load(ckpt_path, map_location="cpu", weights_only=False)
-    args = state.get("args") or argparse.Namespace(**dict(state["cfg"]["model"]))
+    args = state.get("args")
+    if args is None:
+        m = state["cfg"]["model"]   # a Namespace for legacy (non-dataclass) models such as diff_discrete, else a dict / DictConfig
+        args = argparse.Namespace(**(vars(m) if isinstance(m, argparse.Namespace) else dict(m)))
     if not hasattr(args, "task"):
         args.task = "speech_diffusion_discrete"
     if getattr(args, "arch", None) not in ("diff_discrete",):

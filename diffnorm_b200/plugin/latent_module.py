@@ -51,13 +51,15 @@ def _transformer_spec(pre: str, dim: int, depth: int, heads: int, dim_head: int,
     s: List[Spec] = []
     for l in range(depth):
         p = f"{pre}layers.{l}."
-        for n in (0, 4):
-            if dim_time is not None:
-                s += _lin(p + f"{n}.to_gamma_beta", 2 * dim, dim_time)
-            else:
-                s.append((p + f"{n}.gamma", (dim,), "ones", 0))
+
+        def norm(n):
+            return _lin(p + f"{n}.to_gamma_beta", 2 * dim, dim_time) if dim_time is not None else [(p + f"{n}.gamma", (dim,), "ones", 0)]
+        # the reference's ModuleList order (LM:666-674): norm, attention, norm, feed-forward — parameters() (and with it the
+        # optimizer state of a resumed checkpoint) follows registration order
+        s += norm(0)
         s += _lin(p + "1.to_q", hd, dim, bias=False) + _lin(p + "1.to_kv", 2 * hd, dim, bias=False)
         s += _lin(p + "1.to_out", dim, hd, bias=False)
+        s += norm(4)
         s += _lin(p + "5.0", 2 * inner, dim) + _lin(p + "5.2.1", inner, inner, 3) + _lin(p + "5.3", dim, inner)
     s.append((pre + "to_pred.0.gamma", (dim,), "ones", 0))
     return s + _lin(pre + "to_pred.1", dim, dim, bias=False)
@@ -123,12 +125,30 @@ class SpeechVAEEncoderDecoder(FairseqEncoder):
         self.cfg = DiffNormConfig(latent_dim=latent_dim, feat_dim=dim)
         _materialise(self, vae_spec(self.cfg))
         self._owner = None  # set by LatentDiscreteModel so both share one engine
+        self._eng = None    # stand-alone VAE (speech_vae_decoder checkpoints): its own VAE-only engine
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self):
+        self._eng = None
+        self._vae_trainer_obj = None
+
+    def train(self, mode: bool = True):
+        # optimizers update weights through p.data (fairseq/optim/adam.py:183-237), which no version counter sees: any
+        # switch into training mode drops the packed inference weights, they are re-packed on the next inference call
+        if mode:
+            self._eng = None
+        return super().train(mode)
 
     def _engine(self):
-        if self._owner is None:
-            raise RuntimeError("stand-alone VAE inference goes through LatentDiscreteModel's engine; wrap the VAE in "
-                               "LatentDiscreteModel (diff_discrete) — VAE-only execution is not built yet")
-        return self._owner()._engine()
+        if self._owner is not None and self._owner() is not None:
+            return self._owner()._engine()
+        p = next(self.parameters())
+        _require_cuda(p, "SpeechVAEEncoderDecoder")
+        if self._eng is None:
+            from ..engine import DiffNormEngine
+            sd = {"speech_decoder." + k: v for k, v in self.state_dict().items()}
+            self._eng = DiffNormEngine(sd, device=str(p.device), cfg=self.cfg, vae_only=True)
+        return self._eng
 
     @torch.no_grad()
     def encode_feature(self, feature: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -235,18 +255,23 @@ class LatentDiscreteModel(FairseqEncoder):
         self._eng = None
         self._trainer_obj = None   # holds the packed frozen VAE
 
-    def _param_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+    def train(self, mode: bool = True):
+        # fairseq's optimizers write through p.data (optim/adam.py:183-237): no version counter changes, so staleness of
+        # the packed inference weights is keyed on the mode switch instead: entering training mode (and every training
+        # forward, below) drops the engine; the next inference call re-packs from the current parameters.
+        if mode:
+            self._eng = None
+        return super().train(mode)
 
     def _engine(self):
         p = next(self.model.parameters())
         _require_cuda(p, "LatentDiscreteModel")
-        ver = self._param_version()
-        if self._eng is None or self._eng_version != ver:
+        dev = (p.device, p.data_ptr())
+        if self._eng is None or self._eng_version != dev:   # also re-pack after .to(device) / a re-allocated parameter
             from ..engine import DiffNormEngine
             sd = {k: v for k, v in self.state_dict().items()}
-            self._eng = DiffNormEngine(sd, device=str(p.device), cfg=None)
-            self._eng_version = ver
+            self._eng = DiffNormEngine(sd, device=str(p.device), cfg=self.cfg)
+            self._eng_version = dev
         return self._eng
 
     @property
@@ -308,6 +333,8 @@ class LatentDiscreteModel(FairseqEncoder):
             raise ValueError("tgt_mask is required (diff_discrete.py:46-54 always passes it)")
         tr = self._trainer()
         tr.drop_p = 0.1 if self.training else 0.0
+        if self.training:
+            self._eng = None      # the weights are about to move: the packed inference copy is stale from here on
         lens = _mask_to_lengths(tgt_mask)
         names = list(tr.P.keys())
         params = [tr.P[n] for n in names]

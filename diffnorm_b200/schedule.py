@@ -13,7 +13,10 @@ import numpy as np
 
 
 class DDPMScheduler:
-    def __init__(self, timesteps: int = 200, betas: np.ndarray = None):
+    def __init__(self, timesteps: int = 200, scale: float = 1.0, *, betas: np.ndarray = None):
+        """Same positional signature as the reference (LM:1242: timesteps, scale); `betas` (keyword only) builds a
+        re-spaced schedule."""
+        self.scale = scale
         if betas is None:
             ab = lambda u: math.cos((u + 0.008) / 1.008 * math.pi / 2) ** 2
             betas = np.array([min(1 - ab((i + 1) / timesteps) / ab(i / timesteps), 0.999) for i in range(timesteps)],
@@ -41,6 +44,33 @@ class DDPMScheduler:
                 nb.append(1 - ac / last)
                 last = ac
         return DDPMScheduler(betas=np.array(nb, dtype=np.float64)), keep
+
+    # ---- the reference's lookups (LM:1226-1238, :1278-1297): float64 table entry -> fp32 -> broadcast to `shape`
+    @staticmethod
+    def _extract(arr: np.ndarray, t, shape):
+        import torch
+        res = torch.from_numpy(arr).to(device=t.device)[t].float()
+        while res.dim() < len(shape):
+            res = res[..., None]
+        return res.expand(shape)
+
+    def get_beta(self, t, shape):
+        return self._extract(self.betas, t, shape)
+
+    def get_sqrt_alpha_cum(self, t, shape):
+        return self._extract(self.sqrt_alphas_cumprod, t, shape)
+
+    def get_sqrt_one_minus_alpha_cum(self, t, shape):
+        return self._extract(self.sqrt_one_minus_alphas_cumprod, t, shape)
+
+    def get_alpha_cum(self, t, shape):
+        return self._extract(self.alphas_cumprod, t, shape)
+
+    def get_alpha_prev_cum(self, t, shape):
+        return self._extract(self.alphas_cumprod_prev, t, shape)
+
+    def get_snr(self, t):
+        return self.get_sqrt_alpha_cum(t, t.shape) ** 2 / self.get_sqrt_one_minus_alpha_cum(t, t.shape) ** 2
 
     # ---- device coefficient rows (float32 x 8 per step) -------------------------------------------------------
     def ddim_rows(self) -> np.ndarray:

@@ -31,6 +31,8 @@ PASS_CASES = {
     "pass_z16_default": (16, 0, None, 2, 40, [40, 29], 6, 11),
     "pass_z16_parity": (16, 1, "parity", 2, 48, [48, 33], 8, 12),
     "pass_z128_parity": (128, 2, "parity", 1, 40, [40], 5, 13),
+    # start_step = 1: timesteps = [0], the break at time == 1 never fires -> ONE call at t = 0 (LM:1402,1444)
+    "pass_z16_start1": (16, 1, "parity", 1, 24, [24], 1, 14),
 }
 
 
@@ -415,6 +417,14 @@ def make_vocoder():
     np.savez_compressed(os.path.join(GOLD, "vocoder_code_hifigan.npz"), **out)
 
 
+def make_keys():
+    """state_dict key ORDER of the reference's LatentDiscreteModel (= its parameter registration order, which is what an
+    optimizer state of a resumed checkpoint is matched by) -> tests/golden/state_dict_keys_z16.txt."""
+    ldm = ref_loader.build_reference_model(16)
+    with open(os.path.join(GOLD, "state_dict_keys_z16.txt"), "w") as f:
+        f.write("\n".join(ldm.state_dict().keys()) + "\n")
+
+
 def make_dataset():
     """The reference's own ReprToReprUnitDataset / Creator (repr_to_repr_unit_dataset.py, loaded untouched with its real
     Dictionary by ref_loader.load_dataset_module) on the synthetic corpus of oracle/dataset_fixture.py ->
@@ -453,6 +463,10 @@ def main():
     torch.manual_seed(0)
     if "--dataset-only" in sys.argv:
         return make_dataset()
+    if "--keys-only" in sys.argv:
+        return make_keys()
+    if "--pass-only" in sys.argv:
+        return make_pass(sys.argv[sys.argv.index("--pass-only") + 1])
     if "--vocoder-only" in sys.argv:
         return make_vocoder()
     if "--batcher-only" in sys.argv:
@@ -481,6 +495,7 @@ def main():
     make_kmeans()
     make_vocoder()
     make_dataset()
+    make_keys()
 
 
 if __name__ == "__main__":

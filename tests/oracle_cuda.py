@@ -46,7 +46,7 @@ def oracle_pass(sd: Dict[str, torch.Tensor], arch: "O.Arch", feat, mask, start_s
         z = torch.cat([O.vae_encode(sd, arch, feat[i:i + chunk], eps_vae[i:i + chunk]) for i in range(0, B, chunk)])
         x = O.q_sample(sch, z, start_step, eps_q)
         out["z"], out["x_start"] = z, x.clone()
-        for t in range(start_step - 1, 0, -1):
+        for t in (range(start_step - 1, 0, -1) if start_step > 1 else [0]):   # LM:1402,1444
             eh = torch.cat([O.denoiser(sd, arch, x[i:i + chunk], torch.full((min(chunk, B - i),), t, dtype=torch.long,
                                                                             device=dev), mask[i:i + chunk])
                             for i in range(0, B, chunk)])

@@ -74,7 +74,7 @@ def test_reduce_tgt_c_matches_reference():
         assert kp[:r].tolist() == g[n + "_keep"].tolist(), n
 
 
-@pytest.mark.parametrize("name", ["pass_z16_default", "pass_z16_parity", "pass_z128_parity"])
+@pytest.mark.parametrize("name", ["pass_z16_default", "pass_z16_parity", "pass_z128_parity", "pass_z16_start1"])
 def test_pass_matches_reference(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     z, parity = int(g["latent_dim"]), bool(g["parity_gains"])

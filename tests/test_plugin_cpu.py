@@ -46,6 +46,11 @@ def test_state_dict_keys_match_reference_layout(z):
     sd = model.state_dict()
     ref = O.init_state_dict(O.Arch(latent_dim=z), seed=3)
     assert set(sd) == {"encoder." + k for k in ref}
+    if z == 16:   # ORDER too (parameter registration order; golden from the live reference, oracle/make_golden.py make_keys)
+        import os
+        want = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "state_dict_keys_z16.txt")).read().split()
+        assert list(sd) == ["encoder." + k for k in want]
+        assert [n for n, _ in model.named_parameters()] == ["encoder." + k for k in want if not k.endswith("_float_tensor")]
     assert all(tuple(sd["encoder." + k].shape) == tuple(v.shape) for k, v in ref.items())
     model.load_state_dict({"encoder." + k: v for k, v in ref.items()}, strict=True)
     assert torch.equal(model.encoder.model.final_proj.weight, ref["model.final_proj.weight"])
@@ -69,6 +74,21 @@ def test_compute_requires_cuda_and_training_not_silently_faked():
     assert abs(red["loss"] - 2.5) < 1e-6 and red["sample_size"] == 4   # ddpm_discrete_loss.py:77-95 weighting
     crit = task.build_criterion(_args())
     assert type(crit).__name__ == "DDPMDiscreteLoss" and crit.logging_outputs_can_be_summed() is False
+
+
+def test_scheduler_has_the_reference_signature_and_accessors():
+    from diffnorm_b200.plugin.latent_module import DDPMScheduler
+    s = DDPMScheduler(200, 1.0)          # (timesteps, scale) like LM:1242
+    o = O.Schedule(200)
+    t = torch.tensor([0, 99, 199])
+    assert s.scale == 1.0 and s.num_timesteps == 200
+    got = s.get_sqrt_alpha_cum(t, (3, 4, 5))
+    assert got.shape == (3, 4, 5) and got.dtype == torch.float32
+    assert torch.equal(got[:, 0, 0], torch.from_numpy(o.sqrt_alphas_cumprod)[t].float())
+    assert torch.equal(s.get_alpha_prev_cum(t, (3,)), torch.from_numpy(o.alphas_cumprod_prev)[t].float())
+    assert torch.equal(s.get_beta(t, (3,)), torch.from_numpy(o.betas)[t].float())
+    snr = s.get_snr(t)
+    assert torch.allclose(snr, torch.from_numpy(o.alphas_cumprod / (1 - o.alphas_cumprod))[t].float(), rtol=1e-5)
 
 
 def test_mask_must_be_prefix():
