@@ -6,8 +6,9 @@ A "step" = one full pass of the hot path over one batch of synthetic 768-d featu
 batch 64 x 1000 frames, paper-size VAE + denoiser, start_step 100 => 99 denoiser calls, then decode, argmax,
 _reduce_tgt).  Work is sharded by utterance: every rank processes its own batch, no data-path collective
 ("scaling": "weak"); `value` = frames all ranks normalized / max-over-ranks device time.
-`--impl reference` times the reference algorithm's CPU implementation (the oracle port; the reference itself is
-Python and cannot travel to the GPU box) on the host cores.
+`--impl reference` times the reference's own CPU implementation on the host cores: the UNMODIFIED latent_module.py,
+staged for the GPU box by `make -C oracle ref` (oracle/_ref/reference, git-ignored), through ddim_sample on a bounded
+sample.  `--impl reference-gpu` runs the same modules eagerly on one B200 (fp32 / TF32 / autocast bf16).
 """
 from __future__ import annotations
 
@@ -97,39 +98,73 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU (reference) arm
-def cpu_pass_sample(z: int, B: int, T: int, start_step: int, calls_timed: int, threads: int):
-    """Times the oracle port of the reference path on the host: encode + `calls_timed` denoiser calls + decode +
-    argmax + reduce, and extrapolates the loop to start_step-1 calls.  Returns (frames/s, description, seconds)."""
-    from oracle import diffnorm_oracle as O
-    torch.set_num_threads(threads)
-    arch = O.Arch(latent_dim=z)
-    sd = O.init_state_dict(arch, seed=0)
-    g = torch.Generator().manual_seed(1234)
-    feat = torch.randn(B, T, 768, generator=g)
-    mask = torch.ones(B, T, dtype=torch.bool)
-    ev, eq = torch.randn(B, z, T, generator=g), torch.randn(B, T, z, generator=g)
-    sch = O.Schedule(arch.timesteps)
-    with torch.no_grad():
+CPU_SAMPLE = (2, 1000)   # utterances x frames of the bounded CPU sample: config 2's utterance length, 2 of its 64 utterances
+
+
+class CpuReference:
+    """The reference's CPU implementation of the path on the host cores.  kind "reference": the UNMODIFIED
+    latent_module.py / distributions.py (found under /root/reference, or staged by `make -C oracle ref` under
+    oracle/_ref/reference for the GPU box) through their public entry LatentDiscreteModel.ddim_sample; kind "port": the
+    oracle port, only if those files are missing.  A full config-2 pass takes ~20 min on 16 cores, so each step is a
+    bounded sample: ddim_sample(start_step=3) on B 2 x T 1000 = encode + 2 of the 99 denoiser calls + decode + argmax;
+    the cost of one call comes from the difference to ddim_sample(start_step=2), and the loop is extrapolated to 99."""
+
+    def __init__(self, z: int, threads: int):
+        from oracle import diffnorm_oracle as O
+        from oracle import ref_loader
+        torch.set_num_threads(threads)
+        self.O, self.z, self.threads = O, z, threads
+        B, T = CPU_SAMPLE
+        g = torch.Generator().manual_seed(1234)
+        self.feat = torch.randn(B, T, 768, generator=g)
+        self.mask = torch.ones(B, T, dtype=torch.bool)
+        self.ref_units = torch.zeros(B, T, dtype=torch.long)
+        self.kind = "reference" if ref_loader.available() else "port"
+        if self.kind == "reference":
+            torch.manual_seed(0)
+            self.ldm = ref_loader.build_reference_model(z).eval()   # the reference's own default init
+        else:
+            self.arch = O.Arch(latent_dim=z)
+            self.sd = O.init_state_dict(self.arch, seed=0)
+        self.t_short = []
+
+    def sample(self, start_step: int) -> float:
+        """Seconds of one pass with start_step - 1 denoiser calls, through the reference's public entry."""
+        O = self.O
         t0 = time.perf_counter()
-        zl = O.vae_encode(sd, arch, feat, ev)
-        x = O.q_sample(sch, zl, start_step, eq)
-        t1 = time.perf_counter()
-        for k in range(calls_timed):
-            t = start_step - 1 - k
-            eh = O.denoiser(sd, arch, x, torch.full((B,), t, dtype=torch.long), mask)
-            x = O.ddim_step(sch, x, eh, t)
-        t2 = time.perf_counter()
-        rec, logits = O.vae_decode(sd, arch, x, mask)
-        units = torch.argmax(logits, -1) - O.UNIT_OFFSET
-        for b in range(B):
-            O.reduce_tgt(units[b].tolist())
-        t3 = time.perf_counter()
-    calls = start_step - 1
-    per_call = (t2 - t1) / max(calls_timed, 1)
-    total = (t1 - t0) + per_call * calls + (t3 - t2)
-    desc = (f"oracle port of the reference path, fp32 torch CPU, B {B} x T {T}, z {z}: encode + {calls_timed} of {calls} "
-            f"denoiser calls + decode + argmax + reduce timed ({t3 - t0:.1f} s), loop extrapolated x{calls}")
-    return B * T / total, desc, t3 - t0
+        with torch.no_grad():
+            if self.kind == "reference":
+                toks, _, _, _ = self.ldm.ddim_sample(self.feat, input_mask=self.mask, ref_units=self.ref_units, start_step=start_step)
+            else:
+                B, T = CPU_SAMPLE
+                g = torch.Generator().manual_seed(1)
+                out = O.normalize_pass(self.sd, self.arch, self.feat, self.mask, start_step, torch.randn(B, self.z, T, generator=g),
+                                       torch.randn(B, T, self.z, generator=g))
+                toks = out["out_tokens"]
+            for tk in toks:     # the driver's second reduce (diff_norm_synthesis.py:213-216), Python like the reference's
+                O.reduce_tgt(tk.tolist())
+        return time.perf_counter() - t0
+
+    def calibrate(self):
+        self.t_short.append(self.sample(2))      # encode + 1 call + decode
+
+    def step(self, calls: int):
+        """Returns (frames/s extrapolated to `calls` denoiser calls, seconds actually spent)."""
+        if not self.t_short:
+            self.calibrate()
+        t3 = self.sample(3)                      # encode + 2 calls + decode
+        per_call = max(t3 - float(np.mean(self.t_short)), 1e-6)
+        total = t3 + (calls - 2) * per_call
+        B, T = CPU_SAMPLE
+        return B * T / total, t3
+
+    def describe(self, calls: int, seconds: float) -> str:
+        B, T = CPU_SAMPLE
+        what = ("the UNMODIFIED reference modules (latent_module.py LatentDiscreteModel.ddim_sample, fp32 torch CPU)"
+                if self.kind == "reference" else "oracle port of the reference path (fp32 torch CPU)")
+        return (f"{what} on a bounded sample B {B} x T {T}, z {self.z}: ddim_sample(start_step=3) = encode + 2 of {calls} denoiser "
+                f"calls + decode + argmax + reduce timed ({seconds:.1f} s per step); per-call cost from the difference to "
+                f"ddim_sample(start_step=2); loop extrapolated to {calls} calls")
 
 
 def run_reference(args):
@@ -137,23 +172,70 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals, desc = [], ""
-    B, T = 8, 500  # bounded sample shape (BASELINE configs[0] shape; per-frame cost is ~shape independent on CPU)
-    for i in range(args.warmup + args.steps):
-        v, desc, _ = cpu_pass_sample(args.latent_dim, B, T, args.start_step, 1 if i < args.warmup else 2, threads)
-        if i >= args.warmup:
-            vals.append(v)
+    cpu = CpuReference(args.latent_dim, threads)
+    calls = args.start_step - 1
+    for _ in range(max(args.warmup, 1)):
+        cpu.calibrate()
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, s = cpu.step(calls)
+        vals.append(v)
+        secs.append(s)
     value = float(np.mean(vals))
+    desc = cpu.describe(calls, float(np.mean(secs)))
+    cfg = workload_config(args)
+    cfg["workload"] += " || reference arm: " + desc
+    cfg["sample"] = {"batch": CPU_SAMPLE[0], "frames": CPU_SAMPLE[1], "calls_timed": 2, "calls_extrapolated_to": calls}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * args.batch * args.frames / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": cpu.kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def run_reference_gpu(args):
+    """BASELINE.md §3's second baseline: the UNMODIFIED reference modules on one B200 through ddim_sample, eager PyTorch:
+    strict fp32 (TF32 off), TF32, or torch.autocast(bf16) (--ref-precision).  Full config shape, all calls, no extrapolation."""
+    from oracle import ref_loader
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not ref_loader.available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "reference files not staged (make -C oracle ref)"}))
+        return
+    prec = args.ref_precision
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = prec == "tf32"
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    ldm = ref_loader.build_reference_model(args.latent_dim).eval().to(dev)
+    B, T, start = args.batch, args.frames, args.start_step
+    g = torch.Generator().manual_seed(1234)
+    feat = torch.randn(B, T, 768, generator=g).to(dev)
+    mask = torch.ones(B, T, dtype=torch.bool, device=dev)
+    ref_units = torch.zeros(B, T, dtype=torch.long, device=dev)
+
+    def step(s):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=prec == "bf16"):
+            return ldm.ddim_sample(feat, input_mask=mask, ref_units=ref_units, start_step=s)
+
+    step(3)   # warm-up: cuDNN / cuBLAS handles and autotuning, 2 calls
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(start)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    cfg = workload_config(args)
+    cfg["weights"] = f"reference default init; eager PyTorch {prec}"
+    print(json.dumps({"impl": "reference-gpu", "precision": prec, "metric": METRIC, "value": B * T / (ms / 1e3), "unit": UNIT,
+                      "n_gpus": 1, "steps": args.steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "dtype": prec,
+                      "data": "synthetic", "config": cfg, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
 
 
 def workload_config(args):
@@ -162,7 +244,9 @@ def workload_config(args):
                         f"DDIM eta=0 stride 1 = the reference sampler), VAE encode + decode + argmax + _reduce_tgt",
             "batch": args.batch, "frames": args.frames, "latent_dim": args.latent_dim, "start_step": args.start_step,
             "sharding": "by utterance, no collective", "l2": "inputs 197 MB/step and >1 GB of activations per call exceed the 126 MB L2",
-            "weights": "random init (torch default init law), bf16 operands / fp32 accumulate"}
+            "weights": "random init (torch default init law)",
+            "operands": "fp16 x fp16 -> fp32 accumulate in the 99-call loop (fp32 latent, residual stream and logits); VAE "
+                        "encoder / decoder in split precision (bf16 hi|lo pairs, 3 MMAs per K block)"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -278,11 +362,13 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, desc, _ = cpu_pass_sample(z, 8, 500, start, 2, threads)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
+            ref = CpuReference(z, threads)
+            ref.calibrate()
+            v, secs = ref.step(calls)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": ref.kind, "sample": ref.describe(calls, secs)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -299,7 +385,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--ref-precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="--impl reference-gpu only")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--latent-dim", type=int, default=16)
@@ -308,6 +395,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device for the product arm (there is no CPU fallback); "

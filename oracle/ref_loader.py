@@ -16,7 +16,12 @@ import types
 import torch
 from torch import nn
 
+# /root/reference in the authoring container; on the GPU box the untouched files of the path staged by `make -C oracle ref`
+# under oracle/_ref/reference (git-ignored, travels with the snapshot; sha256 list in oracle/_ref/reference.sha256)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
 REF_ROOT = os.environ.get("DIFFNORM_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REF_ROOT, "fairseq", "models", "text_to_speech", "latent_module.py")):
+    REF_ROOT = _STAGED
 _TTS = os.path.join(REF_ROOT, "fairseq", "models", "text_to_speech")
 
 
