@@ -380,6 +380,194 @@ def run_ours(args):
         print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ configs 4 and 5
+class _Dist:
+    """One process per GPU (torchrun env), NCCL for the barrier / max-over-ranks / gathers only."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(self, x: float, op="max") -> float:
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def run_dataset(args):
+    """BASELINE config 4: dataset-scale normalization of --utts synthetic variable-length utterances (N_i ~
+    round(exp(N(ln 600, 0.5^2))) clipped to [200, 2000], seed 1234), length-bucketed under a padded-frame budget
+    and sharded by utterance over the ranks with the LPT plan (no data-path collective).  A step = one pass over the whole
+    set.  `value` = valid (un-padded) frames / max-over-ranks sum of the device time of the passes' batches (features
+    resident); `e2e` = valid frames / max-over-ranks wall time of the same pass with every batch's features copied from
+    pinned host memory and its reduced units copied back."""
+    from diffnorm_b200 import _lib, data
+    from diffnorm_b200.plugin import compat
+    D = _Dist()
+    dev, rank, world = D.dev, D.rank, D.world
+    z, start = args.latent_dim, args.start_step
+    torch.manual_seed(0)
+    ns = argparse.Namespace(task="speech_diffusion_discrete", arch="diff_discrete", target_is_code=True,
+                            target_code_size=1000, latent_dim=z)
+    ldm = compat.setup_task(ns).build_model(ns, from_checkpoint=True).to(dev).eval().encoder
+    eng = ldm._engine()
+    rng = np.random.default_rng(1234)
+    n = np.clip(np.rint(np.exp(rng.normal(np.log(600.0), 0.5, size=args.utts))), 200, 2000).astype(np.int64)
+    plan = data.plan_batches(n, args.max_tokens, world_size=world, pad_multiple=8)[rank]
+    eng.reserve(args.max_tokens)
+    my_valid = int(sum(int(n[idx].sum()) for idx in plan))
+    my_padded = int(sum(len(idx) * int(n[idx].max()) for idx in plan))
+    host = torch.randn(args.max_tokens * 768, generator=torch.Generator().manual_seed(rank)).pin_memory()
+
+    def one_pass(limit=None):
+        ev, h2d, d2h = [], 0, 0
+        for k, idx in enumerate(plan):
+            if limit is not None and k >= limit:
+                break
+            B, T = len(idx), int(n[idx].max())
+            lens = torch.from_numpy(n[idx].astype(np.int32)).to(dev, non_blocking=True)
+            feat = host[: B * T * 768].view(B, T, 768).to(dev, non_blocking=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = ldm.normalize_units(feat, lens, start_step=start)
+            e1.record()
+            res = [out[k2].to("cpu", non_blocking=True) for k2 in ("dedup", "counts")]
+            ev.append((e0, e1))
+            h2d += B * T * 768 * 4 + B * 4
+            d2h += sum(r.numel() * r.element_size() for r in res)
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) * 1e-3, h2d, d2h
+
+    one_pass(limit=max(args.warmup, 1))      # warm-up on the first batches: kernel load, workspace at its final size
+    D.barrier()
+    sampler = ClockSampler(D.local) if rank == 0 else None
+    n0, r0 = _lib.launch_count(), eng.replayed_kernels
+    dev_s, wall_s, h2d, d2h = 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        d, h2d, d2h = one_pass()
+        wall_s += time.perf_counter() - t0
+        dev_s += d
+    D.barrier()
+    launches = (_lib.launch_count() - n0) + (eng.replayed_kernels - r0)
+    dev_max, wall_max = D.reduce(dev_s / args.steps), D.reduce(wall_s / args.steps)
+    valid, padded = D.reduce(my_valid, "sum"), D.reduce(my_padded, "sum")
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        peaks = load_peaks()
+        fpf = flops_per_frame(z, 600, start - 1)
+        print(json.dumps({
+            "metric": METRIC, "value": valid / dev_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_max * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16",
+            "data": "synthetic",
+            "config": {"workload": f"config 4: dataset-scale normalization of {args.utts} variable-length utterances "
+                                   f"(lengths 200-2000, median 600), start_step {start}, length-bucketed batches of <= "
+                                   f"{args.max_tokens} padded frames, sharded by utterance over {world} GPU(s) (LPT plan), "
+                                   "valid frames counted", "utterances": args.utts, "valid_frames": int(valid),
+                       "padded_frames": int(padded), "batches_rank0": len(plan), "latent_dim": z, "start_step": start,
+                       "l2": "every batch's inputs and activations exceed the 126 MB L2", "sharding": "by utterance, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": valid / wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": fpf * valid / dev_max / 1e12 / world, "peak": peaks["sustained"],
+                         "unit": "TFLOP/s", "frac": fpf * valid / dev_max / 1e12 / world / peaks["sustained"], "traffic": None,
+                         "kernel": "whole pass, algorithmic FLOPs of the valid frames at the median length, per GPU"},
+            "padded_frames_per_s": padded / dev_max}))
+    D.close()
+
+
+def run_train(args):
+    """BASELINE config 5: denoiser training step (latent-noise MSE; frozen-VAE encode, forward with dropout, full backward
+    of the 260 M denoiser parameters) + the data-parallel gradient mean over NCCL / NVLink.  Per GPU: --batch x --frames
+    frames (default 12 x 1000 = scripts/diffusion/train.sh's --max-tokens 12000).  The optimizer is fairseq's."""
+    from diffnorm_b200 import _lib
+    from diffnorm_b200.dist import GradAllReducer
+    from diffnorm_b200.plugin import compat
+    from diffnorm_b200.train import DenoiserTrainer
+    D = _Dist()
+    dev, rank, world = D.dev, D.rank, D.world
+    z, B, T = args.latent_dim, args.batch, args.frames
+    torch.manual_seed(0)
+    ns = argparse.Namespace(task="speech_diffusion_discrete", arch="diff_discrete", target_is_code=True,
+                            target_code_size=1000, latent_dim=z, multitask=False)
+    ldm = compat.setup_task(ns).build_model(ns, from_checkpoint=True).to(dev).train().encoder
+    tr = DenoiserTrainer(ldm, drop_p=0.1, seed=rank)
+    g = torch.Generator().manual_seed(1234 + rank)
+    audio_h = torch.randn(B, T, 768, generator=g).pin_memory()
+    units_h = (torch.randint(0, 1000, (B, T), generator=g) + 4).pin_memory()
+    lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    audio, units = audio_h.to(dev), units_h.to(dev)
+    variants = [(args.grad_comm, True, args.sm_reserve)]
+    if args.comm_sweep and world > 1:
+        variants = [("fp32", True, 0), ("fp32", False, 0), ("fp32", True, 8), ("fp32", True, 16), ("fp32", True, 32),
+                    ("bf16", True, 0), ("bf16", True, 16), ("bf16", False, 0)]
+    for comm, overlap, reserve in variants:
+        red = GradAllReducer(comm_dtype=torch.bfloat16 if comm == "bf16" else torch.float32, overlap=overlap,
+                             sm_reserve=reserve if world > 1 else 0)
+
+        def step(a=audio, u=units):
+            out, _ = tr.step(a, u, lens, grad_hook=red.hook)
+            return out, red.finish()
+
+        for _ in range(max(args.warmup, 1)):
+            step()
+        D.barrier()
+        sampler = ClockSampler(D.local) if rank == 0 else None
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out, grads = step()
+        e1.record()
+        D.barrier()
+        launches = _lib.launch_count() - n0
+        ms = D.reduce(e0.elapsed_time(e1) / args.steps)
+        clocks = sampler.stop() if sampler else None
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):     # e2e: the batch comes from pinned host memory, the loss goes back
+            out, grads = step(audio_h.to(dev, non_blocking=True), units_h.to(dev, non_blocking=True))
+            loss = float(out["total_loss"])
+        D.barrier()
+        e2e_s = D.reduce((time.perf_counter() - t0) / args.steps)
+        if rank == 0:
+            nbytes = sum(v.numel() for v in grads.values()) * (2 if comm == "bf16" else 4)
+            print(json.dumps({
+                "metric": "training frames/sec", "value": B * T * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"config 5: denoiser training step, {B} x {T} frames per GPU, z {z}, dropout 0.1, forward + "
+                                       f"backward + gradient mean over {world} GPU(s) (NCCL all-reduce, {comm} on the wire, "
+                                       f"{'launched as buckets fill' if overlap else 'launched after backward'}, {reserve} SMs "
+                                       "left to NCCL)", "batch": B, "frames": T, "latent_dim": z, "grad_comm": comm,
+                           "overlap": overlap, "sm_reserve": reserve, "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")},
+                           "l2": "1 GB of gradients and > 4 GB of saved activations per step exceed the 126 MB L2"},
+                "clocks": clocks, "loss": loss, "grad_bytes_allreduced": nbytes,
+                "e2e": {"value": B * T * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": audio_h.numel() * 4 + units_h.numel() * 8,
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches)}), flush=True)
+    D.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -392,6 +580,13 @@ def main():
     ap.add_argument("--latent-dim", type=int, default=16)
     ap.add_argument("--start-step", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="pass", choices=["pass", "dataset", "train"],
+                    help="pass = BASELINE config 2 (the headline); dataset = config 4; train = config 5")
+    ap.add_argument("--utts", type=int, default=20000, help="--config dataset")
+    ap.add_argument("--max-tokens", type=int, default=64000, help="--config dataset: padded frames per batch")
+    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="--config train: gradient wire format")
+    ap.add_argument("--sm-reserve", type=int, default=16, help="--config train: SMs left to NCCL while buckets are in flight")
+    ap.add_argument("--comm-sweep", action="store_true", help="--config train: one line per exchange variant")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -401,7 +596,16 @@ def main():
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device for the product arm (there is no CPU fallback); "
                              "use --impl reference for the CPU baseline")
-        run_ours(args)
+        if args.config == "dataset":
+            if args.steps == 3 and args.warmup == 3:
+                args.steps = 1      # a step is a pass over the whole set
+            run_dataset(args)
+        elif args.config == "train":
+            if (args.batch, args.frames) == (64, 1000):
+                args.batch = 12     # scripts/diffusion/train.sh: --max-tokens 12000 per GPU
+            run_train(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdiffnorm_b200.so")
+LIB_PATH = os.environ.get("DN_LIB") or os.path.join(_HERE, "csrc", "libdiffnorm_b200.so")   # DN_LIB: A/B experiment builds
 
 
 class DiffNormLibraryError(RuntimeError):
@@ -87,6 +87,7 @@ ABI_VERSION = 2
 
 # name -> argtypes ; every function returns int status except the two info calls
 _SIGS = {
+    "dn_set_sm_limit": [i32],
     "dn_reduce_tgt": [vp, vp, i32, i32, vp, vp, vp, vp, vp],
     "dn_argmax_units": [vp, i32, i64, i32, i32, i32, vp, vp],
     "dn_unit_accuracy": [vp, vp, vp, i32, i32, vp, vp],

@@ -260,6 +260,14 @@ static int launch_attention(const void* qkv, void* out, const int32_t* lengths, 
 
 int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st,
                         float* lse2, const uint32_t* keep, float keep_scale, bool train, bool f16);
+int launch_attention_tc96(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st, float* lse2,
+                          const uint32_t* keep, float keep_scale, bool train, bool f16, int out_lo_col);
+
+// DN_ATTN_IMPL=mma selects the mma.sync kernels (bring-up / A-B reference of the tcgen05 kernels)
+static bool use_mma_attention() {
+    const char* e = getenv("DN_ATTN_IMPL");
+    return e && e[0] == 'm';
+}
 
 }  // namespace dn
 
@@ -269,12 +277,13 @@ extern "C" int dn_attention(const void* qkv, void* out, const int32_t* lengths, 
     if ((unsigned)fmt > 1u || (out_lo_col && dh != 96) || (fmt == DN_FMT_F16 && dh != 96 && dh != 64)) return DN_EINVAL;
     if (out_lo_col && (out_lo_col < H * dh || out_lo_col % 2)) return DN_EINVAL;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dh == 96 && !dn::use_mma_attention() && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+        return dn::launch_attention_tc96(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, false, fmt == DN_FMT_F16, out_lo_col);
     if (dh == 96 && fmt == DN_FMT_F16)
         return dn::launch_attention<96, true>(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, out_lo_col);
     if (dh == 64) {
-        // tcgen05/TMEM kernel (attention_tc.cu); DN_ATTN_IMPL=mma selects the mma.sync kernel (bring-up / A-B timing)
-        const char* e = getenv("DN_ATTN_IMPL");
-        const bool use_mma = e && e[0] == 'm';
+        // tcgen05/TMEM kernel (attention_tc.cu)
+        const bool use_mma = dn::use_mma_attention();
         if (!use_mma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
             return dn::launch_attention_tc(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, false, fmt == DN_FMT_F16);
         if (fmt == DN_FMT_F16) return DN_EINVAL;   // the mma.sync dh-64 kernel is the bf16 A/B reference only
@@ -289,9 +298,13 @@ extern "C" int dn_attention_train(const void* qkv, void* out, float* lse2, const
                                   float keep_scale, int32_t B, int32_t T, int32_t H, int32_t dh, void* stream) {
     if (!qkv || !out || !lse2 || B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535) return DN_EINVAL;
     if (reinterpret_cast<uintptr_t>(qkv) & 15) return DN_EINVAL;
-    if (dh == 96)   // VAE decoder: frozen / eval inside a diffusion step (no dropout), train mode in VAE training
-        return dn::launch_attention<96>(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
-                                        keep_scale);
+    if (dh == 96) {   // VAE decoder: frozen / eval inside a diffusion step (no dropout), train mode in VAE training
+        if (dn::use_mma_attention())
+            return dn::launch_attention<96>(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
+                                            keep_scale);
+        return dn::launch_attention_tc96(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
+                                         keep_scale, true, false, 0);
+    }
     if (dh != 64) return DN_EINVAL;
     return dn::launch_attention_tc(qkv, out, lengths, B, T, H, reinterpret_cast<cudaStream_t>(stream), lse2, keep_bits,
                                    keep_scale, true, false);

@@ -537,6 +537,7 @@ bool pdl_enabled() {
     return v == 1;
 }
 
+static int g_sm_limit = 0;   // dn_set_sm_limit: SMs the persistent kernels may occupy (0 = all)
 int num_sms() {
     static int n = 0;
     if (!n) {
@@ -545,7 +546,7 @@ int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 template <int EPI, int CTAS, int MODE>
@@ -645,4 +646,9 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
 }
 
 extern "C" int dn_abi_version(void) { return 2; }
+extern "C" int dn_set_sm_limit(int32_t n) {
+    if (n < 0 || (n & 1)) return DN_EINVAL;   // even: CTA pairs occupy two SMs
+    dn::g_sm_limit = n;
+    return 0;
+}
 extern "C" unsigned long long dn_launch_count(void) { return dn::g_launch_count; }

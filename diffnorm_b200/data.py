@@ -122,64 +122,104 @@ def plan_batches(lengths: Sequence[int], max_tokens: int, max_sentences: int = 0
 
 # ------------------------------------------------------------------------------------------------ runner
 class NormalizationRunner:
-    """Drives DiffNormEngine over lists of utterances (features + original unit strings) and returns TSV rows."""
+    """Drives DiffNormEngine over lists of utterances (features + original unit strings) and returns TSV rows.
+
+    A batch goes through three stages so that disk, host and device overlap (SURVEY §8f-1 "overlap I/O with compute"):
+      stage    host only: np.load, pack the feature rows and pad the unit rows into pinned buffers  (prefetch thread)
+      launch   enqueue H2D + reduce + gather + the whole pass; no host synchronisation when the reduced lengths are known
+               from the TSV (the padded length T then comes from the manifest, not from the device)
+      collect  ONE device-to-host read per batch (reduced units + both count vectors), the reference's length assert
+    `run_items` keeps one batch staged ahead and one launched ahead of the one being collected."""
 
     def __init__(self, engine, start_step: int = 50, max_tokens: int = 64000, max_sentences: int = 0, sampler: str = "ddim"):
         self.eng, self.start_step, self.max_tokens, self.max_sentences, self.sampler = engine, start_step, max_tokens, max_sentences, sampler
+
+    @staticmethod
+    def stage(feats: List[np.ndarray], full_units: List[np.ndarray]):
+        import torch
+        n_full = np.array([len(u) for u in full_units], dtype=np.int64)
+        for f, u in zip(feats, full_units):
+            if f.shape[0] != len(u):
+                raise ValueError(f"feature rows {f.shape[0]} != number of original units {len(u)}")
+        B, Tf = len(feats), int(n_full.max())
+        units_h = torch.zeros(B, Tf, dtype=torch.int64).pin_memory()
+        for i, u in enumerate(full_units):
+            units_h[i, : len(u)] = torch.from_numpy(np.asarray(u, dtype=np.int64))
+        packed_h = torch.from_numpy(np.concatenate([np.asarray(f, dtype=np.float32) for f in feats], axis=0)).pin_memory()
+        row0_h = torch.from_numpy(np.concatenate([[0], np.cumsum(n_full)[:-1]]).astype(np.int64)).pin_memory()
+        lens_h = torch.from_numpy(n_full.astype(np.int32)).pin_memory()
+        return dict(B=B, units=units_h, packed=packed_h, row0=row0_h, lens=lens_h)
+
+    def launch(self, st, expect_reduced: Optional[Sequence[int]] = None):
+        from . import ops
+        dev = self.eng.dev
+        units_d = st["units"].to(dev, non_blocking=True)
+        packed = st["packed"].to(dev, non_blocking=True)
+        lens_full = st["lens"].to(dev, non_blocking=True)
+        _, _, keep, counts = ops.reduce_tgt(units_d, lens_full)   # first reduce: index_to_keep of the ORIGINAL units (:150)
+        if expect_reduced is not None:
+            T = int(max(expect_reduced))                          # known from the TSV: nothing to wait for
+        else:
+            T = int(counts.max().item())
+        T = max(1, min(T, keep.shape[1]))
+        keep_t = keep[:, :T].contiguous()
+        feat = ops.gather_pack(packed, st["row0"].to(dev, non_blocking=True), keep_t, counts, T)  # [B,T,768], zero padded (:164-169)
+        out = self.eng.normalize(feat, counts, self.start_step, sampler=self.sampler)
+        return dict(B=st["B"], counts=counts, out=out, feat=feat, expect=None if expect_reduced is None else list(expect_reduced))
+
+    @staticmethod
+    def collect(h, return_units: bool = False):
+        import torch
+        out = h["out"]
+        counts_h, dedup, cnt2 = (t.to("cpu", non_blocking=True) for t in (h["counts"], out["dedup"], out["counts"]))
+        units = out["units"].to("cpu", non_blocking=True) if return_units else None
+        torch.cuda.synchronize()
+        counts_h, dedup, cnt2 = counts_h.numpy(), dedup.numpy(), cnt2.numpy()
+        if h["expect"] is not None and list(counts_h) != h["expect"]:   # the reference's assert (:152)
+            raise AssertionError("reduced length from the original units does not match reduce_tgt_n_frames")
+        res = [(dedup[i, : cnt2[i]].copy(), int(counts_h[i])) for i in range(h["B"])]
+        if return_units:
+            units = units.numpy()
+            return res, [units[i, : counts_h[i]].copy() for i in range(h["B"])], h["feat"].cpu()
+        return res
 
     def normalize_batch(self, feats: List[np.ndarray], full_units: List[np.ndarray], expect_reduced: Optional[List[int]] = None,
                         return_units: bool = False):
         """feats[i] fp32 [N_full_i, 768], full_units[i] int64 [N_full_i] -> per utterance (reduced units, n_frames)
         where n_frames = frames fed to the model = length BEFORE the second reduce (diff_norm_synthesis.py:211-222)."""
-        import torch
-
-        from . import ops
-        dev = self.eng.dev
-        B = len(feats)
-        n_full = np.array([len(u) for u in full_units], dtype=np.int64)
-        for f, u in zip(feats, full_units):
-            if f.shape[0] != len(u):
-                raise ValueError(f"feature rows {f.shape[0]} != number of original units {len(u)}")
-        Tf = int(n_full.max())
-        units_h = torch.zeros(B, Tf, dtype=torch.int64).pin_memory()
-        for i, u in enumerate(full_units):
-            units_h[i, : len(u)] = torch.from_numpy(np.asarray(u, dtype=np.int64))
-        packed_h = torch.from_numpy(np.concatenate([np.asarray(f, dtype=np.float32) for f in feats], axis=0)).pin_memory()
-        row0_h = torch.from_numpy(np.concatenate([[0], np.cumsum(n_full)[:-1]]).astype(np.int64))
-        units_d = units_h.to(dev, non_blocking=True)
-        packed = packed_h.to(dev, non_blocking=True)
-        lens_full = torch.from_numpy(n_full.astype(np.int32)).to(dev)
-        # first reduce: index_to_keep of the ORIGINAL units (:150)
-        _, _, keep, counts = ops.reduce_tgt(units_d, lens_full)
-        counts_h = counts.cpu().numpy()
-        if expect_reduced is not None and list(counts_h) != list(expect_reduced):  # the reference's assert (:152)
-            raise AssertionError("reduced length from the original units does not match reduce_tgt_n_frames")
-        T = int(counts_h.max())
-        keep_t = keep[:, :T].contiguous()
-        feat = ops.gather_pack(packed, row0_h.to(dev), keep_t, counts, T)  # [B, T, 768] fp32, zero padded (:164-169)
-        out = self.eng.normalize(feat, counts, self.start_step, sampler=self.sampler)
-        dedup = out["dedup"].cpu().numpy()
-        cnt2 = out["counts"].cpu().numpy()
-        res = [(dedup[i, : cnt2[i]].copy(), int(counts_h[i])) for i in range(B)]
-        if return_units:
-            units = out["units"].cpu().numpy()
-            return res, [units[i, : counts_h[i]].copy() for i in range(B)], feat.cpu()
-        return res
+        return self.collect(self.launch(self.stage(feats, full_units), expect_reduced), return_units)
 
     def run_items(self, items: List[UtteranceItem], rank: int = 0, world_size: int = 1, progress=None) -> Dict[int, str]:
         """Normalizes this rank's share of `items`; returns {item index: TSV line}."""
+        from concurrent.futures import ThreadPoolExecutor
         lengths = [it.reduce_tgt_n_frames for it in items]
         plan = plan_batches(lengths, self.max_tokens, self.max_sentences, world_size=world_size)[rank]
         lines: Dict[int, str] = {}
-        for idx in plan:
+
+        def load(idx):
             feats = [np.load(items[i].feature_file) for i in idx]
             units = [np.array([int(x) for x in items[i].tgt_unit.split(" ")], dtype=np.int64) for i in idx]
-            res = self.normalize_batch(feats, units, [items[i].reduce_tgt_n_frames for i in idx])
-            for i, (red, n_frames) in zip(idx, res):
+            return self.stage(feats, units)
+
+        def finish(idx, handle):
+            for i, (red, n_frames) in zip(idx, self.collect(handle)):
                 it = items[i]
                 lines[int(i)] = f"{it.audio_id}\t{it.src_audio}\t{it.src_n_frames}\t{' '.join(str(int(v)) for v in red)}\t{n_frames}"
             if progress is not None:
                 progress(len(idx))
+
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            staged = pool.submit(load, plan[0]) if plan else None
+            in_flight = None
+            for k, idx in enumerate(plan):
+                st = staged.result()
+                staged = pool.submit(load, plan[k + 1]) if k + 1 < len(plan) else None     # disk + pinning under the GPU's work
+                handle = self.launch(st, [items[i].reduce_tgt_n_frames for i in idx])
+                if in_flight is not None:
+                    finish(*in_flight)                                                       # batch k-1, while batch k runs
+                in_flight = (idx, handle)
+            if in_flight is not None:
+                finish(*in_flight)
         return lines
 
 

@@ -31,6 +31,11 @@ def _chk(t: torch.Tensor, dtype, name: str):
     return t
 
 
+def set_sm_limit(n: int):
+    """Cap the persistent kernels' grids at n SMs (0 = all): leaves SMs to a concurrent NCCL collective."""
+    check(lib.dn_set_sm_limit(int(n)), "dn_set_sm_limit")
+
+
 # ------------------------------------------------------------------------------------------------ integer ops
 def reduce_tgt(units: torch.Tensor, lengths: torch.Tensor):
     """Batched run-length reduction.  units [B,T] int64, lengths [B] int32 ->

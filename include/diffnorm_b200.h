@@ -26,6 +26,11 @@ extern "C" {
 /* ---- library info ------------------------------------------------------------------------------------ */
 int dn_abi_version(void);                 /* = 2 */
 unsigned long long dn_launch_count(void); /* kernels launched by this library so far (bench.py gpu_launches) */
+/* The persistent kernels (dn_gemm, dn_wgrad) size their grids to the SM count and stride tiles statically over their CTAs:
+ * a concurrent kernel that takes SMs away (NCCL's all-reduce of the gradient buckets during the training step's backward)
+ * delays whole CTAs and with them the launch.  n > 0 (even) caps the grids at n SMs so that the rest stays free for the
+ * collective; 0 restores all SMs.  Process-wide; takes effect for launches enqueued afterwards. */
+int dn_set_sm_limit(int32_t n);
 
 /* ---- integer kernels --------------------------------------------------------------------------------- */
 

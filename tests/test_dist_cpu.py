@@ -11,17 +11,21 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from diffnorm_b200.dist import GradAllReducer
-    red = GradAllReducer(bucket_bytes=4 * 100)   # 100 floats per bucket -> several buckets, one oversize tensor
     ok = True
-    for step in range(2):                        # buckets are persistent across steps
-        shapes = [(7, 5), (64,), (3, 4, 3), (250,), (1,), (30, 3)]
-        grads = {f"p{i}": torch.full(s, float((rank + 1) * (i + 1) + step)) for i, s in enumerate(shapes)}
-        for k, v in grads.items():
-            red.hook(k, v)
-        out = red.finish()
-        for i, s in enumerate(shapes):
-            want = sum((r + 1) * (i + 1) + step for r in range(world)) / world
-            ok &= out[f"p{i}"].shape == torch.Size(s) and bool(torch.allclose(out[f"p{i}"], torch.full(s, want)))
+    # fp32 wire format (DDP's arithmetic), launched as buckets fill or all at the end; bf16 wire format (values here are
+    # small integers and halves: exact in bf16)
+    for kw in (dict(), dict(overlap=False), dict(comm_dtype=torch.bfloat16)):
+        red = GradAllReducer(bucket_bytes=4 * 100, **kw)   # ~100 floats per bucket -> several buckets, one oversize tensor
+        for step in range(2):                        # buckets are persistent across steps
+            shapes = [(7, 5), (64,), (3, 4, 3), (250,), (1,), (30, 3)]
+            grads = {f"p{i}": torch.full(s, float((rank + 1) * (i + 1) + step)) for i, s in enumerate(shapes)}
+            for k, v in grads.items():
+                red.hook(k, v)
+            out = red.finish()
+            for i, s in enumerate(shapes):
+                want = sum((r + 1) * (i + 1) + step for r in range(world)) / world
+                ok &= out[f"p{i}"].shape == torch.Size(s) and out[f"p{i}"].dtype == torch.float32
+                ok &= bool(torch.allclose(out[f"p{i}"], torch.full(s, want)))
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -235,6 +235,38 @@ def test_attention_tcgen05_matches_mma_kernel():
     torch.testing.assert_close(outs[1], outs[0], rtol=2e-2, atol=2e-2)
 
 
+def test_attention_dh96_tcgen05_matches_mma_kernel():
+    """dh = 96 (VAE decoder) runs on the tcgen05/TMEM kernel of attention_tc96.cu (two 64-column boxes per operand);
+    DN_ATTN_IMPL=mma selects the mma.sync kernel: forward (bf16) and the training form (dropout bits + row statistic)."""
+    B, T, H, dh = 3, 700, 8, 96
+    qkv = rnd(B, T, 3 * H * dh, seed=24, scale=1.2).bfloat16()
+    lengths = torch.tensor([700, 129, 1], dtype=torch.int32, device=DEV)
+    keep = torch.empty(B, H, T, (T + 31) // 32, dtype=torch.int32, device=DEV)
+    ops.dropout_bits(keep, 0.1, 7, 0)
+    res = {}
+    for impl in ("mma", "tc"):
+        os.environ["DN_ATTN_IMPL"] = impl
+        out = torch.full((B, T, H * dh), 9.0, dtype=torch.bfloat16, device=DEV)
+        ops.attention(qkv, out, lengths, B, T, H, dh)
+        out_t = torch.full((B, T, H * dh), 9.0, dtype=torch.bfloat16, device=DEV)
+        lse = torch.zeros(B * H, T, device=DEV)
+        ops.attention_train(qkv, out_t, lse, lengths, keep, 1.0 / 0.9, B, T, H, dh)
+        torch.cuda.synchronize()
+        res[impl] = (out.float(), out_t.float(), lse.clone())
+    os.environ.pop("DN_ATTN_IMPL")
+    mask = (torch.arange(T, device=DEV)[None] < lengths[:, None])
+    torch.testing.assert_close(res["tc"][0], res["mma"][0], rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(res["tc"][1], res["mma"][1], rtol=2e-2, atol=3e-2)
+    lm = mask[:, None, :].expand(B, H, T).reshape(B * H, T)
+    torch.testing.assert_close(res["tc"][2][lm], res["mma"][2][lm], rtol=1e-3, atol=2e-3)
+    # and against the plain statement of the op
+    q, k, v = (t.float().view(B, T, H, dh).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+    sim = torch.einsum("bhid,bhjd->bhij", q, k) * dh ** -0.5
+    sim = sim.masked_fill(~mask[:, None, None, :], -torch.finfo(torch.float32).max)
+    want = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), v).transpose(1, 2).reshape(B, T, H * dh)
+    torch.testing.assert_close(res["tc"][0], want, rtol=2e-2, atol=2e-2)
+
+
 # --------------------------------------------------------------------------------------------------- GEMM
 def _gemm_case(plan, A, out_shape, out_dtype, B, T, **kw):
     outs = []
