@@ -44,7 +44,12 @@ __device__ __forceinline__ uint32_t ta_idesc(uint32_t n, uint32_t b_mn_major, bo
 // TRAIN: additionally applies the attention-dropout keep bits (LM:338; keep [B,H,T,ceil(T/32)] words, bit k%32 of word
 // k/32 = key k kept; P is scaled by keep_scale = 1/(1-p) after the row sum) and saves L2 = m + log2(l) per query row.
 // F16: q, k, v, the probabilities P and the output are fp16 instead of bf16 (the sampler loop's format).
-template <bool TRAIN, bool F16>
+// OPT: key blocks after the first exponentiate OPTIMISTICALLY against the running max they already have, while the second
+// half of S is still on its way from TMEM and before the two threads of a row have exchanged their maxima; the block is
+// redone from the registers in the rare case that its true max exceeds the running one by more than 2^8 (the same lazy
+// threshold the un-optimistic path applies before it raises the max).  The dependent chain of a block shrinks from
+// LDTM -> max -> barrier -> exp2 -> STTM to LDTM/exp2 overlapped -> barrier -> STTM.
+template <bool TRAIN, bool F16, bool OPT>
 __global__ void __launch_bounds__(TA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
                     const int* __restrict__ lengths, int T, int H, float scale_log2, float* __restrict__ lse2,
@@ -266,9 +271,100 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
             tc_fence_before();          // TMEM reads / writes ordered before the MMA that follows the barrier
             mbar_arrive(p_full);
         };
+        // optimistic form of `block` for j >= 1 (m is finite): same outputs unless the rare redo path runs
+        auto block_opt = [&](const int j, auto masked_tag) {
+            constexpr bool masked = decltype(masked_tag)::value;
+            float s0[32], s1[32];
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            tmem_ld32(tS + lane_off + half * 64, s0);
+            tmem_ld_wait();
+            tmem_ld32(tS + lane_off + half * 64 + 32, s1);   // in flight under the first half's exponentials
+            const int kbase = j * TA_BN + half * 64;
+            uint64_t nm2 = pack2(-m, -m);
+            uint64_t rs2[2] = {0ull, 0ull};
+            float mx[2] = {-INFINITY, -INFINITY};
+            auto half_row = [&](float (&s)[32], uint32_t (&w)[16], const int k0, const bool with_max) {
+                if constexpr (masked) {
+                    if (with_max) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) s[i] = (k0 + i < len) ? s[i] : -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float e0, e1;
+                    if (with_max) mx[(i >> 1) & 1] = max3(mx[(i >> 1) & 1], s[i], s[i + 1]);
+                    unpack2(ffma2(pack2(s[i], s[i + 1]), scale2, nm2), e0, e1);
+                    e0 = ex2_approx(e0);   // masked keys: ex2(-inf) = +0
+                    e1 = ex2_approx(e1);
+                    rs2[(i >> 1) & 1] = fadd2(rs2[(i >> 1) & 1], pack2(e0, e1));
+                    w[i >> 1] = pack16<F16>(e0, e1);
+                }
+            };
+            // P goes to TMEM half by half as soon as it exists (its columns are free once PV_{j-1} has completed, which it
+            // has long before the first 32 exponentials are done), so only S stays in registers for the redo path
+            uint32_t w[16];
+            half_row(s0, w, kbase, true);
+            mbar_wait(p_empty, (j - 1) & 1);              // PV_{j-1} done: P columns free, O stable
+            tc_fence_after();
+            tmem_st16(tP + lane_off + half * 32, w);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+            half_row(s1, w, kbase + 32, true);
+            tmem_st16(tP + lane_off + half * 32 + 16, w);
+            float mxx = fmaxf(mx[0], mx[1]);
+            xmax[((j & 1) * 2 + half) * TA_BM + row] = mxx;
+            named_bar_sync(1, 256);
+            mxx = fmaxf(mxx, xmax[((j & 1) * 2 + (half ^ 1)) * TA_BM + row]);
+            const float mxs = mxx * scale_log2;
+            const bool raise = mxs > m + RESCALE_LOG2;
+            if (__any_sync(0xffffffffu, raise)) {         // rare: the optimistic exponentials used a stale max
+                // the whole warp redoes the block (tcgen05.st / wait are warp-collective); lanes that did not raise
+                // recompute the values they already had
+                const float m_old = m;
+                if (raise) {
+                    l *= ex2_approx(m - mxs);
+                    m = mxs;
+                }
+                nm2 = pack2(-m, -m);
+                rs2[0] = rs2[1] = 0ull;
+                tmem_st_wait();
+                half_row(s0, w, kbase, false);
+                tmem_st16(tP + lane_off + half * 32, w);
+                half_row(s1, w, kbase + 32, false);
+                tmem_st16(tP + lane_off + half * 32 + 16, w);
+                const float a = raise ? ex2_approx(m_old - m) : 1.f;
+#pragma unroll 1
+                for (int c8 = 0; c8 < 32; c8 += 8) {
+                    float o[8];
+                    tmem_ld8(tO + lane_off + half * 32 + c8, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] *= a;
+                    tmem_st8(tO + lane_off + half * 32 + c8, o);
+                }
+            }
+            float r0, r1, r2, r3;
+            unpack2(rs2[0], r0, r1);
+            unpack2(rs2[1], r2, r3);
+            l += (r0 + r1) + (r2 + r3);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        };
         const int n_full = len / TA_BN;  // key blocks without any masked key
-        for (int j = 0; j < n_full; ++j) block(j, FalseTag{});
-        if (n_full < nkb) block(n_full, TrueTag{});
+        if constexpr (OPT && !TRAIN) {
+            if (nkb > 0) {
+                if (n_full > 0) block(0, FalseTag{}); else block(0, TrueTag{});   // j = 0 has no running max yet
+                for (int j = 1; j < n_full; ++j) block_opt(j, FalseTag{});
+                if (n_full < nkb && n_full > 0) block_opt(n_full, TrueTag{});
+            }
+        } else {
+            for (int j = 0; j < n_full; ++j) block(j, FalseTag{});
+            if (n_full < nkb) block(n_full, TrueTag{});
+        }
         // combine the two partial row sums, normalise, store my 32 output columns
         lsum[half * TA_BM + row] = l;
         named_bar_sync(2, 256);
@@ -309,10 +405,17 @@ int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int 
                         float* lse2, const uint32_t* keep, float keep_scale, bool train, bool f16) {
     static bool attr_set = false;
     if (!attr_set) {
-        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        DN_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         attr_set = true;
+    }
+    static int opt = -1;       // DN_ATTN_OPT=0: the max-first softmax for every key block (A/B switch)
+    if (opt < 0) {
+        const char* e = getenv("DN_ATTN_OPT");
+        opt = (e && e[0] == '0') ? 0 : 1;
     }
     if (train && f16) return DN_EINVAL;
     CUtensorMap m;
@@ -324,15 +427,15 @@ int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int 
     if (r) return r;
     dim3 grid((T + TA_BM - 1) / TA_BM, H, B);
     const float scale_log2 = (1.0f / sqrtf((float)TA_DH)) * 1.4426950408889634f;
-    if (train)
-        DN_CUDA_OK(launch_ex(attention_tc_kernel<true, false>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
-                             lengths, T, H, scale_log2, lse2, keep, keep_scale));
-    else if (f16)
-        DN_CUDA_OK(launch_ex(attention_tc_kernel<false, true>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
-                             lengths, T, H, scale_log2, (float*)nullptr, (const uint32_t*)nullptr, 1.f));
-    else
-        DN_CUDA_OK(launch_ex(attention_tc_kernel<false, false>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out),
-                             lengths, T, H, scale_log2, (float*)nullptr, (const uint32_t*)nullptr, 1.f));
+#define DN_ATT_LAUNCH(TR, FH, OP, L2, KP, KS)                                                                                 \
+    DN_CUDA_OK(launch_ex(attention_tc_kernel<TR, FH, OP>, grid, TA_THREADS, TA_SMEM, st, 1, m, reinterpret_cast<__nv_bfloat16*>(out), \
+                         lengths, T, H, scale_log2, L2, KP, KS))
+    if (train) DN_ATT_LAUNCH(true, false, false, lse2, keep, keep_scale);
+    else if (f16 && opt) DN_ATT_LAUNCH(false, true, true, (float*)nullptr, (const uint32_t*)nullptr, 1.f);
+    else if (f16) DN_ATT_LAUNCH(false, true, false, (float*)nullptr, (const uint32_t*)nullptr, 1.f);
+    else if (opt) DN_ATT_LAUNCH(false, false, true, (float*)nullptr, (const uint32_t*)nullptr, 1.f);
+    else DN_ATT_LAUNCH(false, false, false, (float*)nullptr, (const uint32_t*)nullptr, 1.f);
+#undef DN_ATT_LAUNCH
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

@@ -436,7 +436,9 @@ class DenoiserTrainer:
         self.drop_p, self.seed, self.step_no = drop_p, seed, 0
         from .engine import DiffNormEngine
         sd = {k: v for k, v in ldm.state_dict().items()}
-        self.vae = DiffNormEngine(sd, device=str(self.dev), cfg=self.cfg, vae_only=True)   # frozen VAE
+        # frozen VAE encoder of the training step: bf16 operands (the latent is about to be noised at sigma >= 0.016; the
+        # split-precision encode of the normalization pass costs 3x here for nothing — 35.0 vs 29.5 ms per step)
+        self.vae = DiffNormEngine(sd, device=str(self.dev), cfg=self.cfg, vae_only=True, vae_fmt="bf16")
         c = self.cfg
         s = DDPMScheduler(c.timesteps)
         self.sched = s

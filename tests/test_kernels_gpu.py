@@ -235,6 +235,32 @@ def test_attention_tcgen05_matches_mma_kernel():
     torch.testing.assert_close(outs[1], outs[0], rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_attention_optimistic_softmax_redo_path(dt):
+    """Key blocks after the first exponentiate against the running max before the block's own max is known
+    (attention_tc.cu OPT); a block whose max exceeds it by more than 2^8 is redone.  Scores that climb steeply from key
+    block to key block force that path in every block; scores that fall never take it."""
+    B, T, H, dh = 2, 640, 8, 64
+    g = torch.Generator().manual_seed(5)
+    for direction in (+1.0, -1.0):
+        q = torch.randn(B, T, H * dh, generator=g) * 0.3 + 1.0
+        ramp = (torch.arange(T) // 128).float()[None, :, None] * direction          # grows by one unit per key block
+        k = torch.randn(B, T, H * dh, generator=g) * 0.3 + 0.9 * ramp              # s*scale*log2(e) moves ~10 per key block
+        v = torch.randn(B, T, H * dh, generator=g)
+        qkv = torch.cat([q, k, v], -1).to(DEV).to(dt).contiguous()
+        lengths = torch.tensor([640, 389], dtype=torch.int32, device=DEV)
+        out = torch.empty(B, T, H * dh, dtype=dt, device=DEV)
+        ops.attention(qkv, out, lengths, B, T, H, dh)
+        qq, kk, vv = (t.float().view(B, T, H, dh).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+        sim = torch.einsum("bhid,bhjd->bhij", qq, kk) * dh ** -0.5
+        mask = torch.arange(T, device=DEV)[None] < lengths[:, None]
+        sim = sim.masked_fill(~mask[:, None, None, :], -torch.finfo(torch.float32).max)
+        jump = (sim[0, 0, 0, 128:256].max() - sim[0, 0, 0, :128].max()) * 1.4427
+        assert direction * float(jump) > 8.0                                       # the redo threshold really is crossed
+        want = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), vv).transpose(1, 2).reshape(B, T, H * dh)
+        torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
+
+
 def test_attention_dh96_tcgen05_matches_mma_kernel():
     """dh = 96 (VAE decoder) runs on the tcgen05/TMEM kernel of attention_tc96.cu (two 64-column boxes per operand);
     DN_ATTN_IMPL=mma selects the mma.sync kernel: forward (bf16) and the training form (dropout bits + row statistic)."""

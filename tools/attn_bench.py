@@ -9,8 +9,9 @@ import torch  # noqa: E402
 from diffnorm_b200 import ops  # noqa: E402
 
 B, T, H, dh = int(os.environ.get("B", 64)), int(os.environ.get("T", 1000)), 8, int(os.environ.get("DH", 64))
-qkvs = [torch.randn(B * T, 3 * H * dh, device="cuda").to(torch.bfloat16) for _ in range(3)]
-out = torch.empty(B * T, H * dh, dtype=torch.bfloat16, device="cuda")
+DT = torch.float16 if os.environ.get("F16", "1") == "1" else torch.bfloat16
+qkvs = [torch.randn(B * T, 3 * H * dh, device="cuda").to(DT) for _ in range(3)]
+out = torch.empty(B * T, H * dh, dtype=DT, device="cuda")
 lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
 for q in qkvs:
     ops.attention(q, out, lens, B, T, H, dh)
@@ -24,7 +25,7 @@ e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / n * 1e3
 fl = 4.0 * B * H * T * T * dh
-print(f"attention B={B} T={T} H={H} dh={dh} stagger={os.environ.get('DN_ATTN_STAGGER')}: {us:.1f} us  {fl / us / 1e6:.0f} TFLOP/s")
+print(f"attention B={B} T={T} H={H} dh={dh} opt={os.environ.get("DN_ATTN_OPT", "1")} {DT}: {us:.1f} us  {fl / us / 1e6:.0f} TFLOP/s")
 
 if os.environ.get("BWD"):
     lse = torch.empty(B * H, T, device="cuda")
