@@ -49,6 +49,7 @@ class GemmDesc(C.Structure):
         ("out", vp), ("ldo", i32), ("out_batch_stride", i64), ("g_out_col", i32),
         ("pe", vp), ("lengths", vp),
         ("a_fmt", i32), ("w_fmt", i32), ("out_fmt", i32), ("out_lo_col", i32),
+        ("coef", vp), ("aux", vp), ("aux_ld", i32), ("aux_lo_col", i32), ("n_classes", i32),
     ]
 
 
@@ -80,7 +81,7 @@ class ResidNormDesc(C.Structure):
     ]
 
 
-EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_WN_GATE = range(5)
+EPI_BF16, EPI_F32, EPI_RESID, EPI_GEGLU, EPI_WN_GATE, EPI_DDIM, EPI_ARGMAX = range(7)
 GEMM_TCGEN05, GEMM_SIMT_CHECK, GEMM_TCGEN05_2CTA = 0, 1, 2
 FMT_BF16, FMT_F16 = 0, 1
 ABI_VERSION = 2
@@ -90,6 +91,7 @@ _SIGS = {
     "dn_set_sm_limit": [i32],
     "dn_reduce_tgt": [vp, vp, i32, i32, vp, vp, vp, vp, vp],
     "dn_argmax_units": [vp, i32, i64, i32, i32, i32, vp, vp],
+    "dn_argmax_combine": [vp, i64, i32, i32, vp, vp],
     "dn_unit_accuracy": [vp, vp, vp, i32, i32, vp, vp],
     "dn_gather_pack": [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp],
     "dn_cast_pad_bf16": [vp, i64, i32, i32, vp, i32, vp],
@@ -106,6 +108,12 @@ _SIGS = {
     "dn_time_features": [vp, vp, i32, i32, vp, vp],
     "dn_gemm": [C.POINTER(GemmDesc), i32, vp],
     "dn_attention": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    # unit vocoder (the step after the pass)
+    "dn_voc_conv1d": [vp, i32, i32, vp, vp, i32, i32, i32, i32, f32, i32, vp, f32, i32, vp, vp],
+    "dn_voc_conv_transpose1d": [vp, i32, i32, vp, vp, i32, i32, i32, i32, f32, vp, vp],
+    "dn_voc_layernorm": [vp, i32, i32, vp, vp, vp, vp],
+    "dn_voc_durations": [vp, i32, vp, vp, vp],
+    "dn_voc_embed_repeat": [vp, i32, vp, i32, vp, i32, vp, vp],
     # training step
     "dn_wgrad": [C.POINTER(WgradDesc), vp],
     "dn_gemm_resid_norm": [C.POINTER(ResidNormDesc), vp],

@@ -234,7 +234,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
             const int ocol0 = c.g * p.g_out_col;
 
-            if constexpr (EPI == DN_EPI_BF16 || EPI == DN_EPI_F32 || EPI == DN_EPI_RESID) {
+            if constexpr (EPI == DN_EPI_DDIM) {
+                // eps_hat stays in registers: x <- sqrt(ab_prev) x0 + sqrt(1 - ab_prev) eps~ with x0, eps~ re-derived from x and
+                // eps_hat exactly as the reference does (safe_div clamps 1e-10), then the fp32 state and its split-precision
+                // staging copy are written straight from the thread that owns the row (rows are contiguous: coalesced)
+                if (half == 0) {   // warp-uniform: tcgen05.ld is warp-collective, rows past T only skip the global accesses
+                    const float* cf = p.coef + (long long)(p.t_idx ? p.t_idx[0] : 0) * 8;
+                    const float c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3];
+                    const float d0 = fmaxf(c0, 1e-10f), d1 = fmaxf(c1, 1e-10f);
+                    const long long r = (long long)c.b * p.T + (t < p.T ? t : 0);
+                    float* xr = reinterpret_cast<float*>(p.out) + r * p.ldo;
+                    __nv_bfloat16* sr = reinterpret_cast<__nv_bfloat16*>(p.aux) + r * p.aux_ld;
+                    for (int cc = 0; cc < p.n_out; cc += 16) {
+                        float e[16];
+                        tmem_ld16(taddr + cc, e);
+                        tmem_ld_wait();
+                        if (t >= p.T) continue;
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 xv = *reinterpret_cast<const float4*>(xr + cc + i);
+                            const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + cc + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, bs[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                            for (int q2 = 0; q2 < 4; ++q2) {
+                                const float eh = e[i + q2] + bs[q2];
+                                const float x0 = (xs[q2] - c1 * eh) / d0;
+                                const float pn = (xs[q2] - c0 * x0) / d1;
+                                v[i + q2] = x0 * c2 + c3 * pn;
+                            }
+                            *reinterpret_cast<float4*>(xr + cc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 8) {
+                            uint32_t hh[4], ll[4];
+#pragma unroll
+                            for (int q2 = 0; q2 < 4; ++q2) split_bf16(v[i + 2 * q2], v[i + 2 * q2 + 1], hh[q2], ll[q2]);
+                            *reinterpret_cast<uint4*>(sr + cc + i) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                            if (p.aux_lo_col) *reinterpret_cast<uint4*>(sr + p.aux_lo_col + cc + i) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                        }
+                    }
+                }
+            } else if constexpr (EPI == DN_EPI_ARGMAX) {
+                // this warpgroup's 128 accumulator columns of the row -> one (max, first index) partial; NaN is greatest and
+                // the first occurrence wins (torch.argmax); columns are scanned in ascending order so a strict > keeps it
+                const int c0 = c.n * WT + half * 128;
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int sub = 0; sub < 4; ++sub) {
+                    const int cs = c0 + sub * 32;
+                    if (cs >= p.n_classes) break;
+                    float v[32];
+                    tmem_ld32(taddr + half * 128 + sub * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int cc = cs + i;
+                        if (cc < p.n_classes) {
+                            const float x = v[i] + (p.bias ? __ldg(p.bias + cc) : 0.f);
+                            const bool xn = x != x, bn = bv != bv;
+                            if (bi == 0x7fffffff || (xn && !bn) || (!bn && x > bv)) { bv = x; bi = cc; }
+                        }
+                    }
+                }
+                if (t < p.T) {
+                    float* o = reinterpret_cast<float*>(p.out) + ((long long)c.b * p.T + t) * p.ldo + (c.n * 2 + half) * 2;
+                    *reinterpret_cast<float2*>(o) = make_float2(bv, __int_as_float(bi));
+                }
+            } else if constexpr (EPI == DN_EPI_BF16 || EPI == DN_EPI_F32 || EPI == DN_EPI_RESID) {
                 constexpr int UCOLS = (EPI == DN_EPI_BF16) ? 64 : 32;   // columns per 16 KB unit
                 const float* bias = p.bias ? p.bias + c.g * p.g_bias : nullptr;
                 long long pe_row = -1;
@@ -469,6 +536,42 @@ __global__ void gemm_check_kernel(const dn_gemm_desc p) {
                 v += p.pe[(long long)pos * p.n_out + oc];
             }
             reinterpret_cast<float*>(p.out)[o] = v;
+        } else if (p.epi == DN_EPI_ARGMAX) {
+            // slow but simple: every class writes through a per-row scan done by the thread of class 0 of each 128-column part
+            if (oc % 128 == 0 && oc < p.n_classes) {
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int cc = oc; cc < oc + 128 && cc < p.n_classes; ++cc) {
+                    float acc = 0.f;
+                    for (int s2 = 0; s2 < p.num_segs; ++s2) {
+                        const dn_gemm_seg sg = p.seg[s2];
+                        const int ts = t - sg.shift_mul * d;
+                        if (ts < 0 || ts >= p.T) continue;
+                        const uint16_t* a = A + (long long)b * p.a_batch_stride + (long long)ts * p.lda + sg.a_col0;
+                        const uint16_t* w = W + (long long)cc * p.ldw + sg.w_k0;
+                        for (int k = 0; k < sg.k_blocks * BK; ++k)
+                            acc += ((sg.a_col0 + k < p.a_cols) ? load16(a[k], p.a_fmt) : 0.f) * load16(w[k], p.w_fmt);
+                    }
+                    const float x = acc + (p.bias ? p.bias[cc] : 0.f);
+                    const bool xn = x != x, bn = bv != bv;
+                    if (bi == 0x7fffffff || (xn && !bn) || (!bn && x > bv)) { bv = x; bi = cc; }
+                }
+                float* po = reinterpret_cast<float*>(p.out) + ((long long)b * p.T + t) * p.ldo + (oc / 128) * 2;
+                po[0] = bv;
+                po[1] = __int_as_float(bi);
+            }
+        } else if (p.epi == DN_EPI_DDIM) {
+            const float* cf = p.coef + (long long)(p.t_idx ? p.t_idx[0] : 0) * 8;
+            const float eh = lo + (p.bias ? p.bias[oc] : 0.f);
+            const float xv = reinterpret_cast<float*>(p.out)[o];
+            const float x0 = (xv - cf[1] * eh) / fmaxf(cf[0], 1e-10f);
+            const float pn = (xv - cf[0] * x0) / fmaxf(cf[1], 1e-10f);
+            const float v = x0 * cf[2] + cf[3] * pn;
+            reinterpret_cast<float*>(p.out)[o] = v;
+            const long long so = ((long long)b * p.T + t) * p.aux_ld + oc;
+            const __nv_bfloat16 h = __float2bfloat16(v);
+            reinterpret_cast<__nv_bfloat16*>(p.aux)[so] = h;
+            if (p.aux_lo_col) reinterpret_cast<__nv_bfloat16*>(p.aux)[so + p.aux_lo_col] = __float2bfloat16(v - __bfloat162float(h));
         } else if (p.epi == DN_EPI_RESID) {
             reinterpret_cast<float*>(p.out)[o] += lo + (p.bias ? p.bias[g * p.g_bias + oc] : 0.f);
         } else if (p.epi == DN_EPI_GEGLU) {
@@ -578,8 +681,15 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
     if (d.n_out % 8 || d.lda % 8 || d.ldw % 8 || d.w_rows % 16) return DN_EINVAL;
     if ((reinterpret_cast<uintptr_t>(d.A) | reinterpret_cast<uintptr_t>(d.W) | reinterpret_cast<uintptr_t>(d.out)) & 15)
         return DN_EINVAL;
-    const bool f32out = d.epi == DN_EPI_F32 || d.epi == DN_EPI_RESID;
+    const bool f32out = d.epi == DN_EPI_F32 || d.epi == DN_EPI_RESID || d.epi == DN_EPI_DDIM || d.epi == DN_EPI_ARGMAX;
+    if (d.epi == DN_EPI_ARGMAX && (d.groups != 1 || d.n_classes <= 0 || d.n_classes > d.n_out || d.ldo < 4 * d.n_tiles || d.ldo % 2 ||
+                                   d.out_batch_stride != (long long)d.T * d.ldo))
+        return DN_EINVAL;
     if (d.ldo % (f32out ? 4 : 8) || d.g_out_col % 8) return DN_EINVAL;
+    if (d.epi == DN_EPI_DDIM && (!d.coef || !d.aux || !d.t_idx || d.groups != 1 || d.n_tiles != 1 || d.n_out % 16 || d.n_out > 256 ||
+                                 d.aux_ld % 8 || d.aux_lo_col % 8 || d.out_batch_stride != (long long)d.T * d.ldo ||
+                                 ((reinterpret_cast<uintptr_t>(d.aux) | reinterpret_cast<uintptr_t>(d.bias)) & 15)))
+        return DN_EINVAL;
     if ((unsigned)d.a_fmt > 1u || (unsigned)d.w_fmt > 1u || (unsigned)d.out_fmt > 1u || d.out_lo_col < 0) return DN_EINVAL;
     if (d.out_lo_col && (f32out || d.n_out % 64 || d.out_lo_col % 8 || d.out_fmt != DN_FMT_BF16)) return DN_EINVAL;
     if (d.out_fmt == DN_FMT_F16 && f32out) return DN_EINVAL;
@@ -639,6 +749,8 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
         case DN_EPI_BF16: return mode == 1 ? DN_BY_CTAS(DN_EPI_BF16, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_BF16, 2) : DN_BY_CTAS(DN_EPI_BF16, 0);
         case DN_EPI_F32: return DN_BY_CTAS(DN_EPI_F32, 0);
         case DN_EPI_RESID: return DN_BY_CTAS(DN_EPI_RESID, 0);
+        case DN_EPI_DDIM: return DN_BY_CTAS(DN_EPI_DDIM, 0);
+        case DN_EPI_ARGMAX: return DN_BY_CTAS(DN_EPI_ARGMAX, 0);
         case DN_EPI_GEGLU: return mode == 1 ? DN_BY_CTAS(DN_EPI_GEGLU, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_GEGLU, 2) : DN_BY_CTAS(DN_EPI_GEGLU, 0);
         case DN_EPI_WN_GATE: return mode == 1 ? DN_BY_CTAS(DN_EPI_WN_GATE, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_WN_GATE, 2) : DN_BY_CTAS(DN_EPI_WN_GATE, 0);
         default: return DN_EINVAL;

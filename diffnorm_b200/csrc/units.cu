@@ -75,6 +75,22 @@ argmax_units_kernel(const void* __restrict__ logits, long long rows, int C, int 
     }
 }
 
+// second stage of the GEMM's argmax epilogue (DN_EPI_ARGMAX): fold a row's (value, index) partials
+__global__ void argmax_combine_kernel(const float* __restrict__ partials, long long rows, int parts, int offset,
+                                      long long* __restrict__ units) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        const float2* p = reinterpret_cast<const float2*>(partials) + r * parts;
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int k = 0; k < parts; ++k) {
+            const float2 q = p[k];
+            const int qi = __float_as_int(q.y);
+            if (qi != 0x7fffffff && better(q.x, qi, bv, bi)) { bv = q.x; bi = qi; }
+        }
+        units[r] = (long long)bi - offset;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ run-length reduce
 constexpr int RL_THREADS = 256;
 __global__ void __launch_bounds__(RL_THREADS)
@@ -180,6 +196,17 @@ extern "C" int dn_reduce_tgt(const int64_t* units, const int32_t* lengths, int32
     reduce_tgt_kernel<<<B, RL_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const long long*>(units), lengths, T, reinterpret_cast<long long*>(dedup),
         reinterpret_cast<long long*>(duration), reinterpret_cast<long long*>(index_to_keep), counts);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_argmax_combine(const float* partials, int64_t rows, int32_t parts, int32_t offset, int64_t* units,
+                                 void* stream) {
+    if (!partials || !units || rows <= 0 || parts <= 0 || (reinterpret_cast<uintptr_t>(partials) & 7)) return DN_EINVAL;
+    const long long blocks = (rows + 255) / 256;
+    argmax_combine_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        partials, rows, parts, offset, reinterpret_cast<long long*>(units));
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

@@ -78,6 +78,8 @@ class DiffNormEngine:
             raise ValueError("wfmt must be bf16 | f16 and vae_fmt bf16 | split")
         self.vsplit = self.vae_fmt == "split"
         self.adt = torch.float16 if self.wfmt == "f16" else bf16     # 16-bit activation format of the sampler loop
+        # the DDIM update runs in the epilogue of the denoiser's last GEMM (DN_EPI_DDIM); DN_FUSE_DDIM=0 keeps dn_ddim_step
+        self.fuse_ddim = os.environ.get("DN_FUSE_DDIM", "1") != "0" and self.cfg.latent_dim % 16 == 0
         self.gemm_impl = None   # None = automatic (CTA-pair kernel when the launch has >= 74 pair tiles); tests force others
         self._graphs: Dict[tuple, object] = {}
         self._shape_seen: Dict[tuple, int] = {}
@@ -332,8 +334,10 @@ class DiffNormEngine:
         return x
 
     def denoise(self, xb: torch.Tensor, lengths: torch.Tensor, B: int, T: int, t_idx: torch.Tensor,
-                t_idx_stride: int = 0) -> torch.Tensor:
-        """Model.forward (LM:828-876).  xb bf16 [B*T, 2*zp] latent staging (split pair); returns eps_hat fp32 [B*T, zn]."""
+                t_idx_stride: int = 0, ddim_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Model.forward (LM:828-876).  xb bf16 [B*T, 2*zp] latent staging (split pair); returns eps_hat fp32 [B*T, zn].
+        ddim_into = the fp32 latent x [B*T, z]: the last GEMM's epilogue applies the DDIM update to x and xb instead of
+        writing eps_hat (shared timestep only); returns x."""
         c = self.cfg
         M = B * T
         h0 = self.buf("d.h0", M, c.hid, self.adt)
@@ -350,6 +354,10 @@ class DiffNormEngine:
             ops.adarmsnorm(x, hb, B, T, self.d_pred_gamma)
         pb = self.buf("d.pred", M, c.hid, self.adt)
         self._run(self.d_pred, hb, pb, B, T)
+        if ddim_into is not None:
+            assert t_idx_stride == 0
+            self._run(self.d_proj, pb, ddim_into, B, T, ddim=(self.ddim_rows, t_idx, xb, self.zp))
+            return ddim_into
         eh = self.buf("d.eps", M, self.zn, f32)
         self._run(self.d_proj, pb, eh, B, T)
         return eh
@@ -373,9 +381,10 @@ class DiffNormEngine:
         params = self.encode_params(feat)
         return ops.vae_reparam(params, eps.contiguous(), self.cfg.latent_dim, eps_channel_first)
 
-    def decode(self, xb: torch.Tensor, lengths: torch.Tensor, B: int, T: int):
+    def decode(self, xb: torch.Tensor, lengths: torch.Tensor, B: int, T: int, units_only: bool = False):
         """decode_feature (LM:1109-1116): latent staging bf16 [B*T, 2*zp] (split pair) -> (recon fp32 [B,T,768], logits
-        fp32 [B,T,vp])."""
+        fp32 [B,T,vp]).  units_only: the unit head's epilogue takes the argmax itself (LM:1450-1451) and the second value
+        returned is units int64 [B,T] — the 257 MB of logits are never written."""
         c = self.cfg
         M = B * T
         sp = self.vsplit
@@ -395,6 +404,10 @@ class DiffNormEngine:
         self._run(self.v_pred, hb, recon, B, T)
         rb = self.buf("v.recon_bf16", M, w2 * c.feat_dim)
         ops.cast_split(recon, rb, c.feat_dim if sp else 0)
+        if units_only:
+            parts = self.buf("v.argmax_parts", M, 4 * self.v_lm.n_tiles, f32)
+            self._run(self.v_lm, rb, parts, B, T, argmax_classes=c.vocab)
+            return recon.view(B, T, -1), ops.argmax_combine(parts, UNIT_OFFSET).view(B, T)
         logits = self.buf("v.logits", M, self.vp, f32)
         self._run(self.v_lm, rb, logits, B, T)
         return recon.view(B, T, -1), logits.view(B, T, -1)
@@ -410,8 +423,11 @@ class DiffNormEngine:
         M, z = B * T, self.cfg.latent_dim
         x, xb = self.buf("s.x", M, z, f32), self.buf("s.xb", M, self.xw)
         t_idx, lens = self.buf("s.t", 1, 1, i32, frames=False).view(-1), self.buf("s.len", B, 1, i32, frames=False).view(-1)
-        eh = self.denoise(xb, lens, B, T, t_idx)
-        ops.ddim_step(x, eh, self.ddim_rows, t_idx, 0, xb, self.zp)
+        if self.fuse_ddim:
+            self.denoise(xb, lens, B, T, t_idx, ddim_into=x)
+        else:
+            eh = self.denoise(xb, lens, B, T, t_idx)
+            ops.ddim_step(x, eh, self.ddim_rows, t_idx, 0, xb, self.zp)
         ops.advance_step(t_idx, -1)
 
     def _ddim_graph(self, B, T):
@@ -437,9 +453,12 @@ class DiffNormEngine:
     def normalize(self, feat: torch.Tensor, lengths: torch.Tensor, start_step: int, eps_vae: Optional[torch.Tensor] = None,
                   eps_q: Optional[torch.Tensor] = None, ref_units: Optional[torch.Tensor] = None, sampler: str = "ddim",
                   step_noise: Optional[Sequence[torch.Tensor]] = None, timesteps: Optional[Sequence[int]] = None,
-                  large_var: bool = False, use_graph: bool = True, collect: bool = False, reduce: bool = True):
+                  large_var: bool = False, use_graph: bool = True, collect: bool = False, reduce: bool = True,
+                  logits: bool = False):
         """The whole pass on resident inputs (ddim_sample, LM:1386-1471, + the driver's reduce,
-        diff_norm_synthesis.py:211-216).  feat fp32 [B,T,768] cuda, lengths int32 [B] cuda."""
+        diff_norm_synthesis.py:211-216).  feat fp32 [B,T,768] cuda, lengths int32 [B] cuda.
+        logits (or collect): also return the [B,T,1004] logits; by default the unit head reduces them to units in its own
+        epilogue and they are never materialised (the units are bit-identical either way)."""
         c = self.cfg
         B, T, _ = feat.shape
         M = B * T
@@ -507,9 +526,14 @@ class DiffNormEngine:
         else:
             raise ValueError(f"unknown sampler {sampler!r}")
         out["calls"] = calls
-        recon, logits = self.decode(xb, lens, B, T)  # xb mirrors x in bf16 (written by q_sample / step kernels)
-        units = ops.argmax_units(logits, c.vocab, UNIT_OFFSET)
-        out.update(x0=x.view(B, T, z), recon=recon, logits=logits, units=units)
+        # xb mirrors x as a split-precision pair (written by q_sample / the step kernels)
+        if logits or collect:
+            recon, lg = self.decode(xb, lens, B, T)
+            units = ops.argmax_units(lg, c.vocab, UNIT_OFFSET)
+            out["logits"] = lg
+        else:
+            recon, units = self.decode(xb, lens, B, T, units_only=True)
+        out.update(x0=x.view(B, T, z), recon=recon, units=units)
         if ref_units is not None:
             out["acc"] = ops.unit_accuracy(units, ref_units.contiguous(), lens)
         if reduce:

@@ -65,6 +65,16 @@ def argmax_units(logits: torch.Tensor, n_classes: int, offset: int = 4, out: Opt
     return out
 
 
+def argmax_combine(partials: torch.Tensor, offset: int = 4, out: Optional[torch.Tensor] = None):
+    """partials fp32 [rows, 2 * parts] written by a GEMM with the argmax epilogue -> units [rows] int64."""
+    _chk(partials, f32, "partials")
+    rows, w = partials.shape
+    if out is None:
+        out = torch.empty(rows, dtype=i64, device=partials.device)
+    check(lib.dn_argmax_combine(_p(partials), rows, w // 2, offset, _p(out), _stream()), "dn_argmax_combine")
+    return out
+
+
 def unit_accuracy(units, ref_units, lengths):
     _chk(units, i64, "units"), _chk(ref_units, i64, "ref_units"), _chk(lengths, i32, "lengths")
     B, T = units.shape
@@ -236,9 +246,19 @@ class GemmPlan:
     def run(self, A, out, B: int, T: int, *, g_a_col: int = 0, g_out_col: int = 0, gb=None, gb_t_stride: int = 0,
             g_gb: int = 0, gb_half: int = 0, t_idx=None, t_idx_stride: int = 0, pe=None, lengths=None,
             epi: Optional[int] = None, impl: Optional[int] = None, a_cols: Optional[int] = None, out_split: bool = False,
-            out_f16: bool = False):
+            out_f16: bool = False, ddim=None, argmax_classes: Optional[int] = None):
         """out_split: 16-bit output written as a split-precision pair (out is [.., 2 * width]: hi | lo).  out_f16: fp16 output."""
         epi = self.epi if epi is None else epi
+        if ddim is not None:
+            # (coef_rows fp32 [steps, 8], t_idx int32 device, staging bf16 [M, ld], lo_col): `out` is the fp32 latent, updated
+            # in place by the DDIM step that consumes this GEMM's eps_hat in registers (DN_EPI_DDIM)
+            epi = _lib.EPI_DDIM
+            coef, t_idx, aux, aux_lo = ddim
+            _chk(coef, f32, "coef"), _chk(aux, bf16, "staging")
+        if argmax_classes is not None:
+            epi = _lib.EPI_ARGMAX      # `out` = fp32 partials [M, 4 * n_tiles]; the logits themselves are never stored
+            if out.shape[-1] != 4 * self.n_tiles:
+                raise ValueError("argmax epilogue: out must be [rows, 4 * n_tiles]")
         if self._flat_ok and gb is None and pe is None:
             # no frame shifts and no per-utterance epilogue inputs: treat the batch as one long utterance so M tiles
             # run across utterance boundaries (T = 1000 would otherwise waste 24 of every 1024 tile rows)
@@ -253,7 +273,7 @@ class GemmPlan:
                 impl = _lib.GEMM_TCGEN05
         wdt = f16 if self.fmt == "f16" else bf16
         _chk(A, wdt, "A")     # one 16-bit format per MMA: fp16 plans take fp16 activations
-        f32out = epi in (_lib.EPI_F32, _lib.EPI_RESID)
+        f32out = epi in (_lib.EPI_F32, _lib.EPI_RESID, _lib.EPI_DDIM, _lib.EPI_ARGMAX)
         out_f16 = out_f16 or (not f32out and not out_split and out.dtype == f16)
         _chk(out, f32 if f32out else (f16 if out_f16 else bf16), "out")
         _chk(self.W, wdt, "W")
@@ -281,6 +301,11 @@ class GemmPlan:
         ldo = out.shape[-1]
         d.out, d.ldo, d.out_batch_stride, d.g_out_col = _p(out), ldo, T * ldo, g_out_col
         d.pe, d.lengths = _p(pe), _p(lengths)
+        d.n_classes = 0 if argmax_classes is None else int(argmax_classes)
+        if ddim is not None:
+            d.coef, d.aux, d.aux_ld, d.aux_lo_col = _p(coef), _p(aux), aux.shape[-1], aux_lo
+            if out.shape[-1] != self.n_out:
+                raise ValueError("DDIM epilogue: the latent width must equal the plan's output width (z % 16 == 0)")
         check(lib.dn_gemm(C.byref(d), impl, _stream()), f"dn_gemm[{self.name}]")
         return out
 

@@ -49,6 +49,10 @@ int dn_reduce_tgt(const int64_t* units, const int32_t* lengths, int32_t B, int32
 int dn_argmax_units(const void* logits, int32_t logits_bf16, int64_t rows, int32_t C, int32_t ld, int32_t offset,
                     int64_t* units, void* stream);
 
+/* Second stage of DN_EPI_ARGMAX: units[r] = index of the best of the row's `parts` (value, index) partials - offset
+ * (same ordering as dn_argmax_units).  partials fp32 [rows, 2 * parts]. */
+int dn_argmax_combine(const float* partials, int64_t rows, int32_t parts, int32_t offset, int64_t* units, void* stream);
+
 /* match = #{valid (b,t): units == ref_units}, total = #valid.  Replaces LM:1453-1454 (two .item() syncs).
  * out2[0] = match, out2[1] = total (int64, device). */
 int dn_unit_accuracy(const int64_t* units, const int64_t* ref_units, const int32_t* lengths, int32_t B, int32_t T,
@@ -171,7 +175,19 @@ enum {
     DN_EPI_F32 = 1,      /* out_f32 = acc + bias (+ pe[pos(b,t)] when pe != null; LM:867-868) */
     DN_EPI_RESID = 2,    /* out_f32 += acc + bias   (residual stream, LM:692,704) */
     DN_EPI_GEGLU = 3,    /* W tile = 128 "x" rows then 128 "gate" rows: out = gelu_erf(gate) * x (LM:881-885) */
-    DN_EPI_WN_GATE = 4   /* W tile = 128 conv rows then 128 res rows: y = tanh(u')sigmoid(u') + res (LM:513-536) */
+    DN_EPI_WN_GATE = 4,  /* W tile = 128 conv rows then 128 res rows: y = tanh(u')sigmoid(u') + res (LM:513-536) */
+    /* eps_hat = acc + bias is consumed in registers by the sampler's DDIM eta = 0 update (LM:1419-1442, dn_ddim_step mode 0):
+     * out = the fp32 latent x [B*T, ldo] updated IN PLACE, aux = its split-precision bf16 staging copy.  The denoiser's
+     * last GEMM (final_proj, n_out = z <= 128: one W tile) runs this, so eps_hat never goes to HBM and the separate update
+     * kernel (a 16 MB launch at z = 16, pure latency) leaves the loop.  n_out % 16 == 0, groups == 1. */
+    DN_EPI_DDIM = 5,
+    /* The unit head (decoder_lm, LM:1095-1096,1450): the 1004 logits of a frame are never written; every epilogue
+     * warpgroup reduces its 128 accumulator columns (+ bias) to one (max value, first index) pair with torch.argmax's
+     * ordering (NaN greatest, first occurrence wins) and writes it to out = fp32 [B*T, 2 * (2 * n_tiles)]: partial p of a
+     * row at columns 2p (value) and 2p + 1 (the index, as int32 bits).  dn_argmax_combine folds the partials of a row.
+     * Columns >= n_classes are excluded.  The max is taken over the SAME fp32 values DN_EPI_F32 would have stored, so the
+     * units are bit-identical to dn_argmax_units over materialised logits. */
+    DN_EPI_ARGMAX = 6
 };
 enum { DN_GEMM_TCGEN05 = 0, DN_GEMM_SIMT_CHECK = 1, DN_GEMM_TCGEN05_2CTA = 2 };
 enum { DN_FMT_BF16 = 0, DN_FMT_F16 = 1 };   /* 16-bit operand / output formats (same tensor-core rate) */
@@ -219,6 +235,11 @@ typedef struct {
     /* != 0: split-precision 16-bit output: column c holds hi = rn(v), column c + out_lo_col holds rn(v - hi); the GEGLU /
      * WaveNet-gate epilogues then use full-precision erf / tanh / exp.  n_out must be a multiple of 64. */
     int32_t out_lo_col;
+    /* DN_EPI_DDIM only */
+    const float* coef;          /* per-step coefficient rows (float32 x 8, see dn_ddim_step); row t_idx[0] is used */
+    void* aux;                  /* bf16 staging copy of x: hi in columns [0, n_out), lo in [aux_lo_col, aux_lo_col + n_out) */
+    int32_t aux_ld, aux_lo_col;
+    int32_t n_classes;          /* DN_EPI_ARGMAX: classes that take part in the argmax (<= n_out) */
 } dn_gemm_desc;
 
 /* out = epilogue(A (*) W^T): bf16 operands, fp32 accumulation in TMEM (tcgen05.mma fed by TMA).
@@ -373,6 +394,32 @@ typedef struct {
     int32_t tile0, tiles_c;
 } dn_pack_op;
 int dn_pack_weights(const dn_pack_op* ops_device, int32_t n_ops, int32_t total_tiles, void* stream);
+
+/* ---- the step after the pass: duration-aware unit vocoder ------------------------------------ */
+/* CodeHiFiGAN generator + duration predictor on the reduced units the pass writes (fairseq/models/text_to_speech/
+ * codehifigan.py:49-76, hifigan.py:20-179, fastspeech2.py:117-151; driver examples/speech_to_speech/
+ * generate_waveform_from_code.py:78-96).  fp32, ONE utterance, channel-first activations [C, L] like the reference. */
+
+/* y[co, l] = act(bias[co] + sum_ci sum_k w[co, ci, k] * lrelu(x[ci, l + k*dilation - pad], in_slope)) (+ res[co, l]), times
+ * out_scale, stored or (accumulate != 0) added to y.  x [Cin, L], w [Cout, Cin, K] (nn.Conv1d layout, weight norm already
+ * folded), y [Cout, L] ("same" padding is the caller's pad = dilation (K-1)/2).  in_slope = 1 leaves x as is (hifigan.py:93-97
+ * applies leaky_relu 0.1 before every conv); out_act: 0 none, 1 ReLU (duration predictor), 2 tanh (conv_post). K <= 16. */
+int dn_voc_conv1d(const float* x, int32_t L, int32_t Cin, const float* w, const float* bias, int32_t Cout, int32_t K,
+                  int32_t dilation, int32_t pad, float in_slope, int32_t out_act, const float* res, float out_scale,
+                  int32_t accumulate, float* y, void* stream);
+/* nn.ConvTranspose1d(Cin, Cout, K, stride, padding = (K - stride) / 2) after leaky_relu(in_slope): x [Cin, L] -> y [Cout, L*stride];
+ * w [Cin, Cout, K] (hifigan.py:128-140, :157-158). */
+int dn_voc_conv_transpose1d(const float* x, int32_t L, int32_t Cin, const float* w, const float* bias, int32_t Cout, int32_t K,
+                            int32_t stride, int32_t pad, float in_slope, float* y, void* stream);
+/* LayerNorm over the C channels at every position, eps 1e-5 (fastspeech2.py:147,149); x, y [C, L]. */
+int dn_voc_layernorm(const float* x, int32_t C, int32_t L, const float* gamma, const float* beta, float* y, void* stream);
+/* dur[t] = max(round(exp(log_dur[t]) - 1), 1) (round half to even, codehifigan.py:66-68; log_dur null = all ones) and
+ * start[0..T] = its exclusive prefix sum (start[T] = number of output frames). */
+int dn_voc_durations(const float* log_dur, int32_t T, int64_t* dur, int64_t* start, void* stream);
+/* x[c, j] = table[code[u], c] for start[u] <= j < start[u+1]: embedding lookup + repeat_interleave (codehifigan.py:57,69);
+ * table [num_embeddings, dim], x [dim, Lo]. */
+int dn_voc_embed_repeat(const int64_t* code, int32_t T, const float* table, int32_t dim, const int64_t* start, int32_t Lo,
+                        float* x, void* stream);
 
 /* ---- host-side helper (no CUDA) --------------------------------------------------------------------------- */
 

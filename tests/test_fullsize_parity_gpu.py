@@ -67,6 +67,11 @@ def run_case(z, B, T, start, chunk):
     steps = sorted({start - 1, start // 2, 1})
     ref = OC.oracle_pass(sdg, arch, feat, mask, start, ev, eq, keep_steps=steps, chunk=chunk)
     out = eng.normalize(feat, lens, start, ev, eq, collect=True)
+    fast = eng.normalize(feat, lens, start, ev, eq)      # the product path: sampler-step CUDA graph, DDIM update and argmax in
+    assert "logits" not in fast                          # GEMM epilogues, logits never materialised — the same units, bit for bit
+    assert torch.equal(fast["units"], out["units"]) and torch.equal(fast["counts"], out["counts"])
+    for b, r in enumerate(out["counts"].tolist()):       # rows are valid up to counts[b]
+        assert torch.equal(fast["dedup"][b, :r], out["dedup"][b, :r]) and torch.equal(fast["duration"][b, :r], out["duration"][b, :r])
     n = int(mask.sum())
     rep = dict(z=rel_rms(out["z"][mask], ref["z"][mask]), x_start=rel_rms(out["x_start"][mask], ref["x_start"][mask]),
                x0=rel_rms(out["x0"].view(B, T, z)[mask], ref["x0"][mask]),

@@ -404,6 +404,53 @@ def test_gemm_wavenet_level(cond):
     torch.testing.assert_close(tc, chk, rtol=1e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("z", [16, 128])
+def test_gemm_ddim_epilogue_matches_gemm_plus_ddim_step(z):
+    """DN_EPI_DDIM (the sampler update inside the last GEMM's epilogue) against EPI_F32 + dn_ddim_step on the same inputs:
+    the fp32 latent and both halves of the split-precision staging copy."""
+    B, T, K, zp = 3, 333, 512, 128 if z > 64 else 64
+    A = rnd(B * T, K, seed=95).half()
+    W, b = rnd(z, K, seed=96, scale=0.05), rnd(z, seed=97)
+    plan = packing.pack_linear(W.cpu(), b.cpu(), epi=_lib.EPI_F32, n_pad=z, fmt="f16").to(DEV)
+    rows = torch.from_numpy(DDPMScheduler(200).ddim_rows()).to(DEV)
+    t_idx = torch.tensor([57], dtype=torch.int32, device=DEV)
+    x0 = rnd(B * T, z, seed=98)
+    eh = torch.empty(B * T, z, device=DEV)
+    plan.run(A, eh, B, T)
+    x_ref, xb_ref = x0.clone(), torch.zeros(B * T, 2 * zp, dtype=torch.bfloat16, device=DEV)
+    ops.ddim_step(x_ref, eh, rows, t_idx, 0, xb_ref, zp)
+    for impl in (_lib.GEMM_SIMT_CHECK, _lib.GEMM_TCGEN05, _lib.GEMM_TCGEN05_2CTA):
+        x, xb = x0.clone(), torch.zeros(B * T, 2 * zp, dtype=torch.bfloat16, device=DEV)
+        plan.run(A, x, B, T, ddim=(rows, t_idx, xb, zp), impl=impl)
+        torch.testing.assert_close(x, x_ref, rtol=1e-5, atol=1e-5)
+        full = lambda p: p[:, :z].double() + p[:, zp:zp + z].double()
+        assert (full(xb) - x.double()).abs().max() <= 2.0 ** -16 * x.abs().max()
+        assert (xb[:, z:zp] == 0).all() and (xb[:, zp + z:] == 0).all()
+
+
+def test_gemm_argmax_epilogue_matches_torch_argmax():
+    """DN_EPI_ARGMAX + dn_argmax_combine (the unit head without materialised logits) == torch.argmax(logits) - 4 on the
+    logits the same plan writes with EPI_F32, including ties (first index), NaN (greatest) and the excluded pad columns."""
+    B, T, K, V = 2, 257, 768, 1004
+    A = rnd(B * T, K, seed=100).bfloat16()
+    W, b = rnd(V, K, seed=101, scale=0.05), rnd(V, seed=102)
+    W[7] = W[3]; b[7] = b[3]                                  # exact tie between classes 3 and 7 in every row
+    b[3] += 100.0; b[7] += 100.0                              # ... and they win: first index must be reported
+    plan = packing.pack_linear(W.cpu(), b.cpu(), epi=_lib.EPI_F32, n_pad=1008).to(DEV)
+    assert plan.n_tiles == 4
+    A[5] = float("nan")                                       # a NaN row: every logit NaN -> index 0
+    logits = torch.empty(B * T, 1008, device=DEV)
+    plan.run(A, logits, B, T)
+    want = torch.argmax(logits[:, :V], dim=-1) - 4
+    assert (want[[0, 1, 2]] == 3 - 4).all() and want[5] == -4
+    for impl in (_lib.GEMM_SIMT_CHECK, _lib.GEMM_TCGEN05, _lib.GEMM_TCGEN05_2CTA):
+        parts = torch.full((B * T, 16), 7.0, device=DEV)
+        plan.run(A, parts, B, T, argmax_classes=V, impl=impl)
+        got = ops.argmax_combine(parts, 4)
+        assert torch.equal(got, want), impl
+    assert torch.equal(ops.argmax_units(logits, V, 4), want)
+
+
 def test_gemm_persistent_many_tiles():
     # > 148 tiles per launch: exercises the smem ring wrap-around and both TMEM accumulator stages
     B, T, K, N = 8, 1000, 512, 1536

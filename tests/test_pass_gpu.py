@@ -82,7 +82,10 @@ def test_stages_and_pass_against_golden(name):
     # --- the full pass, graph and eager
     ref = O.normalize_pass(sd, arch, t("feat"), mask_cpu, start, t("eps_vae"), t("eps_q"))
     for use_graph in (False, True):
-        out = eng.normalize(feat, lens, start, eps_vae, eps_q, ref_units=t("ref_units").to(DEV), use_graph=use_graph)
+        out = eng.normalize(feat, lens, start, eps_vae, eps_q, ref_units=t("ref_units").to(DEV), use_graph=use_graph, logits=True)
+        # default path: the unit head's epilogue takes the argmax itself, logits never materialised -> identical units
+        fused = eng.normalize(feat, lens, start, eps_vae, eps_q, use_graph=use_graph)
+        assert "logits" not in fused and torch.equal(fused["units"], out["units"])
         units = out["units"].cpu()
         gold_units = t("units")
         top2 = ref["logits"].topk(2, dim=-1).values

@@ -222,8 +222,14 @@ def test_train_step_against_oracle_autograd(drop_p, multitask, extreme_t):
         tot_den += float(gr.double().pow(2).sum())
         if e > worst[1]:
             worst = (k, e)
-        # softmax-gradient cancellation (dP - D) makes the to_q / to_kv gradients the noisiest under bf16 operands
-        assert e < (0.25 if (".1.to_" in k or extreme_t) else 0.12), (k, e, float(gr.norm()))
+        # softmax-gradient cancellation (dP - D) makes the to_q / to_kv gradients the noisiest under bf16 operands: measured
+        # worst 8.1 % (21 % at the extreme timesteps), everything else below 6 % (profiles/r02_b3_gpu_tests_85_passed.log);
+        # bounds = 2x the measured worst
+        assert e < (0.25 if extreme_t else (0.16 if ".1.to_" in k else 0.12)), (k, e, float(gr.norm()))
+        # rounding noise is (nearly) orthogonal to the gradient, a wrong scale factor is not: the NORM of every tensor's
+        # gradient must match far more tightly than its direction
+        ratio = float(gg.double().norm() / gr.double().norm().clamp_min(1e-30))
+        assert abs(ratio - 1.0) < (0.08 if extreme_t else 0.04), (k, ratio)
     print(f"[parity] train grads (drop_p={drop_p}, multitask={multitask}): t={times}: global rel err {np.sqrt(tot_num / tot_den):.3e}, worst {worst}, "
           f"pred_noise rel err {e_pred:.2e}")
     # extreme_t case: utterance 1 sits at t = 199 where x1_hat = (x_t - s1 pred) / sqrt(ab) is scaled by 1/2.5e-4, so the
