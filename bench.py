@@ -99,6 +99,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU (reference) arm
 CPU_SAMPLE = (2, 1000)   # utterances x frames of the bounded CPU sample: config 2's utterance length, 2 of its 64 utterances
+if os.environ.get("DN_BENCH_CPU_SAMPLE"):   # tests shrink the sample (e.g. "1x64"); the line always states the shape it ran
+    CPU_SAMPLE = tuple(int(v) for v in os.environ["DN_BENCH_CPU_SAMPLE"].split("x"))
 
 
 class CpuReference:

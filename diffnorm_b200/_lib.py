@@ -98,6 +98,7 @@ _SIGS = {
     "dn_cast_split": [vp, i64, i32, i32, vp, i32, i32, vp],
     "dn_vae_reparam": [vp, i32, vp, i32, i32, i32, i32, vp, vp],
     "dn_split_bf16x3": [vp, i64, i32, vp, vp],
+    "dn_sround_bf16": [vp, vp, i64, C.c_uint32, vp, vp],
     "dn_q_sample": [vp, vp, f32, f32, i64, i32, vp, vp, i32, i32, vp],
     "dn_ddim_step": [vp, vp, i32, vp, vp, i64, i32, i32, vp, i32, i32, vp],
     "dn_ddpm_step": [vp, vp, i32, vp, vp, vp, i64, i32, vp, i32, i32, vp],

@@ -51,6 +51,30 @@ __global__ void cast_split_kernel(const float* __restrict__ src, long long rows,
     }
 }
 
+// ---------------------------------------------------------------------------------------------- stochastic weight rounding
+// dst[i] = bf16 stochastic rounding of src[i]: add 16 uniform random bits below the kept mantissa, truncate.  The bits come
+// from a counter hash of (element index, seed, step), so a step's weights are a deterministic function of the seed, and the
+// rounding error of a weight is independent from step to step (E[dst] = src).
+__device__ __forceinline__ uint32_t sr_hash(uint32_t x) {   // lowbias32 (avalanching 32-bit finaliser)
+    x ^= x >> 16; x *= 0x7feb352dU;
+    x ^= x >> 15; x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+__global__ void __launch_bounds__(EW_THREADS)
+sround_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, uint32_t seed,
+                   const int* __restrict__ step) {
+    const uint32_t key = sr_hash(seed ^ (0x9E3779B9U * (uint32_t)(step ? step[0] + 1 : 1)));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + i);
+        const uint32_t r0 = sr_hash((uint32_t)(2 * i) ^ key), r1 = sr_hash((uint32_t)(2 * i + 1) ^ key ^ (uint32_t)(i >> 31));
+        const uint32_t b0 = __float_as_uint(v.x) + (r0 & 0xFFFFu), b1 = __float_as_uint(v.y) + (r0 >> 16);
+        const uint32_t b2 = __float_as_uint(v.z) + (r1 & 0xFFFFu), b3 = __float_as_uint(v.w) + (r1 >> 16);
+        // (finite weights: the carry may reach the exponent, which is the correct round-up to the next binade)
+        *reinterpret_cast<uint2*>(dst + 4 * i) = make_uint2((b0 >> 16) | (b1 & 0xFFFF0000u), (b2 >> 16) | (b3 & 0xFFFF0000u));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- bf16 split staging
 // fp32 [rows, C] -> bf16 [rows, 3C] = [hi | hi | lo] with hi = bf16(x), lo = bf16(x - hi): against weights packed as
 // [hi | lo | hi] one bf16 GEMM over K = 3C computes x.w to ~2^-16 relative (the lo.lo term is dropped) — the fp32-grade
@@ -446,6 +470,15 @@ extern "C" int dn_cast_split(const float* src, int64_t rows, int32_t C, int32_t 
     if (lo_col ? (C > lo_col || lo_col + C > ldo) : C > ldo) return DN_EINVAL;
     cast_split_kernel<<<ew_grid(rows * (ldo / 8), EW_THREADS), EW_THREADS, 0, ST(stream)>>>(
         src, rows, C, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldo, lo_col ? lo_col : ldo);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_sround_bf16(const float* src, void* dst, int64_t n, uint32_t seed, const int32_t* step, void* stream) {
+    if (!src || !dst || n <= 0 || n % 4 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15)) return DN_EINVAL;
+    sround_bf16_kernel<<<ew_grid(n / 4, EW_THREADS), EW_THREADS, 0, ST(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n / 4,
+                                                                                 seed, step);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

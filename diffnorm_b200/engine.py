@@ -74,8 +74,13 @@ class DiffNormEngine:
         # a 1 % logit error flips 2.5 % of near-tie units: they run split-precision (hi | lo bf16 pairs, 3 MMAs per K block).
         self.wfmt = wfmt or os.environ.get("DN_WFMT", "bf16" if self.fuse_norm else "f16")
         self.vae_fmt = vae_fmt or os.environ.get("DN_VAE_FMT", "split")
-        if self.wfmt not in ("bf16", "f16") or self.vae_fmt not in ("bf16", "split"):
-            raise ValueError("wfmt must be bf16 | f16 and vae_fmt bf16 | split")
+        if self.wfmt not in ("bf16", "bf16sr", "f16") or self.vae_fmt not in ("bf16", "split"):
+            raise ValueError("wfmt must be bf16 | bf16sr | f16 and vae_fmt bf16 | split")
+        # "bf16sr": bf16 operands whose WEIGHTS are re-rounded stochastically from their fp32 masters at every sampler step
+        # (dn_sround_bf16 inside the step graph): the weight error stops being the same in all 99 calls and averages out like
+        # the activations' does, at bf16's power draw (fp16 costs 4 % of clock under the 1000 W cap)
+        self.sr_seed = int(os.environ.get("DN_SR_SEED", "20240518"))
+        self._sr32 = self._sr16 = None
         self.vsplit = self.vae_fmt == "split"
         self.adt = torch.float16 if self.wfmt == "f16" else bf16     # 16-bit activation format of the sampler loop
         # the DDIM update runs in the epilogue of the denoiser's last GEMM (DN_EPI_DDIM); DN_FUSE_DDIM=0 keeps dn_ddim_step
@@ -142,6 +147,35 @@ class DiffNormEngine:
         self.d_pred = self._dev(pack_linear(sd["model.transformer.to_pred.1.weight"], None, name="model.to_pred", fmt=w))
         self.d_proj = self._dev(pack_linear(sd["model.final_proj.weight"], sd["model.final_proj.bias"],
                                             epi=_lib.EPI_F32, n_pad=self.zn, name="model.final_proj", fmt=w))
+        if w == "bf16sr":
+            self._gather_sr_weights()
+
+    def _sr_plans(self):
+        plans = [*self.d_wn.plans(), self.d_pred, self.d_proj]
+        for L in self.d_layers:
+            plans += [L.qkv, L.out, L.ff1, L.ffc, L.ff3]
+        return [p for p in plans if p.W32 is not None]
+
+    def _gather_sr_weights(self):
+        """Move every re-rounded plan's fp32 master and bf16 weight into ONE flat buffer each (offsets 256-byte aligned), so
+        that a sampler step re-rounds all of them with a single launch; the plans keep views."""
+        plans = self._sr_plans()
+        offs, tot = [], 0
+        for p in plans:
+            offs.append(tot)
+            tot += (p.W32.numel() + 127) // 128 * 128
+        self._sr32 = torch.zeros(tot, dtype=f32, device=self.dev)
+        self._sr16 = torch.zeros(tot, dtype=bf16, device=self.dev)
+        for p, o in zip(plans, offs):
+            n = p.W32.numel()
+            self._sr32[o:o + n].copy_(p.W32.reshape(-1))
+            self._sr16[o:o + n].copy_(p.W.reshape(-1))
+            p.W = self._sr16[o:o + n].view(p.W.shape)
+            p.W32 = self._sr32[o:o + n].view(p.W.shape)
+
+    def reround_weights(self, t_idx):
+        if self._sr32 is not None:
+            ops.sround_bf16(self._sr32, self._sr16, self.sr_seed, t_idx)
 
     def _pack_vae(self, sd):
         c = self.cfg
@@ -423,6 +457,7 @@ class DiffNormEngine:
         M, z = B * T, self.cfg.latent_dim
         x, xb = self.buf("s.x", M, z, f32), self.buf("s.xb", M, self.xw)
         t_idx, lens = self.buf("s.t", 1, 1, i32, frames=False).view(-1), self.buf("s.len", B, 1, i32, frames=False).view(-1)
+        self.reround_weights(t_idx)
         if self.fuse_ddim:
             self.denoise(xb, lens, B, T, t_idx, ddim_into=x)
         else:

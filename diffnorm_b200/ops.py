@@ -115,6 +115,13 @@ def cast_split(src: torch.Tensor, out: torch.Tensor, lo_col: int):
     return out
 
 
+def sround_bf16(src: torch.Tensor, dst: torch.Tensor, seed: int, step: Optional[torch.Tensor] = None):
+    """dst (bf16) = stochastic rounding of src (fp32), fresh for every value of the device step counter."""
+    _chk(src, f32, "src"), _chk(dst, bf16, "dst")
+    check(lib.dn_sround_bf16(_p(src), _p(dst), src.numel(), int(seed) & 0xFFFFFFFF, _p(step), _stream()), "dn_sround_bf16")
+    return dst
+
+
 def vae_reparam(params, eps, z: int, eps_channel_first: bool, out=None):
     _chk(params, f32, "params"), _chk(eps, f32, "eps")
     B, T, ldp = params.shape
@@ -227,8 +234,11 @@ class GemmPlan:
         """fmt: operand format of this plan.  "bf16" / "f16": W is that 16-bit type, A is bf16.  "split": W = [W_hi | W_lo]
         (bf16 pairs side by side along K) and A = [A_hi | A_lo] (two halves of the row): every K segment runs three times
         — (A_hi, W_hi), (A_hi, W_lo), (A_lo, W_hi) — which contracts to ~2^-17 relative instead of 2^-9."""
-        if fmt not in ("bf16", "f16", "split"):
+        if fmt not in ("bf16", "bf16sr", "f16", "split"):
             raise ValueError(fmt)
+        self.W32 = None     # "bf16sr": the fp32 packed master the engine re-rounds stochastically every sampler step
+        if fmt == "bf16sr":
+            fmt = "bf16"
         self.fmt = fmt
         self.W, self.segs, self.n_out, self.n_tiles, self.epi = W, [tuple(s) for s in segs], n_out, n_tiles, epi
         if fmt == "split" and 3 * len(self.segs) > _lib.MAX_SEGS:
@@ -239,6 +249,7 @@ class GemmPlan:
 
     def to(self, device):
         self.W = self.W.to(device)
+        self.W32 = None if self.W32 is None else self.W32.to(device)
         self.bias = None if self.bias is None else self.bias.to(device)
         self.bias2 = None if self.bias2 is None else self.bias2.to(device)
         return self

@@ -31,10 +31,19 @@ def _bf(t: torch.Tensor, fmt: str = "bf16") -> torch.Tensor:
     """fp32 packed weight -> the plan's operand format: bf16, fp16 (saturating), or the split pair [hi | lo] along K."""
     if fmt == "f16":
         return t.clamp(-65504.0, 65504.0).to(torch.float16).contiguous()
-    hi = t.to(torch.bfloat16)
+    hi = t.to(torch.bfloat16)      # "bf16" and "bf16sr" (the latter also keeps the fp32 master, see GemmPlan.W32)
     if fmt == "split":
         return torch.cat([hi, (t - hi.float()).to(torch.bfloat16)], dim=1).contiguous()
     return hi.contiguous()
+
+
+def _mk(Wp: torch.Tensor, wfmt: str, *args, **kw) -> GemmPlan:
+    """GemmPlan over the packed fp32 matrix Wp cast to the plan's operand format; "bf16sr" also keeps Wp itself (the master
+    the engine re-rounds stochastically every sampler step)."""
+    plan = GemmPlan(_bf(Wp, wfmt), *args, **kw)
+    if wfmt == "bf16sr":
+        plan.W32 = Wp.contiguous()
+    return plan
 
 
 def pack_linear(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.EPI_BF16, k_pad: Optional[int] = None,
@@ -50,7 +59,7 @@ def pack_linear(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.E
     if bias is not None:
         bp = torch.zeros(Np, device=W.device)
         bp[:N] = bias.float()
-    return GemmPlan(_bf(Wp, fmt), [(0, 0, Kp // BK, 0, 0)], Np, (Np + WT - 1) // WT, epi, bias=bp, name=name, fmt=fmt)
+    return _mk(Wp, fmt, [(0, 0, Kp // BK, 0, 0)], Np, (Np + WT - 1) // WT, epi, bias=bp, name=name, fmt=fmt)
 
 
 def pack_conv3(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.EPI_BF16, cin_pad: Optional[int] = None,
@@ -71,7 +80,7 @@ def pack_conv3(W: torch.Tensor, bias: Optional[torch.Tensor], epi: int = _lib.EP
         bp = torch.zeros(Np, device=W.device)
         bp[:N] = bias.float()
     segs = [(0, shift_sign * (2 - k), Cp // BK, k * Cp, 0) for k in range(3)]
-    return GemmPlan(_bf(Wp, fmt), segs, Np, (Np + WT - 1) // WT, epi, bias=bp, dilation=dilation, name=name, fmt=fmt)
+    return _mk(Wp, fmt, segs, Np, (Np + WT - 1) // WT, epi, bias=bp, dilation=dilation, name=name, fmt=fmt)
 
 
 def pack_geglu(W: torch.Tensor, bias: torch.Tensor, name: str = "", fmt: str = "bf16") -> GemmPlan:
@@ -93,7 +102,7 @@ def pack_geglu(W: torch.Tensor, bias: torch.Tensor, name: str = "", fmt: str = "
         Wp[j * WT + 128:j * WT + 128 + n, :K] = W[inner + lo:inner + hi]
         bp[j * WT:j * WT + n] = bias[lo:hi].float()
         bp[j * WT + 128:j * WT + 128 + n] = bias[inner + lo:inner + hi].float()
-    return GemmPlan(_bf(Wp, fmt), [(0, 0, Kp // BK, 0, 0)], ip, tiles, _lib.EPI_GEGLU, bias=bp, name=name, fmt=fmt)
+    return _mk(Wp, fmt, [(0, 0, Kp // BK, 0, 0)], ip, tiles, _lib.EPI_GEGLU, bias=bp, name=name, fmt=fmt)
 
 
 def pack_wavenet_level(convs: List[torch.Tensor], conv_b: List[torch.Tensor], ress: List[torch.Tensor],
@@ -137,7 +146,7 @@ def pack_wavenet_level(convs: List[torch.Tensor], conv_b: List[torch.Tensor], re
             br[g * Cp:g * Cp + Cc] = res_b[g].float()
     kb = Cp // BK
     segs = [(0, 0, kb, 0, 0), (0, 2, kb, Cp, 128), (0, 1, kb, 2 * Cp, 128)]
-    return GemmPlan(_bf(Wp, fmt), segs, Cp, tiles, _lib.EPI_WN_GATE, bias=bc, bias2=br, groups=G, g_w_row=rows_g,
+    return _mk(Wp, fmt, segs, Cp, tiles, _lib.EPI_WN_GATE, bias=bc, bias2=br, groups=G, g_w_row=rows_g,
                     g_bias=Cp, dilation=1, dilation_shl_group=1, name=name, fmt=fmt)
 
 
@@ -153,7 +162,7 @@ def pack_skip_sum(skips: List[torch.Tensor], skip_b: List[torch.Tensor], c_pad: 
     bp = torch.zeros(c_pad, device=skips[0].device)
     bp[:Cc] = torch.stack([b.float() for b in skip_b]).sum(0)
     Np = Wp.shape[0]
-    return GemmPlan(_bf(Wp, fmt), [(0, 0, G * c_pad // BK, 0, 0)], Np, (Np + WT - 1) // WT, _lib.EPI_BF16, bias=bp, name=name,
+    return _mk(Wp, fmt, [(0, 0, G * c_pad // BK, 0, 0)], Np, (Np + WT - 1) // WT, _lib.EPI_BF16, bias=bp, name=name,
                     fmt=fmt)
 
 

@@ -77,6 +77,14 @@ int dn_cast_pad_bf16(const float* src, int64_t rows, int32_t C, int32_t lds, voi
 int dn_cast_split(const float* src, int64_t rows, int32_t C, int32_t lds, void* dst, int32_t ldo, int32_t lo_col,
                   void* stream);
 
+/* Stochastic re-rounding of packed GEMM weights: dst[i] = bf16(src[i]) rounded up or down with probability proportional to
+ * the distance (16 random bits from a counter hash of (i, seed, step[0]); deterministic given the seed; E[dst] = src).
+ * A bf16 weight rounded ONCE carries the same error into all 99 denoiser calls of a pass, and that error accumulates
+ * coherently in the latent; re-rounding the weights every sampler step makes it independent from step to step,
+ * so it averages out like the activations' rounding does — at bf16's power draw instead of fp16's.  step is a DEVICE int32 (the
+ * sampler's step counter) so the launch sits inside the captured step graph; n % 4 == 0, 16-byte aligned pointers. */
+int dn_sround_bf16(const float* src, void* dst, int64_t n, uint32_t seed, const int32_t* step, void* stream);
+
 /* fp32 [rows, C] -> bf16 [rows, 3C] = [hi | hi | lo] (hi = bf16(x), lo = bf16(x - hi)).  Against weights packed as
  * [hi | lo | hi] a single dn_gemm over K = 3C gives the contraction to ~2^-16 relative: used by the k-means unit
  * quantiser (examples/textless_nlp/gslm/speech2unit/clustering/quantize_with_kmeans.py:109-121). */

@@ -195,6 +195,38 @@ def test_attention_dh64_fp16():
     assert rel(out, want) < 3e-3, rel(out, want)     # fp16 P and output; the bf16 kernel sits at ~1e-2
 
 
+def test_stochastic_weight_rerounding_is_unbiased_and_step_dependent():
+    """dn_sround_bf16: every output is one of the two bf16 neighbours of the fp32 master, a step's rounding is a
+    deterministic function of (seed, step), differs between steps, and averages to the master (E[dst] = src)."""
+    n = 1 << 16
+    w = rnd(n, seed=90, scale=0.05)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dst = torch.empty(n, dtype=bf16, device=DEV)
+    lo = w.view(torch.int32).bitwise_and(-65536).view(torch.float32)           # truncated toward zero
+    hi = (w.view(torch.int32).bitwise_and(-65536) + 65536).view(torch.float32)    # next bf16 away from zero
+    acc = torch.zeros(n, dtype=torch.float64, device=DEV)
+    outs = []
+    for t in range(64):
+        step.fill_(t)
+        ops.sround_bf16(w, dst, 1234, step)
+        v = dst.float()
+        assert bool(((v == lo) | (v == hi)).all())
+        acc += v.double()
+        outs.append(v.clone())
+    assert not torch.equal(outs[0], outs[1])
+    step.fill_(0)
+    ops.sround_bf16(w, dst, 1234, step)
+    assert torch.equal(dst.float(), outs[0])                                  # deterministic given (seed, step)
+    ops.sround_bf16(w, dst, 99, step)
+    assert not torch.equal(dst.float(), outs[0])
+    mean_err = (acc / 64 - w.double()).abs().mean() / w.abs().mean()
+    rn_err = (w.bfloat16().double() - w.double()).abs().mean() / w.abs().mean()
+    assert mean_err < 0.3 * rn_err, (float(mean_err), float(rn_err))          # 64 independent draws: ~1/8 of one rounding
+    up = (torch.stack(outs) == hi).double().mean(0)                           # P(round up) = fractional position
+    frac = ((w.double() - lo.double()) / (hi.double() - lo.double()))
+    assert float((up - frac).abs().mean()) < 0.06
+
+
 @pytest.mark.parametrize("C", [512, 768])
 def test_adarmsnorm_split(C):
     B, T = 3, 41
