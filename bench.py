@@ -247,8 +247,9 @@ def workload_config(args):
             "batch": args.batch, "frames": args.frames, "latent_dim": args.latent_dim, "start_step": args.start_step,
             "sharding": "by utterance, no collective", "l2": "inputs 197 MB/step and >1 GB of activations per call exceed the 126 MB L2",
             "weights": "random init (torch default init law)",
-            "operands": "fp16 x fp16 -> fp32 accumulate in the 99-call loop (fp32 latent, residual stream and logits); VAE "
-                        "encoder / decoder in split precision (bf16 hi|lo pairs, 3 MMAs per K block)"}
+            "operands": "bf16 x bf16 -> fp32 accumulate in the 99-call loop, the weights re-rounded stochastically from their fp32 "
+                        "masters at every step (dn_sround_bf16, inside the timed region); fp32 latent, residual stream and logits; "
+                        "VAE encoder / decoder in split precision (bf16 hi|lo pairs, 3 MMAs per K block)"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -370,7 +371,8 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": ref.kind, "sample": ref.describe(calls, secs)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16sr": "bf16", "f16": "fp16", "bf16": "bf16"}[eng.wfmt],
             "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -479,7 +481,8 @@ def run_dataset(args):
         fpf = flops_per_frame(z, 600, start - 1)
         print(json.dumps({
             "metric": METRIC, "value": valid / dev_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_max * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16",
+            "ms_per_step": dev_max * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"bf16sr": "bf16", "f16": "fp16", "bf16": "bf16"}[eng.wfmt],
             "data": "synthetic",
             "config": {"workload": f"config 4: dataset-scale normalization of {args.utts} variable-length utterances "
                                    f"(lengths 200-2000, median 600), start_step {start}, length-bucketed batches of <= "

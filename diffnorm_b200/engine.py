@@ -66,13 +66,17 @@ class DiffNormEngine:
         self.ws: Dict[tuple, torch.Tensor] = {}
         # residual GEMM + following adaptive RMSNorm in one kernel (dn_gemm_resid_norm); DN_FUSE_NORM=0 keeps the pair
         self.fuse_norm = os.environ.get("DN_FUSE_NORM", "0") == "1"
-        # Operand formats (DESIGN.md "operand formats"; evidence profiles/r02_a3_precision_probe.jsonl).  The sampler loop
-        # runs fp16 operands (weights AND activations: a tcgen05 kind::f16 MMA takes both in one format): a weight's
-        # rounding error is the same in all 99 calls and adds up coherently (x0 error 0.18 % with bf16 weights, 0.02 % with
-        # fp16, same MMA rate), an activation's is fresh every call and averages out; every fp16 store saturates at +-65504
-        # (DN_WFMT=bf16 keeps the wide-range format).  The once-per-pass VAE encoder / decoder have no such averaging, and
-        # a 1 % logit error flips 2.5 % of near-tie units: they run split-precision (hi | lo bf16 pairs, 3 MMAs per K block).
-        self.wfmt = wfmt or os.environ.get("DN_WFMT", "bf16" if self.fuse_norm else "f16")
+        # Operand formats (DESIGN.md "operand formats"; evidence profiles/r02_a3_precision_probe.jsonl).  A bf16 weight rounded
+        # ONCE carries the same error into all 99 calls of the sampler loop and that error adds up coherently in the latent (x0
+        # error 0.18 %, 97.3 % unit agreement); an activation's rounding is fresh every call and averages out.  Two cures:
+        #   "bf16sr" (default): bf16 operands, the weights re-rounded STOCHASTICALLY from their fp32 masters at every step
+        #            (dn_sround_bf16, one launch inside the step graph): x0 error 0.036 %, 99.96 % agreement, bf16's power draw;
+        #   "f16":   fp16 weights and activations (a tcgen05 kind::f16 MMA takes both in one format), stores saturate at
+        #            +-65504: x0 error 0.022 %, but 4 % of clock under the 1000 W cap;
+        #   "bf16":  round 1's format (A/B reference).
+        # The once-per-pass VAE encoder / decoder have no averaging at all, and a 1 % logit error flips 2.5 % of near-tie
+        # units: they run split precision (hi | lo bf16 pairs, 3 MMAs per K block).
+        self.wfmt = wfmt or os.environ.get("DN_WFMT", "bf16" if self.fuse_norm else "bf16sr")
         self.vae_fmt = vae_fmt or os.environ.get("DN_VAE_FMT", "split")
         if self.wfmt not in ("bf16", "bf16sr", "f16") or self.vae_fmt not in ("bf16", "split"):
             raise ValueError("wfmt must be bf16 | bf16sr | f16 and vae_fmt bf16 | split")
@@ -543,6 +547,7 @@ class DiffNormEngine:
             t_idx.fill_(start_step - 1)
             n = start_step - 1
             for k in range(n):
+                self.reround_weights(t_idx)
                 eh = self.denoise(xb, lens, B, T, t_idx)
                 noise = step_noise[k] if step_noise is not None else torch.randn(B, T, z, device=self.dev, dtype=f32)
                 ops.ddpm_step(x, eh, noise.contiguous(), rows, t_idx, xb, self.zp)
@@ -555,6 +560,7 @@ class DiffNormEngine:
             for i in range(len(tmap) - 1, 0, -1):
                 t_idx.fill_(tmap[i])          # the model sees the original step (respace.py:117-129)
                 r_idx.fill_(i)                # the update uses the respaced table row
+                self.reround_weights(t_idx)
                 eh = self.denoise(xb, lens, B, T, t_idx)
                 ops.ddim_step(x, eh, rows, r_idx, 1, xb, self.zp)
                 calls += 1
@@ -584,4 +590,6 @@ class DiffNormEngine:
         return xb
 
     def precision_mode(self) -> str:
-        return f"loop: {self.wfmt} operands (fp32 accumulate, fp32 latent in); VAE encode/decode: {self.vae_fmt}"
+        what = {"bf16sr": "bf16 operands, weights re-rounded stochastically every step", "f16": "fp16 operands",
+                "bf16": "bf16 operands"}[self.wfmt]
+        return f"loop: {what} (fp32 accumulate, fp32 latent in); VAE encode/decode: {self.vae_fmt}"

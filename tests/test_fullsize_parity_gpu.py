@@ -9,14 +9,15 @@ see only their zero padding, attention has one key block, and nothing accumulate
   C2-shape B 8 x T 1000 (ragged), 99 calls
   one denoiser call at T 700: dilations 64 / 128 inside the utterance, 6 attention key blocks
 
-Stated tolerances (operands: fp16 in the loop, split-precision bf16 pairs in the VAE encoder / decoder, fp32 accumulation,
-fp32 latent / residual stream / logits), each about 2-3x the measured value (profiles/r02_b2_fullsize_parity.log):
-  z, x_start                 rel-rms <= 1e-4           (measured 2.3e-5; bf16 operands gave 8.7e-3)
-  eps_hat, one call          rel-rms <= 3e-3           (measured 0.7-1.5e-3; bf16: 6-9e-3)
-  x0 after 99 calls          rel-rms <= 6e-4           (measured 2.2e-4; bf16: 6.3e-3)
-  logits                     rel-rms <= 6e-4           (measured 2.1e-4; bf16: 1.2e-2)
+Stated tolerances (operands of the loop: bf16 with the weights re-rounded stochastically every step, the default, or fp16;
+split-precision bf16 pairs in the VAE encoder / decoder; fp32 accumulation, fp32 latent / residual stream / logits), each about
+2x the measured value (profiles/r02_b2_fullsize_parity.log for fp16, r02_s1_parity_bf16sr_*.json for the default):
+  z, x_start                 rel-rms <= 1e-4           (measured 2.3e-5; round 1's bf16 encoder gave 8.7e-3)
+  eps_hat, one call          rel-rms <= 1.2e-2         (measured 6.8e-3 = one call's bf16 rounding; fp16: 0.7-1.5e-3)
+  x0 after 99 calls          rel-rms <= 8e-4           (measured 3.6e-4; fp16 2.2e-4; round 1's fixed bf16 weights 1.8e-3)
+  logits                     rel-rms <= 8e-4           (measured 3.6e-4; fp16 2.1e-4; round 1 1.2e-2)
   units                      >= 99.5 % of ALL valid frames equal the oracle's (north_star), no margin filter
-                             (measured 100 % / 99.94 % / 99.93 %; bf16 operands gave 97.3 %).
+                             (measured 99.97 % / 99.96 % default, 100 % / 99.94 % / 99.93 % fp16; round 1's formats gave 97.3 %).
 """
 import pytest
 import torch
@@ -90,8 +91,8 @@ def run_case(z, B, T, start, chunk):
           f"largest margin among flips {float(margin[~agree].max()) if (~agree).any() else 0.0:.4f} sigma")
     assert n >= 3000
     assert rep["z"] <= 1e-4 and rep["x_start"] <= 1e-4
-    assert all(rep[f"eps_t{t}"] <= 3e-3 for t in steps)
-    assert rep["x0"] <= 6e-4 and rep["logits"] <= 6e-4
+    assert all(rep[f"eps_t{t}"] <= (3e-3 if eng.wfmt == "f16" else 1.2e-2) for t in steps)
+    assert rep["x0"] <= 8e-4 and rep["logits"] <= 8e-4
     assert agree.float().mean() >= 0.995          # north_star: >= 99.5 % frame agreement, unfiltered
     # the integer tail on the device units equals the oracle's reduce of the same units (bit-exact)
     units, cnt = out["units"].cpu(), out["counts"].cpu()
@@ -119,6 +120,22 @@ def test_z128_full_pass_unit_agreement():
     run_case(128, 8, 500, 50, chunk=8)
 
 
+def test_fp16_loop_format_full_pass():
+    """The other cure of the coherent weight error: fp16 operands in the loop (DN_WFMT=f16), same harness, C1 shape."""
+    z, B, T, start = 16, 8, 500, 100
+    arch, sd, sdg, _ = setup(z)
+    eng = DiffNormEngine(sd, DEV, wfmt="f16")
+    c = OC.case_inputs(z, B, T)
+    mask = c["mask"].to(DEV)
+    feat, ev, eq = c["feat"].to(DEV), c["eps_vae"].to(DEV), c["eps_q"].to(DEV)
+    ref = OC.oracle_pass(sdg, arch, feat, mask, start, ev, eq, chunk=8)
+    out = eng.normalize(feat, c["lens"].to(torch.int32).to(DEV), start, ev, eq, collect=True)
+    agree = (out["units"] == ref["units"])[mask]
+    x0 = rel_rms(out["x0"].view(B, T, z)[mask], ref["x0"][mask])
+    print(f"[fullsize] fp16 loop: x0 rel-rms {x0:.2e}, units agree {int(agree.sum())}/{agree.numel()}")
+    assert x0 <= 6e-4 and agree.float().mean() >= 0.995
+
+
 def test_long_utterance_denoiser_call():
     """One Model.forward at T 700 (LM:828-876): dilation-64/128 taps land inside the utterance, 6 key blocks."""
     z, B, T = 16, 3, 700
@@ -133,4 +150,4 @@ def test_long_utterance_denoiser_call():
         r = rel_rms(got[mask], want[mask])
         d = (got - want)[mask].abs().max()
         print(f"[fullsize] denoiser call T {T} t {t}: rel-rms {r:.2e} max-abs {float(d):.3e} (std {float(want.std()):.3f})")
-        assert r <= 4e-3 and d <= 2e-2 * want.std()
+        assert r <= (4e-3 if eng.wfmt == "f16" else 1.5e-2) and d <= 6e-2 * want.std()
