@@ -133,6 +133,7 @@ _SIGS = {
     "dn_recon_grad": [vp, vp, vp, vp, i32, i32, i32, vp, f32, vp, vp],
     "dn_pred_x1": [vp, vp, i32, vp, vp, i32, i32, i32, vp, i32, vp],
     "dn_decode_losses": [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp, vp],
+    "dn_randn": [vp, i64, C.c_uint64, C.c_uint64, vp],
     "dn_dropout_bits": [vp, i64, f32, C.c_uint64, C.c_uint64, vp],
     "dn_attention_train": [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp],
     "dn_attention_bwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],

@@ -584,6 +584,25 @@ __global__ void dropout_bits_kernel(uint32_t* __restrict__ bits, long long n_wor
     }
 }
 
+// ---------------------------------------------------------------------------------------------- N(0, 1) noise
+// out[i] ~ N(0, 1): Philox4x32-10 counter streams (subsequence = thread, offset = `offset`), Box-Muller, 4 values per draw.
+// The noise of the posterior sample and of q_sample (distributions.py:37-41, LM:1409) when the caller supplies none.
+__global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset) {
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)tid, offset, &st);
+    for (long long i = tid * 4; i < n; i += stride * 4) {
+        const float4 v = curand_normal4(&st);
+        if (i + 3 < n) {
+            *reinterpret_cast<float4*>(out + i) = v;
+        } else {
+            const float e[4] = {v.x, v.y, v.z, v.w};
+            for (int k = 0; k < 4 && i + k < n; ++k) out[i + k] = e[k];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- small fp32 (time MLP)
 __global__ void silu_kernel(const float* __restrict__ pre, float* __restrict__ out, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -863,6 +882,17 @@ extern "C" int dn_recon_grad(const float* recon, const float* audio, const float
     if (!recon || !audio || !d_lm || !lengths || !stats || !out || B <= 0 || T <= 0 || C <= 0 || C % 4) return DN_EINVAL;
     recon_grad_kernel<<<tr_grid((long long)B * T * (C / 4), TR_THREADS), TR_THREADS, 0, ST(stream)>>>(
         recon, audio, d_lm, lengths, B, T, C, stats, mse_scale, (bf*)out);
+    DN_LAUNCH_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" int dn_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (!out || n <= 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return DN_EINVAL;
+    const long long threads = (n + 3) / 4;
+    long long blocks = (threads + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    randn_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, n, seed, offset);
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;

@@ -504,10 +504,10 @@ class DiffNormEngine:
         z = c.latent_dim
         if not (0 < start_step < c.timesteps):
             raise ValueError(f"start_step must be in (0, {c.timesteps}) (LM:1405 indexes the schedule with it)")
-        if eps_vae is None:
-            eps_vae = torch.randn(B, z, T, device=self.dev, dtype=f32)
+        if eps_vae is None:    # the library's own Philox draws (seeded from torch's generator, so torch.manual_seed replays them)
+            eps_vae = ops.randn((B, z, T), self.dev, self._noise_seed(), 0)
         if eps_q is None:
-            eps_q = torch.randn(B, T, z, device=self.dev, dtype=f32)
+            eps_q = ops.randn((B, T, z), self.dev, self._noise_seed(), 0)
         # a CUDA graph pays its warm-up step + capture (GPU idle meanwhile) only for shapes that come back: length-bucketed
         # batches of a dataset are mostly one-off (B, T) shapes and run eager (the host stays ~20x ahead of a 20 ms step)
         seen = self._shape_seen.get((B, T), 0)
@@ -580,6 +580,11 @@ class DiffNormEngine:
         if reduce:
             out["dedup"], out["duration"], out["index_to_keep"], out["counts"] = ops.reduce_tgt(units, lens)
         return out
+
+    @staticmethod
+    def _noise_seed() -> int:
+        """A fresh 63-bit seed from torch's default CPU generator: `torch.manual_seed(s)` makes a pass reproducible."""
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
 
     def stage_latent(self, latent: torch.Tensor) -> torch.Tensor:
         """fp32 [B,T,z] latent -> split-precision bf16 staging buffer [B*T, 2*zp] (for decode / denoise on caller-supplied

@@ -437,6 +437,13 @@ def decode_losses(recon, audio, logits, vocab: int, units, lengths, B, T):
     return out
 
 
+def randn(shape, device, seed: int, offset: int) -> torch.Tensor:
+    """fp32 N(0, 1) tensor drawn by the library's own Philox kernel."""
+    out = torch.empty(*shape, dtype=f32, device=device)
+    check(lib.dn_randn(_p(out), out.numel(), int(seed), int(offset), _stream()), "dn_randn")
+    return out
+
+
 def dropout_bits(bits, p: float, seed: int, offset: int):
     check(lib.dn_dropout_bits(_p(bits), bits.numel(), p, seed, offset, _stream()), "dn_dropout_bits")
     return bits

@@ -354,6 +354,11 @@ int dn_vae_reparam_bwd(const float* params, int32_t ldp, const float* eps, int32
                        int32_t ldz, const int32_t* lengths, int32_t B, int32_t T, int32_t z, float kl_scale, void* dparams,
                        int32_t ldd, void* stream);
 
+/* out[0..n) ~ N(0, 1) (Philox4x32-10 + Box-Muller; `offset` advances the counter so that successive calls with one seed do not
+ * repeat).  Replaces the reference's torch.randn draws of the posterior sample (distributions.py:37-41, drawn on the CPU and
+ * copied) and of q_sample (LM:1409) when the caller supplies no noise. */
+int dn_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
 /* Attention-dropout keep bits (LM:338): n_words uint32, each bit kept with probability 1-p (Philox4x32-10). */
 int dn_dropout_bits(uint32_t* bits, int64_t n_words, float p, uint64_t seed, uint64_t offset, void* stream);
 

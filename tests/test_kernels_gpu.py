@@ -189,6 +189,18 @@ def test_wavenet_gate_kernel():
     torch.testing.assert_close(y.float(), want, rtol=1e-2, atol=1e-2)
 
 
+def test_randn_kernel_is_standard_normal_and_reproducible():
+    a = ops.randn((1000, 1003), DEV, 7, 0)
+    b = ops.randn((1000, 1003), DEV, 7, 0)
+    c = ops.randn((1000, 1003), DEV, 8, 0)
+    d = ops.randn((1000, 1003), DEV, 7, 1)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1.0) < 5e-3
+    assert abs(float((a ** 3).mean())) < 2e-2 and abs(float((a ** 4).mean()) - 3.0) < 5e-2      # skewness 0, kurtosis 3
+    assert abs(float((a[:, :-1] * a[:, 1:]).mean())) < 5e-3                                       # no neighbour correlation
+    assert float(a.abs().max()) < 7.0 and bool(torch.isfinite(a).all())
+
+
 def test_time_table_kernels():
     w = rnd(256, seed=18)
     steps = torch.arange(200, dtype=torch.int32, device=DEV)

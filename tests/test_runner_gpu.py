@@ -56,9 +56,12 @@ def test_runner_end_to_end_against_oracle(tmp_path):
     res, dev_units, feat_dev = runner.normalize_batch([feats[items[i].audio_id] for i in idx],
                                                       [units_full[items[i].audio_id] for i in idx], return_units=True)
     B, T = len(idx), max(items[i].reduce_tgt_n_frames for i in idx)
+    # the engine draws its noise with the library's Philox kernel, seeded from torch's CPU generator: replay both draws
+    from diffnorm_b200 import ops
     torch.manual_seed(99)
-    eps_vae = torch.randn(B, 16, T, device="cuda").cpu()
-    eps_q = torch.randn(B, T, 16, device="cuda").cpu()
+    eps_vae = ops.randn((B, 16, T), "cuda", eng._noise_seed(), 0).cpu()
+    eps_q = ops.randn((B, T, 16), "cuda", eng._noise_seed(), 0).cpu()
+    assert abs(float(eps_q.mean())) < 0.05 and abs(float(eps_q.std()) - 1.0) < 0.05
     # oracle pre-processing: reduce_token(full) -> index_to_keep -> gather -> pad (diff_norm_synthesis.py:150-169)
     lens = torch.tensor([items[i].reduce_tgt_n_frames for i in idx])
     ofeat = torch.zeros(B, T, 768)
