@@ -263,6 +263,15 @@ int launch_attention_tc(const void* qkv, void* out, const int32_t* lengths, int 
 int launch_attention_tc96(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st, float* lse2,
                           const uint32_t* keep, float keep_scale, bool train, bool f16, int out_lo_col);
 
+int launch_attention_tcp(const void* qkv, void* out, const int32_t* lengths, int B, int T, int H, cudaStream_t st, bool f16);
+
+// DN_ATTN_PERSIST=1 selects the persistent kernel of attention_tcp.cu (measured slower: 244 vs 198 us per layer, its softmax
+// role spills inside the key-block loop at the 96-register cap of 2 CTAs / SM; kept as a tested experiment)
+static bool use_persistent_attention() {
+    const char* e = getenv("DN_ATTN_PERSIST");
+    return e && e[0] == '1';
+}
+
 // DN_ATTN_IMPL=mma selects the mma.sync kernels (bring-up / A-B reference of the tcgen05 kernels)
 static bool use_mma_attention() {
     const char* e = getenv("DN_ATTN_IMPL");
@@ -284,8 +293,10 @@ extern "C" int dn_attention(const void* qkv, void* out, const int32_t* lengths, 
     if (dh == 64) {
         // tcgen05/TMEM kernel (attention_tc.cu)
         const bool use_mma = dn::use_mma_attention();
-        if (!use_mma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+        if (!use_mma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+            if (dn::use_persistent_attention()) return dn::launch_attention_tcp(qkv, out, lengths, B, T, H, st, fmt == DN_FMT_F16);
             return dn::launch_attention_tc(qkv, out, lengths, B, T, H, st, nullptr, nullptr, 1.f, false, fmt == DN_FMT_F16);
+        }
         if (fmt == DN_FMT_F16) return DN_EINVAL;   // the mma.sync dh-64 kernel is the bf16 A/B reference only
         return dn::launch_attention<64>(qkv, out, lengths, B, T, H, st);
     }

@@ -232,19 +232,22 @@ def test_attention(dh, T, lens):
 
 
 def test_attention_tcgen05_matches_mma_kernel():
-    """dh = 64 runs on the tcgen05/TMEM kernel; DN_ATTN_IMPL=mma selects the mma.sync kernel: both must agree."""
-    B, T, H, dh = 3, 700, 8, 64
+    """dh = 64 runs on the tcgen05/TMEM kernel; DN_ATTN_IMPL=mma selects the mma.sync kernel, DN_ATTN_PERSIST=1 the persistent
+    form of the tcgen05 kernel (attention_tcp.cu; lengths include an empty utterance and a single key): all must agree."""
+    B, T, H, dh = 4, 700, 8, 64
     qkv = rnd(B, T, 3 * H * dh, seed=23, scale=1.5).bfloat16()
-    lengths = torch.tensor([700, 129, 1], dtype=torch.int32, device=DEV)
+    lengths = torch.tensor([700, 129, 1, 0], dtype=torch.int32, device=DEV)
     outs = []
-    for impl in ("mma", "tc"):
-        os.environ["DN_ATTN_IMPL"] = impl
+    for impl, persist in (("mma", "0"), ("tc", "0"), ("tc", "1")):
+        os.environ["DN_ATTN_IMPL"], os.environ["DN_ATTN_PERSIST"] = impl, persist
         out = torch.full((B, T, H * dh), 9.0, dtype=torch.bfloat16, device=DEV)
         ops.attention(qkv, out, lengths, B, T, H, dh)
         torch.cuda.synchronize()
         outs.append(out.float())
-    os.environ.pop("DN_ATTN_IMPL")
+    os.environ.pop("DN_ATTN_IMPL"), os.environ.pop("DN_ATTN_PERSIST")
     torch.testing.assert_close(outs[1], outs[0], rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(outs[2], outs[1], rtol=1e-2, atol=1e-2)     # same arithmetic up to the lazy-rescale decisions
+    assert (outs[2][3] == 0).all() and (outs[1][3] == 0).all()
 
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
