@@ -49,7 +49,7 @@ class GemmDesc(C.Structure):
         ("out", vp), ("ldo", i32), ("out_batch_stride", i64), ("g_out_col", i32),
         ("pe", vp), ("lengths", vp),
         ("a_fmt", i32), ("w_fmt", i32), ("out_fmt", i32), ("out_lo_col", i32),
-        ("coef", vp), ("aux", vp), ("aux_ld", i32), ("aux_lo_col", i32), ("n_classes", i32),
+        ("coef", vp), ("aux", vp), ("aux_ld", i32), ("aux_lo_col", i32), ("n_classes", i32), ("row_chunk", i32),
     ]
 
 

@@ -36,17 +36,45 @@ constexpr int GEMM_SMEM = 4 * (A_BYTES + B_BYTES) + BAR_BYTES + 2 * UNIT_BYTES +
 
 struct TileCoord {
     int g, b, t0, n;
+    int chunk0;    // packed rows: first row chunk of this CTA's 128 rows
+    bool contig;   // the 128 rows lie inside one utterance: one box at (b, t0) moves them
 };
+// M tiling of a launch.  Plain: per_t tiles per utterance, a tile never leaves its utterance.  Packed rows (row_chunk = ch):
+// per_t chunks per utterance, tiles take bm / ch consecutive chunks of the batch's chunk sequence.
+struct Tiling {
+    int m_tiles, per_t, ch;
+};
+__host__ __device__ __forceinline__ Tiling make_tiling(const dn_gemm_desc& p, int bm) {
+    Tiling g;
+    g.ch = p.row_chunk;
+    if (g.ch) {
+        g.per_t = (p.T + g.ch - 1) / g.ch;
+        g.m_tiles = (int)(((long long)p.B * g.per_t * g.ch + bm - 1) / bm);
+    } else {
+        g.per_t = (p.T + bm - 1) / bm;
+        g.m_tiles = p.B * g.per_t;
+    }
+    return g;
+}
 // bm = rows per tile (128, or 256 for a CTA pair); row_off = this CTA's offset inside the tile
-__device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile, int tiles_t, int bm = BM, int row_off = 0) {
+__device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile, const Tiling& tg, int bm = BM, int row_off = 0) {
     TileCoord c;
     c.n = tile % p.n_tiles;
     int r = tile / p.n_tiles;
-    int m_tiles = p.B * tiles_t;
-    int m = r % m_tiles;
-    c.g = r / m_tiles;
-    c.b = m / tiles_t;
-    c.t0 = (m % tiles_t) * bm + row_off;
+    int m = r % tg.m_tiles;
+    c.g = r / tg.m_tiles;
+    if (tg.ch) {
+        c.chunk0 = (m * bm + row_off) / tg.ch;
+        c.b = c.chunk0 / tg.per_t;           // may be >= B for the tail of the last tile: loads zero-fill, stores are clipped
+        const int r0 = c.chunk0 - c.b * tg.per_t;
+        c.t0 = r0 * tg.ch;
+        c.contig = r0 + BM / tg.ch <= tg.per_t;
+    } else {
+        c.b = m / tg.per_t;
+        c.t0 = (m % tg.per_t) * bm + row_off;
+        c.chunk0 = 0;
+        c.contig = true;
+    }
     return c;
 }
 
@@ -66,7 +94,8 @@ template <int EPI, int CTAS, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmW128, const __grid_constant__ CUtensorMap tmW64,
-               const __grid_constant__ CUtensorMap tmOut, const dn_gemm_desc p) {
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAC,
+               const __grid_constant__ CUtensorMap tmOutC, const dn_gemm_desc p) {
     constexpr int STAGES = Ring<CTAS>::STAGES;
     constexpr int STAGE_BYTES = Ring<CTAS>::STAGE_BYTES;
     static_assert(STAGES * STAGE_BYTES == 4 * (A_BYTES + B_BYTES), "both ring forms use the same 192 KB");
@@ -86,8 +115,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = rank == 0;
     constexpr int TBM = BM * CTAS;                 // rows per tile
     const int row_off = (int)rank * BM;
-    const int tiles_t = (p.T + TBM - 1) / TBM;
-    const int total = p.groups * p.B * tiles_t * p.n_tiles;
+    const Tiling tg = make_tiling(p, TBM);
+    const int total = p.groups * tg.m_tiles * p.n_tiles;
+    const int nbox = tg.ch ? BM / tg.ch : 1;       // boxes per A tile / output unit of a tile that straddles utterances
     const int rows_pg = p.groups > 1 ? p.g_w_row : p.w_rows;
     const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
@@ -97,6 +127,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmW128);
         tma_prefetch_desc(&tmW64);
         tma_prefetch_desc(&tmOut);
+        if (tg.ch) {
+            tma_prefetch_desc(&tmAC);
+            tma_prefetch_desc(&tmOutC);
+        }
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
@@ -123,39 +157,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();       // everything above touched only this CTA's smem / TMEM; inputs are read from here on
 
     if (warp == 0) {
-        if (lane == 0) {
+        // lane 0 produces; with packed rows the other lanes stay in the loop to issue one chunk box each for the tiles
+        // that straddle an utterance boundary
+        if (lane == 0 || tg.ch) {
             // ---------------------------------------------------------------- TMA producer
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < total; tile += tile_step) {
-                TileCoord c = decode_tile(p, tile, tiles_t, TBM, row_off);
+                TileCoord c = decode_tile(p, tile, tg, TBM, row_off);
                 const int d = p.dilation << (p.dilation_shl_group ? c.g : 0);
                 int n_full = rows_pg - c.n * WT;
                 n_full = n_full > WT ? WT : n_full;
+                const bool boxes = !c.contig;          // warp-uniform
+                int lb = 0, lt0 = 0;                   // this lane's chunk of a straddling tile
+                if (boxes && lane < nbox) {
+                    const int chn = c.chunk0 + lane;
+                    lb = chn / tg.per_t;
+                    lt0 = (chn - lb * tg.per_t) * tg.ch;
+                }
                 for (int s = 0; s < p.num_segs; ++s) {
                     const dn_gemm_seg sg = p.seg[s];
                     const bool half_w = sg.n_mma == 128;
                     const int nrows = sg.n_mma ? sg.n_mma : n_full;   // W rows this segment multiplies
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * STAGE_BYTES;
                         uint8_t* sb = sa + A_BYTES;
-                        if (CTAS == 1) {
-                            mbar_expect_tx(&full[stage], A_BYTES + (half_w ? B_BYTES / 2 : B_BYTES));
-                            tma_load_3d(&tmA, &full[stage], sa, sg.a_col0 + c.g * p.g_a_col + kb * BK,
-                                        c.t0 - sg.shift_mul * d, c.b);
-                            tma_load_2d(half_w ? &tmW128 : &tmW, &full[stage], sb, sg.w_k0 + kb * BK,
-                                        c.g * p.g_w_row + c.n * WT);
-                        } else {
-                            // each CTA brings nrows / 2 W rows (box of 128 or 64 rows; rows past the half are not read)
-                            const int half = nrows >> 1;
-                            const bool box128 = half > 64;
-                            const uint32_t bytes = A_BYTES + (box128 ? 128 : 64) * BK * 2;
-                            if (leader) mbar_expect_tx(&full[stage], 2 * bytes);
-                            tma2_load_3d(&tmA, &full[stage], sa, sg.a_col0 + c.g * p.g_a_col + kb * BK,
-                                         c.t0 - sg.shift_mul * d, c.b);
-                            tma2_load_2d(box128 ? &tmW128 : &tmW64, &full[stage], sb, sg.w_k0 + kb * BK,
-                                         c.g * p.g_w_row + c.n * WT + (int)rank * half);
+                        const int acol = sg.a_col0 + c.g * p.g_a_col + kb * BK;
+                        if (lane == 0) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            if (CTAS == 1) {
+                                mbar_expect_tx(&full[stage], A_BYTES + (half_w ? B_BYTES / 2 : B_BYTES));
+                                if (!boxes) tma_load_3d(&tmA, &full[stage], sa, acol, c.t0 - sg.shift_mul * d, c.b);
+                                tma_load_2d(half_w ? &tmW128 : &tmW, &full[stage], sb, sg.w_k0 + kb * BK,
+                                            c.g * p.g_w_row + c.n * WT);
+                            } else {
+                                // each CTA brings nrows / 2 W rows (box of 128 or 64 rows; rows past the half are not read)
+                                const int half = nrows >> 1;
+                                const bool box128 = half > 64;
+                                const uint32_t bytes = A_BYTES + (box128 ? 128 : 64) * BK * 2;
+                                if (leader) mbar_expect_tx(&full[stage], 2 * bytes);
+                                if (!boxes) tma2_load_3d(&tmA, &full[stage], sa, acol, c.t0 - sg.shift_mul * d, c.b);
+                                tma2_load_2d(box128 ? &tmW128 : &tmW64, &full[stage], sb, sg.w_k0 + kb * BK,
+                                             c.g * p.g_w_row + c.n * WT + (int)rank * half);
+                            }
+                        }
+                        if (boxes) {
+                            __syncwarp();      // lane 0 has seen the slot empty
+                            if (lane < nbox) {
+                                uint8_t* dst = sa + lane * tg.ch * (BK * 2);
+                                if (CTAS == 1) tma_load_3d(&tmAC, &full[stage], dst, acol, lt0 - sg.shift_mul * d, lb);
+                                else tma2_load_3d(&tmAC, &full[stage], dst, acol, lt0 - sg.shift_mul * d, lb);
+                            }
                         }
                         if (++stage == STAGES) {
                             stage = 0;
@@ -173,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int as = 0;
             uint32_t aphase = 0;
             for (int tile = tile0; tile < total; tile += tile_step) {
-                TileCoord c = decode_tile(p, tile, tiles_t, TBM, row_off);
+                TileCoord c = decode_tile(p, tile, tg, TBM, row_off);
                 int n_full = rows_pg - c.n * WT;
                 n_full = n_full > WT ? WT : n_full;
                 mbar_wait(&tempty[as], aphase ^ 1);
@@ -227,8 +279,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = tile0; tile < total; tile += tile_step) {
-            TileCoord c = decode_tile(p, tile, tiles_t, TBM, row_off);
-            const int t = c.t0 + row;
+            TileCoord c = decode_tile(p, tile, tg, TBM, row_off);
+            // this thread's row: (utterance wb, frame t); a straddling tile maps every chunk on its own
+            int wb = c.b, t = c.t0 + row;
+            if (!c.contig) {
+                const int chn = c.chunk0 + row / tg.ch;
+                wb = chn / tg.per_t;
+                t = (chn - wb * tg.per_t) * tg.ch + row % tg.ch;
+            }
+            const bool row_ok = t < p.T && wb < p.B;
+            const int pb_ = wb < p.B ? wb : p.B - 1;     // utterance whose per-utterance parameters this row reads
+            // one TMA box per unit, or one per chunk when the tile straddles utterances (issuer thread only)
+            auto store_unit = [&](const uint8_t* src, int ocol, bool reduce) {
+                if (c.contig) {
+                    if (reduce) tma_reduce_add_3d(&tmOut, src, ocol, c.t0, c.b);
+                    else tma_store_3d(&tmOut, src, ocol, c.t0, c.b);
+                } else {
+                    for (int i = 0; i < nbox; ++i) {
+                        const int chn = c.chunk0 + i;
+                        const int bb = chn / tg.per_t, tt = (chn - bb * tg.per_t) * tg.ch;
+                        if (reduce) tma_reduce_add_3d(&tmOutC, src + i * tg.ch * 128, ocol, tt, bb);
+                        else tma_store_3d(&tmOutC, src + i * tg.ch * 128, ocol, tt, bb);
+                    }
+                }
+            };
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -242,14 +316,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const float* cf = p.coef + (long long)(p.t_idx ? p.t_idx[0] : 0) * 8;
                     const float c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3];
                     const float d0 = fmaxf(c0, 1e-10f), d1 = fmaxf(c1, 1e-10f);
-                    const long long r = (long long)c.b * p.T + (t < p.T ? t : 0);
+                    const long long r = row_ok ? (long long)wb * p.T + t : 0;
                     float* xr = reinterpret_cast<float*>(p.out) + r * p.ldo;
                     __nv_bfloat16* sr = reinterpret_cast<__nv_bfloat16*>(p.aux) + r * p.aux_ld;
                     for (int cc = 0; cc < p.n_out; cc += 16) {
                         float e[16];
                         tmem_ld16(taddr + cc, e);
                         tmem_ld_wait();
-                        if (t >= p.T) continue;
+                        if (!row_ok) continue;
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
@@ -297,17 +371,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (t < p.T) {
-                    float* o = reinterpret_cast<float*>(p.out) + ((long long)c.b * p.T + t) * p.ldo + (c.n * 2 + half) * 2;
+                if (row_ok) {
+                    float* o = reinterpret_cast<float*>(p.out) + ((long long)wb * p.T + t) * p.ldo + (c.n * 2 + half) * 2;
                     *reinterpret_cast<float2*>(o) = make_float2(bv, __int_as_float(bi));
                 }
             } else if constexpr (EPI == DN_EPI_BF16 || EPI == DN_EPI_F32 || EPI == DN_EPI_RESID) {
                 constexpr int UCOLS = (EPI == DN_EPI_BF16) ? 64 : 32;   // columns per 16 KB unit
                 const float* bias = p.bias ? p.bias + c.g * p.g_bias : nullptr;
                 long long pe_row = -1;
-                if (EPI == DN_EPI_F32 && p.pe && t < p.T) {
+                if (EPI == DN_EPI_F32 && p.pe && row_ok) {
                     int pos = t + 1;
-                    if (p.lengths && t >= p.lengths[c.b]) pos = 0;
+                    if (p.lengths && t >= p.lengths[wb]) pos = 0;
                     pe_row = (long long)pos * p.n_out;
                 }
                 constexpr int npass = (EPI == DN_EPI_BF16 && MODE == 1) ? 2 : 1;   // split output: hi pass, then lo = v - hi
@@ -360,17 +434,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async_smem();
                     named_bar_sync(bar_id, 128);
                     if (issuer) {
-                        if constexpr (EPI == DN_EPI_RESID)
-                            tma_reduce_add_3d(&tmOut, stage_buf, ocol0 + col, c.t0, c.b);
-                        else
-                            tma_store_3d(&tmOut, stage_buf, ocol0 + col + pass * p.out_lo_col, c.t0, c.b);
+                        store_unit(stage_buf, ocol0 + col + pass * p.out_lo_col, EPI == DN_EPI_RESID);
                         bulk_commit();
                     }
                     }
                 }
             } else {
                 // GEGLU / WN_GATE: two 128-column accumulator halves -> 128 bf16 output columns per tile = 2 units
-                const float* gbr = (EPI == DN_EPI_WN_GATE) ? gb_row(p, c.b, c.g) : nullptr;
+                const float* gbr = (EPI == DN_EPI_WN_GATE) ? gb_row(p, pb_, c.g) : nullptr;
                 const int col = c.n * 128 + half * 64;  // logical output column of this warpgroup's unit
                 if (col < p.n_out) {
                     constexpr bool precise = MODE == 1;   // split output: full-precision erf / tanh / exp, then hi | lo
@@ -450,7 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async_smem();
                     named_bar_sync(bar_id, 128);
                     if (issuer) {
-                        tma_store_3d(&tmOut, stage_buf, ocol0 + col + pass * p.out_lo_col, c.t0, c.b);
+                        store_unit(stage_buf, ocol0 + col + pass * p.out_lo_col, false);
                         bulk_commit();
                     }
                     }
@@ -654,17 +725,16 @@ int num_sms() {
 
 template <int EPI, int CTAS, int MODE>
 static int launch_tc(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& w128, const CUtensorMap& w64,
-                     const CUtensorMap& o, const dn_gemm_desc& d, cudaStream_t st) {
+                     const CUtensorMap& o, const CUtensorMap& ac, const CUtensorMap& oc, const dn_gemm_desc& d, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         DN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_set = true;
     }
-    const int tiles_t = (d.T + BM * CTAS - 1) / (BM * CTAS);
-    const long long total = (long long)d.groups * d.B * tiles_t * d.n_tiles;
+    const long long total = (long long)d.groups * make_tiling(d, BM * CTAS).m_tiles * d.n_tiles;
     const int units = num_sms() / CTAS;   // CTAs (or CTA pairs) resident at once
     const int grid = (int)(total < units ? total : units) * CTAS;
-    DN_CUDA_OK(launch_ex(gemm_tc_kernel<EPI, CTAS, MODE>, grid, GEMM_THREADS, GEMM_SMEM, st, CTAS, a, w, w128, w64, o, d));
+    DN_CUDA_OK(launch_ex(gemm_tc_kernel<EPI, CTAS, MODE>, grid, GEMM_THREADS, GEMM_SMEM, st, CTAS, a, w, w128, w64, o, ac, oc, d));
     DN_LAUNCH_CHECK();
     count_launch();
     return 0;
@@ -693,6 +763,7 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
     if ((unsigned)d.a_fmt > 1u || (unsigned)d.w_fmt > 1u || (unsigned)d.out_fmt > 1u || d.out_lo_col < 0) return DN_EINVAL;
     if (d.out_lo_col && (f32out || d.n_out % 64 || d.out_lo_col % 8 || d.out_fmt != DN_FMT_BF16)) return DN_EINVAL;
     if (d.out_fmt == DN_FMT_F16 && f32out) return DN_EINVAL;
+    if (d.row_chunk != 0 && d.row_chunk != 8 && d.row_chunk != 16 && d.row_chunk != 32 && d.row_chunk != 64) return DN_EINVAL;
     if (d.a_fmt != d.w_fmt) return DN_EINVAL;   // kind::f16 MMAs take both operands in ONE 16-bit format (mixing faults)
     const int mode = d.out_lo_col ? 1 : (d.out_fmt == DN_FMT_F16 ? 2 : 0);
     for (int s = 0; s < d.num_segs; ++s)
@@ -710,13 +781,19 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
         return 0;
     }
 
-    CUtensorMap ma, mw, mw128, mw64;
+    CUtensorMap ma, mw, mw128, mw64, mac, moc;
     {
         cuuint64_t dims[3] = {(cuuint64_t)d.a_cols, (cuuint64_t)d.T, (cuuint64_t)d.B};
         cuuint64_t str[2] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.a_batch_stride * 2};
         cuuint32_t box[3] = {BK, BM, 1};
         int r = encode_bf16_map(&ma, d.A, 3, dims, str, box);
         if (r) return r;
+        mac = ma;
+        if (d.row_chunk) {   // packed rows: one box per row chunk for the tiles that straddle utterances
+            box[1] = (cuuint32_t)d.row_chunk;
+            r = encode_bf16_map(&mac, d.A, 3, dims, str, box);
+            if (r) return r;
+        }
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)d.ldw, (cuuint64_t)d.w_rows};
@@ -742,8 +819,14 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
         int r = encode_map(&mo, f32out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.out, 3,
                            dims, str, box);
         if (r) return r;
+        moc = mo;
+        if (d.row_chunk) {
+            box[1] = (cuuint32_t)d.row_chunk;
+            r = encode_map(&moc, f32out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d.out, 3, dims, str, box);
+            if (r) return r;
+        }
     }
-#define DN_LAUNCH_TC(EPI, CT, MD) launch_tc<EPI, CT, MD>(ma, mw, mw128, mw64, mo, d, st)
+#define DN_LAUNCH_TC(EPI, CT, MD) launch_tc<EPI, CT, MD>(ma, mw, mw128, mw64, mo, mac, moc, d, st)
 #define DN_BY_CTAS(EPI, MD) (impl == DN_GEMM_TCGEN05_2CTA ? DN_LAUNCH_TC(EPI, 2, MD) : DN_LAUNCH_TC(EPI, 1, MD))
     switch (d.epi) {
         case DN_EPI_BF16: return mode == 1 ? DN_BY_CTAS(DN_EPI_BF16, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_BF16, 2) : DN_BY_CTAS(DN_EPI_BF16, 0);

@@ -222,6 +222,9 @@ import os as _os
 
 _USE_2CTA = _os.environ.get("DN_GEMM_2CTA", "1") != "0"   # A/B switch for measurements; results are bit-identical
 _WASTE_AWARE = _os.environ.get("DN_GEMM_WASTE_AWARE", "1") != "0"
+# packed rows: M tiles of the per-utterance launches (shifted taps, per-utterance epilogue inputs) are filled with chunks of
+# this many frames across utterance boundaries (0 = every tile stays inside one utterance); results are bit-identical
+_ROW_CHUNK = int(_os.environ.get("DN_ROW_CHUNK", "32"))
 
 
 class GemmPlan:
@@ -257,7 +260,7 @@ class GemmPlan:
     def run(self, A, out, B: int, T: int, *, g_a_col: int = 0, g_out_col: int = 0, gb=None, gb_t_stride: int = 0,
             g_gb: int = 0, gb_half: int = 0, t_idx=None, t_idx_stride: int = 0, pe=None, lengths=None,
             epi: Optional[int] = None, impl: Optional[int] = None, a_cols: Optional[int] = None, out_split: bool = False,
-            out_f16: bool = False, ddim=None, argmax_classes: Optional[int] = None):
+            out_f16: bool = False, ddim=None, argmax_classes: Optional[int] = None, row_chunk: Optional[int] = None):
         """out_split: 16-bit output written as a split-precision pair (out is [.., 2 * width]: hi | lo).  out_f16: fp16 output."""
         epi = self.epi if epi is None else epi
         if ddim is not None:
@@ -274,13 +277,15 @@ class GemmPlan:
             # no frame shifts and no per-utterance epilogue inputs: treat the batch as one long utterance so M tiles
             # run across utterance boundaries (T = 1000 would otherwise waste 24 of every 1024 tile rows)
             B, T = 1, B * T
+        if row_chunk is None:
+            row_chunk = _ROW_CHUNK if (B > 1 and T % 256) else 0
         if impl is None:
             # CTA-pair form (tcgen05 cta_group::2, M = 256 tiles) whenever it still fills the machine: 74 pairs of SMs ...
             pair_tiles = self.groups * B * ((T + 255) // 256) * self.n_tiles
             impl = _lib.GEMM_TCGEN05_2CTA if (_USE_2CTA and pair_tiles >= 74) else _lib.GEMM_TCGEN05
             # ... unless its 256-row tiles, which cannot cross utterances when taps are shifted, pad a ragged T by more than
             # the pair form gains (~10 % per row): T = 600 is 3 x 256 = 768 rows as pairs but 5 x 128 = 640 rows single
-            if impl == _lib.GEMM_TCGEN05_2CTA and _WASTE_AWARE and (T + 127) // 128 * 128 * 1.10 < (T + 255) // 256 * 256:
+            if impl == _lib.GEMM_TCGEN05_2CTA and _WASTE_AWARE and not row_chunk and (T + 127) // 128 * 128 * 1.10 < (T + 255) // 256 * 256:
                 impl = _lib.GEMM_TCGEN05
         wdt = f16 if self.fmt == "f16" else bf16
         _chk(A, wdt, "A")     # one 16-bit format per MMA: fp16 plans take fp16 activations
@@ -313,6 +318,7 @@ class GemmPlan:
         d.out, d.ldo, d.out_batch_stride, d.g_out_col = _p(out), ldo, T * ldo, g_out_col
         d.pe, d.lengths = _p(pe), _p(lengths)
         d.n_classes = 0 if argmax_classes is None else int(argmax_classes)
+        d.row_chunk = int(row_chunk)
         if ddim is not None:
             d.coef, d.aux, d.aux_ld, d.aux_lo_col = _p(coef), _p(aux), aux.shape[-1], aux_lo
             if out.shape[-1] != self.n_out:

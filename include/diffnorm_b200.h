@@ -248,6 +248,12 @@ typedef struct {
     void* aux;                  /* bf16 staging copy of x: hi in columns [0, n_out), lo in [aux_lo_col, aux_lo_col + n_out) */
     int32_t aux_ld, aux_lo_col;
     int32_t n_classes;          /* DN_EPI_ARGMAX: classes that take part in the argmax (<= n_out) */
+    /* Packed rows (ragged batches): 0 = every M tile lies inside one utterance (a T that is not a multiple of the tile
+     * height pads each utterance up to it); 8 | 16 | 32 | 64 = M tiles are filled with row chunks of that many frames taken
+     * across utterance boundaries — a tile that straddles a boundary loads / stores one TMA box per chunk, each with its own
+     * (utterance, frame) origin so shifted taps still zero-fill at t < 0 — and only the last chunk of an utterance pads.
+     * Results are bit-identical to row_chunk = 0. */
+    int32_t row_chunk;
 } dn_gemm_desc;
 
 /* out = epilogue(A (*) W^T): bf16 operands, fp32 accumulation in TMEM (tcgen05.mma fed by TMA).

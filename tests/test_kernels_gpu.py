@@ -323,6 +323,13 @@ def _gemm_case(plan, A, out_shape, out_dtype, B, T, **kw):
     plan.run(A, out2, B, T, impl=_lib.GEMM_TCGEN05_2CTA, **kw)
     torch.cuda.synchronize()
     assert torch.equal(out2.float(), outs[1]), "cta_group::2 kernel differs from the single-CTA kernel"
+    # packed rows (M tiles filled with row chunks across utterance boundaries) are only a different tiling: bit-identical
+    for rc in (8, 16, 32, 64):
+        for impl in (_lib.GEMM_TCGEN05, _lib.GEMM_TCGEN05_2CTA):
+            torch.manual_seed(0)
+            out3 = torch.randn(out_shape, device=DEV).to(out_dtype).contiguous()
+            plan.run(A, out3, B, T, impl=impl, row_chunk=rc, **kw)
+            assert torch.equal(out3.float(), outs[1]), f"row_chunk {rc} impl {impl} differs from the per-utterance tiling"
     return outs
 
 
@@ -464,6 +471,29 @@ def test_gemm_argmax_epilogue_matches_torch_argmax():
         got = ops.argmax_combine(parts, 4)
         assert torch.equal(got, want), impl
     assert torch.equal(ops.argmax_units(logits, V, 4), want)
+
+
+@pytest.mark.parametrize("B,T", [(5, 600), (7, 200), (3, 1000), (9, 136)])
+def test_gemm_packed_rows_ragged_batches(B, T):
+    """The config-4 shapes: a dilated causal conv (shifts up to 2 x 128 frames: taps must zero-fill at every utterance start,
+    not read the previous utterance's tail), a WaveNet-style conditioned level and the split-precision form, over tiles that
+    straddle utterances, against the SIMT checker and the per-utterance tiling."""
+    Cin, N = 128, 272
+    x = rnd(B, T, Cin, seed=110).bfloat16()
+    W, b = rnd(N, Cin, 3, seed=111, scale=0.1), rnd(N, seed=112)
+    for dil in (1, 16, 128):
+        plan = packing.pack_conv3(W.cpu(), b.cpu(), dilation=dil).to(DEV)
+        chk, tc = _gemm_case(plan, x.view(B * T, Cin), (B * T, N), torch.bfloat16, B, T)
+        want = O.causal_conv1d(x.float().transpose(1, 2), W.bfloat16().float(), b, dil).transpose(1, 2).reshape(B * T, N)
+        torch.testing.assert_close(tc, want, rtol=2e-2, atol=3e-2)
+        torch.testing.assert_close(tc, chk, rtol=1e-2, atol=1e-2)
+    # fp32 output with positions + lengths (per-row utterance parameters) and the in-place residual add (TMA reduce per chunk)
+    lengths = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(5)).to(torch.int32).to(DEV)
+    pe = O.sinusoid_table(T + 1, 512).to(DEV).contiguous()
+    Wl = rnd(512, Cin, seed=113, scale=0.1)
+    plan = packing.pack_linear(Wl.cpu(), None, epi=_lib.EPI_F32).to(DEV)
+    chk, tc = _gemm_case(plan, x.view(B * T, Cin), (B * T, 512), torch.float32, B, T, pe=pe, lengths=lengths)
+    torch.testing.assert_close(tc, chk, rtol=1e-3, atol=1e-3)
 
 
 def test_gemm_persistent_many_tiles():
