@@ -540,8 +540,8 @@ def run_train(args):
         variants = [("fp32", True, 0), ("fp32", False, 0), ("fp32", True, 8), ("fp32", True, 16), ("fp32", True, 32),
                     ("bf16", True, 0), ("bf16", True, 16), ("bf16", False, 0)]
     for comm, overlap, reserve in variants:
-        red = GradAllReducer(comm_dtype=torch.bfloat16 if comm == "bf16" else torch.float32, overlap=overlap,
-                             sm_reserve=reserve if world > 1 else 0)
+        reserve = reserve if world > 1 else 0      # one GPU has nothing to exchange: no SMs are set aside
+        red = GradAllReducer(comm_dtype=torch.bfloat16 if comm == "bf16" else torch.float32, overlap=overlap, sm_reserve=reserve)
 
         def step(a=audio, u=units):
             out, _ = tr.step(a, u, lens, grad_hook=red.hook)
