@@ -108,6 +108,7 @@ _SIGS = {
     "dn_linear_f32": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "dn_time_features": [vp, vp, i32, i32, vp, vp],
     "dn_gemm": [C.POINTER(GemmDesc), i32, vp],
+    "dn_gemm_tile_rows": [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],   # host-only: the kernel's M tiling
     "dn_attention": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     # unit vocoder (the step after the pass)
     "dn_voc_conv1d": [vp, i32, i32, vp, vp, i32, i32, i32, i32, f32, i32, vp, f32, i32, vp, vp],

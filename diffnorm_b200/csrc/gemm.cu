@@ -57,7 +57,7 @@ __host__ __device__ __forceinline__ Tiling make_tiling(const dn_gemm_desc& p, in
     return g;
 }
 // bm = rows per tile (128, or 256 for a CTA pair); row_off = this CTA's offset inside the tile
-__device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile, const Tiling& tg, int bm = BM, int row_off = 0) {
+__host__ __device__ __forceinline__ TileCoord decode_tile(const dn_gemm_desc& p, int tile, const Tiling& tg, int bm = BM, int row_off = 0) {
     TileCoord c;
     c.n = tile % p.n_tiles;
     int r = tile / p.n_tiles;
@@ -838,6 +838,33 @@ extern "C" int dn_gemm(const dn_gemm_desc* dp, int32_t impl, void* stream) {
         case DN_EPI_WN_GATE: return mode == 1 ? DN_BY_CTAS(DN_EPI_WN_GATE, 1) : mode == 2 ? DN_BY_CTAS(DN_EPI_WN_GATE, 2) : DN_BY_CTAS(DN_EPI_WN_GATE, 0);
         default: return DN_EINVAL;
     }
+}
+
+// Host-side statement of the kernel's M tiling (the same make_tiling / decode_tile the device code runs): which (utterance,
+// frame) each of the 128 accumulator rows of CTA `cta_rank` of M tile `m_tile` holds.  Rows past T or past the batch are
+// reported as they are computed (b may equal B, t may be >= T): the TMA loads zero-fill them and the stores are clipped.
+extern "C" int dn_gemm_tile_rows(int32_t B, int32_t T, int32_t row_chunk, int32_t ctas, int32_t m_tile, int32_t cta_rank,
+                                 int32_t* m_tiles, int32_t* b_out, int32_t* t_out, int32_t* boxes) {
+    if (B <= 0 || T <= 0 || (ctas != 1 && ctas != 2) || cta_rank < 0 || cta_rank >= ctas) return DN_EINVAL;
+    if (row_chunk != 0 && row_chunk != 8 && row_chunk != 16 && row_chunk != 32 && row_chunk != 64) return DN_EINVAL;
+    dn_gemm_desc d{};
+    d.B = B; d.T = T; d.row_chunk = row_chunk; d.n_tiles = 1; d.groups = 1;
+    const Tiling tg = make_tiling(d, BM * ctas);
+    if (m_tiles) *m_tiles = tg.m_tiles;
+    if (m_tile < 0 || m_tile >= tg.m_tiles) return (b_out || t_out) ? DN_EINVAL : 0;
+    const TileCoord c = decode_tile(d, m_tile, tg, BM * ctas, cta_rank * BM);
+    if (boxes) *boxes = c.contig ? 1 : BM / tg.ch;
+    for (int row = 0; row < BM; ++row) {
+        int wb = c.b, t = c.t0 + row;
+        if (!c.contig) {
+            const int chn = c.chunk0 + row / tg.ch;
+            wb = chn / tg.per_t;
+            t = (chn - wb * tg.per_t) * tg.ch + row % tg.ch;
+        }
+        if (b_out) b_out[row] = wb;
+        if (t_out) t_out[row] = t;
+    }
+    return 0;
 }
 
 extern "C" int dn_abi_version(void) { return 2; }

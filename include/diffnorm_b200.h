@@ -264,6 +264,13 @@ typedef struct {
  * each CTA stages half of the W tile, the leader issues the MMAs for both SMs); results are bit-identical. */
 int dn_gemm(const dn_gemm_desc* d, int32_t impl, void* stream);
 
+/* Host-only (no CUDA call): the M tiling dn_gemm's kernel uses for a [B, T] launch — m_tiles = M tiles per group and N tile, and
+ * for CTA `cta_rank` (< ctas, 1 or 2) of M tile `m_tile` the (utterance, frame) of each of its 128 accumulator rows
+ * (b_out / t_out, 128 entries each, may be null) and the number of TMA boxes its A tile is loaded with (1, or 128 / row_chunk when
+ * the tile straddles utterances).  Rows with b == B or t >= T are padding.  Lets the packed-rows map be checked without a GPU. */
+int dn_gemm_tile_rows(int32_t B, int32_t T, int32_t row_chunk, int32_t ctas, int32_t m_tile, int32_t cta_rank,
+                      int32_t* m_tiles, int32_t* b_out, int32_t* t_out, int32_t* boxes);
+
 /* ---- attention ------------------------------------------------------------------------------------------ */
 
 /* Non-causal multi-head attention with key-padding mask (LM:299-343, :945-949), flash-style (no N x N matrix).
