@@ -339,15 +339,29 @@ def run_ours(args):
         peaks = load_peaks()
         calls = start - 1
         fpf = flops_per_frame(z, T, calls)
-        # ---- dominant kernel: the tcgen05 GEMM on the FFN causal conv (64 % of transformer MACs); timed live with
-        # one pair of CUDA events around a train of its launches after the timed region
-        # (the 12 layers' launches of this kernel, each on the operands the pass left in the workspace, enqueued back to back so
-        # that no host gap sits between the events; 2 untimed + 5 timed rounds right after the timed passes = under the same
-        # power-capped clocks; at N > 1 this is rank 0's GPU while the other ranks wait, so the N = 1 line is the reference figure)
+        # ---- dominant kernel: the tcgen05 GEMM on the FFN causal conv (64 % of transformer MACs), timed live right after the
+        # timed region.  (a) in the pass: three eager denoiser calls enqueued back to back (the host runs ~10x ahead of the
+        # GPU), CUDA events around every transformer GEMM launch; the 12 conv launches of the LAST call — kernels before and
+        # after them exactly as in the pass, clocks settled by the two calls before — give `achieved`.  (b) alone: a train of
+        # 60 launches of the kernel after 24 untimed ones (the hottest kernel of the pass back to back: the power cap takes the
+        # clock below the pass's average), reported beside it.  At N > 1 this is rank 0's GPU while the other ranks wait, so
+        # the N = 1 line is the reference figure.
+        t_idx = torch.tensor([start - 1], dtype=torch.int32, device=dev)
+        xb = eng.buf("s.xb", B * T, eng.xw)
+
+        def three_calls():
+            for _ in range(3):
+                eng.denoise(xb, lens, B, T, t_idx)
+
+        times = eng.profile_launches("model.transformer.layers", three_calls)
+        times = times[-(len(times) // 3):]                                   # the last call's launches
+        all_gemm_ms = float(np.sum([m for _, m in times]))
+        conv = [m for n_, m in times if n_.endswith("ff.conv")]
+        assert len(conv) == len(eng.d_layers), [n_ for n_, _ in times][:8]
         m1 = eng.buf("d.tf.m1", B * T, eng.d_ip, eng.adt)
         m2 = eng.buf("d.tf.m2", B * T, eng.d_ip, eng.adt)
         rounds = 5
-        for _ in range(2):                       # 24 launches to settle back into the pass's power-capped clocks
+        for _ in range(2):
             for L in eng.d_layers:
                 L.ffc.run(m1, m2, B, T)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -357,11 +371,7 @@ def run_ours(args):
                 L.ffc.run(m1, m2, B, T)
         c1.record()
         torch.cuda.synchronize()
-        t_idx = torch.tensor([start - 1], dtype=torch.int32, device=dev)
-        xb = eng.buf("s.xb", B * T, eng.xw)
-        times = eng.profile_launches("model.transformer.layers", lambda: eng.denoise(xb, lens, B, T, t_idx))
-        all_gemm_ms = float(np.sum([m for _, m in times]))
-        conv = [c0.elapsed_time(c1) / (rounds * len(eng.d_layers))] * (rounds * len(eng.d_layers))
+        train_ms = c0.elapsed_time(c1) / (rounds * len(eng.d_layers))
         inner = 1365
         conv_flops = 2.0 * B * T * inner * inner * 3
         conv_ms = float(np.mean(conv))
@@ -371,8 +381,9 @@ def run_ours(args):
                     "frac": ach / peaks["sustained"], "traffic": NCU_CONV_DRAM_BYTES if (B, T, z) == (64, 1000, 16) else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one ncu --set "
                                       "full capture (profiles/r02_r2n_gemm_layer_ncu_summary.txt: 192.3 + 156.0 MB); algorithmic A + out = 360 MB",
-                    "peak_source": peaks["source"] + " sustained bf16 (60 launches of the kernel, the 12 layers' weights x 5 rounds after 24 untimed ones, "
-                                   "enqueued back to back right after the timed passes, i.e. under the same power-capped clocks)",
+                    "peak_source": peaks["source"] + " sustained bf16; achieved = the kernel's 12 launches inside the third of three eager "
+                                   "denoiser calls enqueued back to back right after the timed passes (CUDA events around each launch)",
+                    "launch_ms_alone_train_of_60": train_ms, "frac_alone_train_of_60": conv_flops / (train_ms * 1e-3) / 1e12 / peaks["sustained"],
                     "frac_of_burst_peak": ach / peaks["burst"], "burst_peak": peaks["burst"],
                     "launch_ms": conv_ms, "launches_timed": len(conv),
                     "transformer_gemm_ms_per_call": all_gemm_ms,
