@@ -36,6 +36,30 @@ def load_model(ckpt_path: str, device: str):
     return model.to(device).eval(), task
 
 
+def write_shards(lines, output_dir: str, split: str, rank: int, world: int) -> str:
+    """The only cross-rank step of the normalization path, and it is host-side: every rank writes its own restartable shard
+    `{split}.rank{r}.tsv` ({item index: TSV line} of the utterances plan_batches gave it); rank 0 gathers the dictionaries (gloo,
+    objects — no tensor ever crosses ranks) and writes `{split}.tsv` in the original utterance order, i.e. the file a single
+    process writes (diff_norm_synthesis.py:218-222).  Returns the path this rank wrote last."""
+    path = os.path.join(output_dir, f"{split}.tsv" if world == 1 else f"{split}.rank{rank}.tsv")
+    write_tsv(path, [lines[i] for i in sorted(lines)])
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+        gathered = [None] * world
+        dist.all_gather_object(gathered, lines)
+        if rank == 0:
+            merged = {}
+            for g in gathered:
+                if set(g) & set(merged):
+                    raise RuntimeError("two ranks normalized the same utterance: the sharding plan is not a partition")
+                merged.update(g)
+            path = os.path.join(output_dir, f"{split}.tsv")
+            write_tsv(path, [merged[i] for i in sorted(merged)])
+    return path
+
+
 def main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -52,19 +76,7 @@ def main(args):
         items, unfound = prepare_data(args.reduce_tsv_dir, args.orig_tsv_dir, args.feature_dir, split)
         print("Unfound: ", unfound)
         lines = runner.run_items(items, rank=rank, world_size=world)
-        shard = os.path.join(args.output_dir, f"{split}.tsv" if world == 1 else f"{split}.rank{rank}.tsv")
-        write_tsv(shard, [lines[i] for i in sorted(lines)])
-        if world > 1:  # every rank writes its own restartable shard; rank 0 stitches them in original order
-            import torch.distributed as dist
-            if not dist.is_initialized():
-                dist.init_process_group("gloo")
-            gathered = [None] * world
-            dist.all_gather_object(gathered, lines)
-            if rank == 0:
-                merged = {}
-                for g in gathered:
-                    merged.update(g)
-                write_tsv(os.path.join(args.output_dir, f"{split}.tsv"), [merged[i] for i in sorted(merged)])
+        write_shards(lines, args.output_dir, split, rank, world)
         print("Finished processing ", split)
 
 

@@ -51,3 +51,46 @@ def test_grad_allreduce_single_process_is_identity():
         red.hook(k, v)
     out = red.finish()
     assert torch.equal(out["a"], g["a"]) and torch.equal(out["b"], g["b"])
+
+
+# ---- the normalization path at N > 1: sharded by utterance, no data-path collective; the one cross-rank step is the host-side
+# ---- stitching of the per-rank TSV shards (normalize_cli.write_shards)
+def _norm_worker(rank, world, port, out_dir, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from diffnorm_b200.data import plan_batches
+    from diffnorm_b200.normalize_cli import write_shards
+    rng = np.random.default_rng(7)          # every rank derives the same plan from the same lengths: nothing is exchanged
+    lengths = np.clip(np.rint(np.exp(rng.normal(np.log(600.0), 0.5, size=301))), 200, 2000).astype(np.int64)
+    plan = plan_batches(lengths, 16000, world_size=world)
+    mine = np.concatenate(plan[rank])
+    lines = {int(i): f"utt{int(i)}\t{int(lengths[i])}" for i in mine}      # stands for this rank's normalized TSV lines
+    path = write_shards(lines, out_dir, "train", rank, world)
+    loads = [int(sum(len(b) * int(lengths[b].max()) for b in plan[r])) for r in range(world)]
+    q.put((rank, len(mine), os.path.basename(path), loads))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_normalization_sharding_and_stitching_world2_gloo(tmp_path):
+    import numpy as np
+    world, port = 2, 29533
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_norm_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p_ in ps:
+        p_.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p_ in ps:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert sum(r[1] for r in res) == 301 and res[0][2] == "train.tsv" and res[1][2] == "train.rank1.tsv"
+    loads = res[0][3]
+    assert max(loads) <= 1.15 * min(loads)                      # LPT plan on ~13 batches per rank (its cost model also weighs T^2)
+    rng = np.random.default_rng(7)
+    lengths = np.clip(np.rint(np.exp(rng.normal(np.log(600.0), 0.5, size=301))), 200, 2000).astype(np.int64)
+    merged = open(os.path.join(str(tmp_path), "train.tsv")).read().splitlines()[1:]
+    assert merged == [f"utt{i}\t{int(lengths[i])}" for i in range(301)]     # = the file one process writes, original order
+    shards = [open(os.path.join(str(tmp_path), f"train.rank{r}.tsv")).read().splitlines()[1:] for r in range(world)]
+    assert sorted(shards[0] + shards[1]) == sorted(merged) and not set(shards[0]) & set(shards[1])
